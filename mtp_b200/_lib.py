@@ -1,0 +1,75 @@
+"""ctypes binding of libmtp_b200.so (the C ABI declared in include/mtp_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmtp_b200.so")
+
+c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+
+class MtpError(RuntimeError):
+    pass
+
+
+class Epilogue(ctypes.Structure):
+    """struct mtp_epilogue (include/mtp_b200.h)."""
+    _fields_ = [("mode", c_int), ("ldo", c_int), ("bias", c_void_p), ("out", c_void_p), ("out2", c_void_p),
+                ("aux", c_void_p), ("row_scale", c_void_p), ("rows_per_group", c_int), ("pos_rows", c_int),
+                ("accumulate", c_int), ("ps_h", c_int), ("ps_w", c_int), ("ps_cout", c_int)]
+
+
+EPI_BF16, EPI_BF16_GELU, EPI_F32_RESID, EPI_F32_POS, EPI_F32, EPI_BF16_DGELU, EPI_BF16_PIXSHUF = range(7)
+
+# name -> argtypes (restype is always int unless listed in _SPECIAL)
+_SIGNATURES = {
+    "mtp_gemm_bf16": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_int, c_void_p],
+    "mtp_layernorm_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],
+    "mtp_layernorm_bwd": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                          c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "mtp_scale_cast_bf16": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "mtp_colsum_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+    "mtp_cast_f32_bf16": [c_void_p, c_void_p, c_size_t, c_void_p],
+    "mtp_add_bf16_into_f32": [c_void_p, c_void_p, c_size_t, c_void_p],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises MtpError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MtpError(f"{LIB_PATH} not found: build it with `python -m mtp_b200.build` "
+                       "(there is no CPU or PyTorch fallback for the backbone kernels)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mtp_last_error.restype = ctypes.c_char_p
+    lib.mtp_last_error.argtypes = []
+    lib.mtp_version.restype = c_int
+    lib.mtp_num_sms.restype = c_int
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return ["mtp_last_error", "mtp_version", "mtp_num_sms"] + list(_SIGNATURES)
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise MtpError(f"{what} failed ({rc}): {load().mtp_last_error().decode()}")
+
+
+def call(name, *args):
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise MtpError(f"{name} failed ({rc}): {load().mtp_last_error().decode()}")

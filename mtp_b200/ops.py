@@ -1,0 +1,78 @@
+"""Thin torch-tensor wrappers over the C ABI (pointers + sizes + the current CUDA stream).  No autograd here."""
+import torch
+
+from . import _lib as L
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), f"{name}: need contiguous cuda {dtype}, got {t.dtype} {t.device} contiguous={t.is_contiguous()}"
+
+
+def gemm(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=None, out2=None, aux=None, row_scale=None,
+         rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None, ps=None, force_bn=0):
+    """acc[m,n] = sum_k A[m,k] B[n,k] with fused epilogue; see include/mtp_b200.h."""
+    ep = L.Epilogue()
+    ep.mode = mode
+    ep.ldo = int(ldo if ldo is not None else out.shape[-1])
+    ep.bias, ep.out, ep.out2, ep.aux, ep.row_scale = _p(bias), _p(out), _p(out2), _p(aux), _p(row_scale)
+    ep.rows_per_group, ep.pos_rows, ep.accumulate = int(rows_per_group), int(pos_rows), int(bool(accumulate))
+    if ps is not None:
+        ep.ps_h, ep.ps_w, ep.ps_cout = ps
+    lda = int(lda if lda is not None else A.shape[-1])
+    ldb = int(ldb if ldb is not None else B.shape[-1])
+    L.call("mtp_gemm_bf16", A.data_ptr(), lda, int(a_mn), B.data_ptr(), ldb, int(b_mn), int(M), int(N), int(K),
+           ep, int(force_bn), _stream())
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-6, gelu=False, save_stats=True):
+    rows, C = x.shape
+    y = torch.empty(rows, C, device=x.device, dtype=BF16)
+    mean = torch.empty(rows, device=x.device, dtype=F32) if save_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=F32) if save_stats else None
+    L.call("mtp_layernorm_fwd", x.data_ptr(), int(x.dtype == BF16), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+           _p(mean), _p(rstd), rows, C, float(eps), int(gelu), _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, beta, dres, dgamma, dbeta, gelu=False):
+    rows, C = x.shape
+    dx = torch.empty(rows, C, device=x.device, dtype=x.dtype)
+    L.call("mtp_layernorm_bwd", dy.data_ptr(), x.data_ptr(), int(x.dtype == BF16), mean.data_ptr(), rstd.data_ptr(),
+           gamma.data_ptr(), _p(beta), _p(dres), dx.data_ptr(), int(dx.dtype == BF16), dgamma.data_ptr(), dbeta.data_ptr(),
+           rows, C, int(gelu), _stream())
+    return dx
+
+
+def scale_cast_bf16(x, row_scale=None, rows_per_group=0, colsum=None):
+    rows, C = x.shape
+    out = torch.empty(rows, C, device=x.device, dtype=BF16)
+    L.call("mtp_scale_cast_bf16", x.data_ptr(), _p(row_scale), int(rows_per_group), out.data_ptr(), _p(colsum), rows, C, _stream())
+    return out
+
+
+def colsum_bf16(x, colsum, ld=None):
+    rows, C = x.shape
+    L.call("mtp_colsum_bf16", x.data_ptr(), int(ld if ld is not None else x.stride(0)), colsum.data_ptr(), rows, C, _stream())
+    return colsum
+
+
+def cast_f32_bf16(x):
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    L.call("mtp_cast_f32_bf16", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def add_bf16_into_f32(src, dst):
+    L.call("mtp_add_bf16_into_f32", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+    return dst

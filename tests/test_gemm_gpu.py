@@ -1,0 +1,122 @@
+"""tcgen05 GEMM vs fp32 torch on identical bf16-rounded inputs (all operand layouts, tile widths and epilogues)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def _ref(A, B, a_mn, b_mn):
+    a = A.float().t() if a_mn else A.float()
+    b = B.float().t() if b_mn else B.float()
+    return a @ b.t()
+
+
+def _tol(K):
+    return 2e-2 * math.sqrt(K / 64.0) * 0.05 + 1e-2
+
+
+@pytest.mark.parametrize("layout", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+def test_gemm_layouts_tiles(layout, bn):
+    from mtp_b200 import ops, _lib as L
+    a_mn, b_mn = layout
+    M, N, K = 392, 320, 456          # ragged in M, N (vs every BN) and K (not a multiple of 64)
+    A = _mk((K, M) if a_mn else (M, K), seed=1)
+    B = _mk((K, N) if b_mn else (N, K), seed=2)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    ops.gemm(A, B, M, N, K, out, a_mn=a_mn, b_mn=b_mn, mode=L.EPI_F32, force_bn=bn)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, a_mn, b_mn)
+    err = (out - ref).abs().max().item()
+    assert err < 1e-2 * math.sqrt(K), f"max err {err}"
+    assert (out - ref).norm().item() / ref.norm().item() < 1e-5      # fp32 accumulate of exact bf16 products
+
+
+@pytest.mark.parametrize("shape", [(1568, 3072, 1024), (1568, 1024, 4096), (6272, 2304, 768), (128, 64, 64), (1, 8, 8)])
+def test_gemm_model_shapes_bias_bf16(shape):
+    from mtp_b200 import ops, _lib as L
+    M, N, K = shape
+    A, B = _mk((M, K), seed=3), _mk((N, K), 0.05, seed=4)
+    bias = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, M, N, K, out, bias=bias)
+    ref = A.float() @ B.float().t() + bias
+    assert ((out.float() - ref).abs() <= 8e-3 * ref.abs() + 1e-2).all()
+
+
+def test_epilogue_gelu_and_dgelu():
+    from mtp_b200 import ops, _lib as L
+    M, N, K = 300, 512, 256
+    A, B = _mk((M, K), seed=5), _mk((N, K), 0.1, seed=6)
+    bias = torch.randn(N, device="cuda") * 0.1
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty_like(out)
+    ops.gemm(A, B, M, N, K, out, mode=L.EPI_BF16_GELU, bias=bias, out2=pre)
+    ref_pre = A.float() @ B.float().t() + bias
+    assert ((pre.float() - ref_pre).abs() <= 8e-3 * ref_pre.abs() + 1e-2).all()
+    ref = torch.nn.functional.gelu(ref_pre)
+    assert ((out.float() - ref).abs() <= 8e-3 * ref.abs() + 1e-2).all()
+    # dgelu: out = acc * gelu'(aux)
+    h = _mk((M, N), seed=7)
+    dg = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, M, N, K, dg, mode=L.EPI_BF16_DGELU, aux=h)
+    hf = h.float().requires_grad_(True)
+    torch.nn.functional.gelu(hf).sum().backward()
+    ref = (A.float() @ B.float().t()) * hf.grad
+    assert ((dg.float() - ref).abs() <= 1e-2 * ref.abs() + 2e-2).all()
+
+
+def test_epilogue_residual_pos_accumulate():
+    from mtp_b200 import ops, _lib as L
+    B_, ntok, N, K = 3, 100, 256, 128
+    M = B_ * ntok
+    A, W = _mk((M, K), seed=8), _mk((N, K), 0.1, seed=9)
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    keep = torch.tensor([0.0, 1.25, 1.0], device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(A, W, M, N, K, out, mode=L.EPI_F32_RESID, bias=bias, aux=resid, row_scale=keep, rows_per_group=ntok)
+    ref = resid + keep.repeat_interleave(ntok)[:, None] * (A.float() @ W.float().t() + bias)
+    assert (out - ref).abs().max().item() < 1e-3
+    # in-place on the residual stream
+    r2 = resid.clone()
+    ops.gemm(A, W, M, N, K, r2, mode=L.EPI_F32_RESID, bias=bias, aux=r2, row_scale=None)
+    assert (r2 - (resid + A.float() @ W.float().t() + bias)).abs().max().item() < 1e-3
+    pos = torch.randn(ntok, N, device="cuda")
+    ops.gemm(A, W, M, N, K, out, mode=L.EPI_F32_POS, bias=bias, aux=pos, pos_rows=ntok)
+    ref = A.float() @ W.float().t() + bias + pos.repeat(B_, 1)
+    assert (out - ref).abs().max().item() < 1e-3
+    acc = torch.ones(M, N, device="cuda")
+    ops.gemm(A, W, M, N, K, acc, mode=L.EPI_F32, accumulate=True)
+    assert (acc - (1 + A.float() @ W.float().t())).abs().max().item() < 1e-3
+
+
+def test_linear_fwd_dgrad_wgrad_consistency():
+    """The three layouts reproduce autograd of y = x W^T on bf16-rounded operands."""
+    from mtp_b200 import ops, _lib as L
+    T, Cin, Cout = 1000, 256, 384
+    x, W = _mk((T, Cin), seed=10), _mk((Cout, Cin), 0.1, seed=11)
+    dy = _mk((T, Cout), seed=12)
+    dx = torch.empty(T, Cin, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, W, T, Cin, Cout, dx, b_mn=True)                      # dX = dY W
+    dW = torch.empty(Cout, Cin, device="cuda")
+    ops.gemm(dy, x, Cout, Cin, T, dW, a_mn=True, b_mn=True, mode=L.EPI_F32)   # dW = dY^T X
+    ref_dx = dy.float() @ W.float()
+    ref_dW = dy.float().t() @ x.float()
+    assert ((dx.float() - ref_dx).abs() <= 8e-3 * ref_dx.abs() + 1e-2).all()
+    assert (dW - ref_dW).norm().item() / ref_dW.norm().item() < 1e-5
+
+
+def test_gemm_rejects_bad_args():
+    from mtp_b200 import ops, _lib as L
+    A, B = _mk((16, 20)), _mk((16, 20))
+    out = torch.empty(16, 16, device="cuda")
+    with pytest.raises(L.MtpError):
+        ops.gemm(A, B, 16, 16, 20, out, mode=L.EPI_F32)       # lda not a multiple of 8

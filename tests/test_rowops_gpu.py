@@ -1,0 +1,71 @@
+"""LayerNorm / cast / column-sum kernels vs fp32 torch."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("C", [128, 768, 1024])
+@pytest.mark.parametrize("rows", [1, 37, 1568])
+def test_layernorm_fwd_bwd(C, rows):
+    from mtp_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(rows, C, device="cuda") * 2 + 0.5
+    g = torch.randn(C, device="cuda") * 0.2 + 1
+    b = torch.randn(C, device="cuda") * 0.2
+    y, mean, rstd = ops.layernorm_fwd(x, g, b)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-6)
+    assert ((y.float() - ref).abs() <= 8e-3 * ref.abs() + 1e-3).all()
+    assert (mean - x.mean(1)).abs().max().item() < 1e-5
+    dy = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
+    dres = torch.randn(rows, C, device="cuda")
+    ref.backward(dy.float())
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = ops.layernorm_bwd(dy, x, mean, rstd, g, b, dres, dg, db)
+    assert (dx - (xr.grad + dres)).abs().max().item() < 1e-3
+    assert (dg - gr.grad).abs().max().item() < 1e-3 * max(1.0, gr.grad.abs().max().item())
+    assert (db - br.grad).abs().max().item() < 1e-3 * max(1.0, br.grad.abs().max().item())
+
+
+def test_layernorm_gelu_bf16_variant():
+    from mtp_b200 import ops
+    torch.manual_seed(1)
+    rows, C = 500, 128
+    x = (torch.randn(rows, C, device="cuda") * 2).to(torch.bfloat16)
+    g = torch.randn(C, device="cuda") * 0.2 + 1
+    b = torch.randn(C, device="cuda") * 0.2
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, gelu=True)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-6))
+    assert ((y.float() - ref).abs() <= 8e-3 * ref.abs() + 2e-3).all()
+    dy = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
+    ref.backward(dy.float())
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = ops.layernorm_bwd(dy, x, mean, rstd, g, b, None, dg, db, gelu=True)
+    assert ((dx.float() - xr.grad).abs() <= 1e-2 * xr.grad.abs() + 5e-3).all()
+    assert (dg - gr.grad).abs().max().item() < 2e-3 * max(1.0, gr.grad.abs().max().item())
+    assert (db - br.grad).abs().max().item() < 2e-3 * max(1.0, br.grad.abs().max().item())
+
+
+def test_casts_and_colsums():
+    from mtp_b200 import ops
+    torch.manual_seed(2)
+    rows, C, ntok = 300, 256, 100
+    x = torch.randn(rows, C, device="cuda")
+    keep = torch.tensor([1.0, 0.0, 2.0], device="cuda")
+    cs = torch.zeros(C, device="cuda")
+    y = ops.scale_cast_bf16(x, keep, ntok, cs)
+    ref = x * keep.repeat_interleave(ntok)[:, None]
+    assert (y.float() - ref).abs().max().item() <= 0.02
+    assert (cs - ref.sum(0)).abs().max().item() < 1e-3
+    cs2 = torch.zeros(C, device="cuda")
+    ops.colsum_bf16(y, cs2)
+    assert (cs2 - y.float().sum(0)).abs().max().item() < 1e-3
+    z = ops.cast_f32_bf16(x)
+    assert torch.equal(z, x.to(torch.bfloat16))
+    acc = torch.ones(rows, C, device="cuda")
+    ops.add_bf16_into_f32(z, acc)
+    assert torch.equal(acc, 1 + z.float())
