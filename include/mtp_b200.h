@@ -97,6 +97,44 @@ int mtp_colsum_bf16(const void* in_bf16, int ld, float* colsum, int rows, int C,
 int mtp_cast_f32_bf16(const float* in, void* out_bf16, size_t n, mtp_stream_t stream);
 int mtp_add_bf16_into_f32(const void* in_bf16, float* out, size_t n, mtp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Rotated varied-size window attention (RVSA), forward.  RotatedVariedSizeWindowAttention.forward, [V]:287-433.
+ * mtp_rvsa_sampling_fwd: AvgPool2d(7) over the zero-padded LN'd tokens -> LeakyReLU -> the three 1x1 convs
+ *   ([V]:228-243,347,354-368).  yn_bf16 [T, C]; w_off/w_scale [2nH, C], w_angle [nH, C] (Conv2d weights flattened);
+ *   pooled (optional out) [B*nWin, C] pre-activation means (saved for backward);
+ *   params (out) [B*nWin, nH, 8] = (ox, oy, sx, sy, theta, -, -, -) with the [V]:359-360 divisions applied.
+ * mtp_rvsa_attn_fwd: coords ([V]:372-385) -> bilinear K/V gather ([V]:397-404) -> scores + decomposed rel-pos with the
+ *   UNscaled q ([V]:410-412) + bias table ([V]:414-418) -> softmax -> PV -> un-window + crop ([V]:420-428).
+ *   qkv_bf16 [T, 3C] (q | k | v, head-major, hd = 64); rel_pos_h/w [13, 64]; bias_table [169, nH];
+ *   out_bf16 [T, C]; lse (optional out) [B*nWin*nH, 49] log-sum-exp per query row (saved for backward).
+ * ------------------------------------------------------------------------------------------------------------- */
+int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, const float* b_off, const float* w_scale,
+                          const float* b_scale, const float* w_angle, const float* b_angle, float* pooled, float* params,
+                          int B, int h, int w, int C, int nH, mtp_stream_t stream);
+int mtp_rvsa_attn_fwd(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,
+                      const float* bias_table, void* out_bf16, float* lse, int B, int h, int w, int C, int nH,
+                      mtp_stream_t stream);
+
+/* Dense attention with decomposed rel-pos bias (q scaled first), flash-style.  Attention.forward [V]:90-111 +
+ * calc_rel_pos_spatial [V]:142-193.  rel_pos_h [2gh-1, 64], rel_pos_w [2gw-1, 64], both NULL = no bias (the mmdet /
+ * mmrotate finetune twins).  lse (optional out) [B, nH, N]. */
+int mtp_full_attn_fwd(const void* qkv_bf16, const float* rel_pos_h, const float* rel_pos_w, void* out_bf16, float* lse, int B,
+                      int gh, int gw, int C, int nH, mtp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Layout kernels.  mtp_patchify: image (B, cin, H, W) f32|bf16 -> patch rows [T, cin*256] bf16 (A operand of the
+ * patch-embed GEMM, [V]:529,536-539).  mtp_tok_to_nchw / mtp_nchw_to_tok: token-major matrix <-> NCHW map
+ * ([V]:807), `level` = number of nested k2/s2 transposed convolutions whose 4 sub-pixels sit side by side in the row
+ * (0: ld >= C; 1, 2: ld >= 4C).  mtp_maxpool2_tok_*: fpn4 = MaxPool2d(2,2) on the token grid ([V]:654).
+ * ------------------------------------------------------------------------------------------------------------- */
+int mtp_patchify(const void* img, int img_is_bf16, void* out_bf16, int B, int cin, int H, int W, mtp_stream_t stream);
+int mtp_tok_to_nchw(const void* tok, int tok_is_bf16, int ld, void* out, int out_is_bf16, int B, int h, int w, int C, int level,
+                    mtp_stream_t stream);
+int mtp_nchw_to_tok(const void* in, int in_is_bf16, void* tok, int tok_is_bf16, int ld, int accumulate, int B, int h, int w, int C,
+                    int level, mtp_stream_t stream);
+int mtp_maxpool2_tok_fwd(const float* x, float* y, int B, int h, int w, int C, mtp_stream_t stream);
+int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, int B, int h, int w, int C, mtp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

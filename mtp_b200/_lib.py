@@ -34,6 +34,14 @@ _SIGNATURES = {
     "mtp_colsum_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "mtp_cast_f32_bf16": [c_void_p, c_void_p, c_size_t, c_void_p],
     "mtp_add_bf16_into_f32": [c_void_p, c_void_p, c_size_t, c_void_p],
+    "mtp_rvsa_sampling_fwd": [c_void_p] * 9 + [c_int] * 5 + [c_void_p],
+    "mtp_rvsa_attn_fwd": [c_void_p] * 7 + [c_int] * 5 + [c_void_p],
+    "mtp_full_attn_fwd": [c_void_p] * 5 + [c_int] * 5 + [c_void_p],
+    "mtp_patchify": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_tok_to_nchw": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_nchw_to_tok": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_maxpool2_tok_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_maxpool2_tok_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
 
 _lib = None

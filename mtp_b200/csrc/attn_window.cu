@@ -1,0 +1,278 @@
+// Rotated varied-size window attention (RVSA), forward.      [V]:287-433, SURVEY.md Appendix A.1
+//
+//   rvsa_sampling_fwd : per (image, window): zero-padded 7x7 mean of the LN'd tokens -> LeakyReLU(0.01) ->
+//                       three 1x1 convs (GEMVs) -> (ox, oy, sx, sy, theta) per head                     [V]:228-243,354-368
+//   rvsa_attn_fwd     : per (image, window, head): sampling coordinates in registers -> 4-tap bilinear gather of the
+//                       K and V rows (one 128-byte line per tap from the token-major qkv matrix) blended in fp32 into
+//                       shared memory -> S = scale q.k~ + q.Rh + q.Rw + bias-table -> softmax -> P v~ -> token-major
+//                       bf16 output (padding rows are never written: crop is free).                      [V]:372-428
+//
+// Tokens live in the [T, 3C] bf16 output of the qkv GEMM (q | k | v, each head-major with hd = 64), so a K or V tap of one
+// head is one contiguous 128-byte line and no window partition / pad / permute copy is ever materialised.
+#include "common.h"
+#include "ptx.cuh"
+#include "rvsa_geom.cuh"
+
+namespace mtp {
+
+// ------------------------------------------------------------------------------------------------ sampling params
+__global__ void __launch_bounds__(256)
+rvsa_sampling_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float* __restrict__ w_off, const float* __restrict__ b_off,
+                         const float* __restrict__ w_sc, const float* __restrict__ b_sc, const float* __restrict__ w_ang,
+                         const float* __restrict__ b_ang, float* __restrict__ pooled_out, float* __restrict__ params,
+                         const RvsaGeom g) {
+  extern __shared__ float act[];                         // [C] LeakyReLU(pooled)
+  const int bw = blockIdx.x;                             // (image, window)
+  const int b = bw / (g.nh * g.nw), win = bw % (g.nh * g.nw);
+  const int wy = win / g.nw, wx = win % g.nw;
+  const int C = g.C;
+  for (int c = threadIdx.x * 4; c < C; c += 256 * 4) {
+    float4 s = make_float4(0, 0, 0, 0);
+    for (int i = 0; i < WS * WS; ++i) {
+      const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
+      if (y >= 0 && y < g.h && x >= 0 && x < g.w) {
+        const uint2 u = *reinterpret_cast<const uint2*>(yn + ((size_t)(b * g.h + y) * g.w + x) * C + c);
+        const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y);
+        s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
+      }
+    }
+    const float inv = 1.0f / (WS * WS);                  // zeros of the padding are part of the mean ([V]:347,354)
+    s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+    if (pooled_out) *reinterpret_cast<float4*>(pooled_out + (size_t)bw * C + c) = s;
+    act[c] = s.x >= 0 ? s.x : 0.01f * s.x;
+    act[c + 1] = s.y >= 0 ? s.y : 0.01f * s.y;
+    act[c + 2] = s.z >= 0 ? s.z : 0.01f * s.z;
+    act[c + 3] = s.w >= 0 ? s.w : 0.01f * s.w;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nH = g.nH;
+  for (int o = warp; o < 5 * nH; o += 8) {
+    // output order: [0,2nH) offsets (head-major, x then y), [2nH,4nH) scales, [4nH,5nH) angle
+    const float* wrow;
+    float bias;
+    if (o < 2 * nH) { wrow = w_off + (size_t)o * C; bias = b_off[o]; }
+    else if (o < 4 * nH) { wrow = w_sc + (size_t)(o - 2 * nH) * C; bias = b_sc[o - 2 * nH]; }
+    else { wrow = w_ang + (size_t)(o - 4 * nH) * C; bias = b_ang[o - 4 * nH]; }
+    float s = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + c));
+      s += wv.x * act[c] + wv.y * act[c + 1] + wv.z * act[c + 2] + wv.w * act[c + 3];
+    }
+    s = warp_sum(s) + bias;
+    if (lane == 0) {
+      int n, slot;
+      if (o < 2 * nH) { n = o >> 1; slot = o & 1; s /= (float)((slot == 0 ? g.h : g.w) / WS); }   // sic: x by h//7, y by w//7
+      else if (o < 4 * nH) { n = (o - 2 * nH) >> 1; slot = 2 + ((o - 2 * nH) & 1); }
+      else { n = o - 4 * nH; slot = 4; }
+      params[((size_t)bw * nH + n) * 8 + slot] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention fwd
+constexpr int LDS_ROW = 68;      // padded fp32 row stride (floats) for Q/K/V tiles: conflict-free float4 row access
+constexpr int LDP = 52;          // row stride of the 49x49 score tile
+constexpr int RVSA_SMEM_FLOATS = 3 * NTOK * LDS_ROW + NTOK * LDP + 2 * NTOK * 8 + 2 * NTOK;
+
+__global__ void __launch_bounds__(64)
+rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
+                     const float* __restrict__ rel_w, const float* __restrict__ bias_table, __nv_bfloat16* __restrict__ out,
+                     float* __restrict__ lse, const RvsaGeom g) {
+  extern __shared__ float sm[];
+  float* Qs = sm;
+  float* Ks = Qs + NTOK * LDS_ROW;
+  float* Vs = Ks + NTOK * LDS_ROW;
+  float* Ps = Vs + NTOK * LDS_ROW;
+  float* relh = Ps + NTOK * LDP;       // [49][8]
+  float* relw = relh + NTOK * 8;
+  float* cpx = relw + NTOK * 8;        // [49]
+  float* cpy = cpx + NTOK;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x % g.nH;
+  const int bw = blockIdx.x / g.nH;
+  const int nwin = g.nh * g.nw;
+  const int b = bw / nwin, win = bw % nwin;
+  const int wy = win / g.nw, wx = win % g.nw;
+  const int C = g.C, C3 = 3 * g.C;
+  const float scale = 0.125f;          // hd^-0.5, hd = 64
+
+  if (tid < NTOK) {
+    const float* p = params + ((size_t)bw * g.nH + n) * 8;
+    float px, py;
+    rvsa_sample_coord(g, wy, wx, tid / WS, tid % WS, p[0], p[1], p[2], p[3], p[4], px, py);
+    cpx[tid] = px;
+    cpy[tid] = py;
+  }
+  __syncthreads();
+
+  const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + n * HD;
+  for (int j = warp; j < NTOK; j += 2) {
+    // ---- q row of window token j (zero for padding positions)
+    {
+      const int y = wy * WS + j / WS - g.pt, x = wx * WS + j % WS - g.pl;
+      float2 qv = make_float2(0.f, 0.f);
+      if (y >= 0 && y < g.h && x >= 0 && x < g.w)
+        qv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qkv_b + (size_t)(y * g.w + x) * C3 + lane * 2));
+      *reinterpret_cast<float2*>(Qs + j * LDS_ROW + lane * 2) = qv;
+    }
+    // ---- bilinear gather of k~, v~ at sample j (grid_sample: bilinear, zeros, align_corners=True)
+    const float px = cpx[j], py = cpy[j];
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float ax = px - fx0, ay = py - fy0;
+    const int x0 = (int)fx0 - g.pl, y0 = (int)fy0 - g.pt;        // tap coords in the un-padded grid
+    float2 ka = make_float2(0.f, 0.f), va = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+      const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
+      // taps in the zero padding or outside the padded grid contribute 0 (pad is applied after the bias, [V]:392)
+      if (xx >= 0 && xx < g.w && yy >= 0 && yy < g.h) {
+        const __nv_bfloat16* src = qkv_b + (size_t)(yy * g.w + xx) * C3 + lane * 2;
+        const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C));
+        const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C));
+        ka.x += wgt * kv.x; ka.y += wgt * kv.y;
+        va.x += wgt * vv.x; va.y += wgt * vv.y;
+      }
+    }
+    *reinterpret_cast<float2*>(Ks + j * LDS_ROW + lane * 2) = ka;
+    *reinterpret_cast<float2*>(Vs + j * LDS_ROW + lane * 2) = va;
+  }
+  __syncthreads();
+
+  // ---- decomposed rel-pos: relh[q][kh] = q . rel_pos_h[qy - kh + 6], relw[q][kw] = q . rel_pos_w[qx - kw + 6]  (q UNscaled)
+  for (int e = tid; e < NTOK * 14; e += 64) {
+    const int q = e / 14, r = e % 14;
+    const int kk = r % 7;
+    const float* tab = (r < 7 ? rel_h : rel_w) + ((r < 7 ? q / WS : q % WS) - kk + WS - 1) * HD;
+    const float* qr = Qs + q * LDS_ROW;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      const float4 tv = __ldg(reinterpret_cast<const float4*>(tab + d));
+      const float4 qv = *reinterpret_cast<const float4*>(qr + d);
+      s += qv.x * tv.x + qv.y * tv.y + qv.z * tv.z + qv.w * tv.w;
+    }
+    (r < 7 ? relh : relw)[q * 8 + kk] = s;
+  }
+  __syncthreads();
+
+  // ---- scores: thread (tq, tj) owns the 7x7 micro-tile q in [7tq, 7tq+7), j in [7tj, 7tj+7)
+  if (tid < NTOK) {
+    const int tq = tid / WS, tj = tid % WS;
+    float acc[WS][WS];
+#pragma unroll
+    for (int a = 0; a < WS; ++a)
+#pragma unroll
+      for (int c = 0; c < WS; ++c) acc[a][c] = 0.f;
+    for (int d = 0; d < HD; d += 4) {
+      float4 qv[WS], kv[WS];
+#pragma unroll
+      for (int a = 0; a < WS; ++a) qv[a] = *reinterpret_cast<const float4*>(Qs + (tq * WS + a) * LDS_ROW + d);
+#pragma unroll
+      for (int c = 0; c < WS; ++c) kv[c] = *reinterpret_cast<const float4*>(Ks + (tj * WS + c) * LDS_ROW + d);
+#pragma unroll
+      for (int a = 0; a < WS; ++a)
+#pragma unroll
+        for (int c = 0; c < WS; ++c)
+          acc[a][c] += qv[a].x * kv[c].x + qv[a].y * kv[c].y + qv[a].z * kv[c].z + qv[a].w * kv[c].w;
+    }
+    // q = (qy = tq, qx = a), key j = (jy = tj, jx = c)
+#pragma unroll
+    for (int a = 0; a < WS; ++a) {
+      const int q = tq * WS + a;
+#pragma unroll
+      for (int c = 0; c < WS; ++c) {
+        const int idx = (tq - tj + WS - 1) * (2 * WS - 1) + (a - c + WS - 1);
+        Ps[q * LDP + tj * WS + c] = scale * acc[a][c] + relh[q * 8 + tj] + relw[q * 8 + c] + __ldg(bias_table + idx * g.nH + n);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax over keys, one thread per query row
+  if (tid < NTOK) {
+    float* row = Ps + tid * LDP;
+    float m = -INFINITY;
+    for (int j = 0; j < NTOK; ++j) m = fmaxf(m, row[j]);
+    float s = 0.f;
+    for (int j = 0; j < NTOK; ++j) {
+      const float e = __expf(row[j] - m);
+      row[j] = e;
+      s += e;
+    }
+    const float inv = 1.0f / s;
+    for (int j = 0; j < NTOK; ++j) row[j] *= inv;
+    if (lse) lse[(size_t)blockIdx.x * NTOK + tid] = m + __logf(s);
+  }
+  __syncthreads();
+
+  // ---- O = P v~ : thread (tq, td) owns rows [7tq, 7tq+7) x dims [4td, 4td+4) and [32+4td, 32+4td+4)
+  if (tid < 56) {
+    const int tq = tid >> 3, td = tid & 7;
+    float acc[WS][8];
+#pragma unroll
+    for (int a = 0; a < WS; ++a)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+    for (int j = 0; j < NTOK; ++j) {
+      const float4 v0 = *reinterpret_cast<const float4*>(Vs + j * LDS_ROW + td * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(Vs + j * LDS_ROW + 32 + td * 4);
+#pragma unroll
+      for (int a = 0; a < WS; ++a) {
+        const float p = Ps[(tq * WS + a) * LDP + j];
+        acc[a][0] += p * v0.x; acc[a][1] += p * v0.y; acc[a][2] += p * v0.z; acc[a][3] += p * v0.w;
+        acc[a][4] += p * v1.x; acc[a][5] += p * v1.y; acc[a][6] += p * v1.z; acc[a][7] += p * v1.w;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < WS; ++a) {
+      const int y = wy * WS + tq - g.pt, x = wx * WS + a - g.pl;
+      if (y >= 0 && y < g.h && x >= 0 && x < g.w) {
+        uint2 u0, u1;
+        u0.x = pack_bf16x2(acc[a][0], acc[a][1]);
+        u0.y = pack_bf16x2(acc[a][2], acc[a][3]);
+        u1.x = pack_bf16x2(acc[a][4], acc[a][5]);
+        u1.y = pack_bf16x2(acc[a][6], acc[a][7]);
+        __nv_bfloat16* orow = out + ((size_t)(b * g.h + y) * g.w + x) * C + n * HD;
+        *reinterpret_cast<uint2*>(orow + td * 4) = u0;
+        *reinterpret_cast<uint2*>(orow + 32 + td * 4) = u1;
+      }
+    }
+  }
+}
+
+}  // namespace mtp
+
+using namespace mtp;
+
+extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, const float* b_off, const float* w_scale,
+                                     const float* b_scale, const float* w_angle, const float* b_angle, float* pooled,
+                                     float* params, int B, int h, int w, int C, int nH, mtp_stream_t stream) {
+  MTP_REQUIRE(yn_bf16 && w_off && b_off && w_scale && b_scale && w_angle && b_angle && params, "mtp_rvsa_sampling_fwd: null pointer");
+  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C % 128 == 0 && C == nH * HD, "mtp_rvsa_sampling_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported (need h,w>=7, C==64*nH)", B, h, w, C, nH);
+  const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
+  rvsa_sampling_fwd_kernel<<<B * g.nh * g.nw, 256, C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(yn_bf16), w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g);
+  return check_launch("rvsa_sampling_fwd_kernel");
+}
+
+extern "C" int mtp_rvsa_attn_fwd(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,
+                                 const float* bias_table, void* out_bf16, float* lse, int B, int h, int w, int C, int nH,
+                                 mtp_stream_t stream) {
+  MTP_REQUIRE(qkv_bf16 && params && rel_pos_h && rel_pos_w && bias_table && out_bf16, "mtp_rvsa_attn_fwd: null pointer");
+  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD, "mtp_rvsa_attn_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported", B, h, w, C, nH);
+  const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
+  static bool attr = false;
+  const int smem = RVSA_SMEM_FLOATS * sizeof(float);
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(rvsa_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_fwd smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  rvsa_attn_fwd_kernel<<<B * g.nh * g.nw * nH, 64, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), params, rel_pos_h, rel_pos_w, bias_table,
+      reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, g);
+  return check_launch("rvsa_attn_fwd_kernel");
+}

@@ -16,7 +16,7 @@ inline int check_launch(const char* what) {
   return MTP_OK;
 }
 
-inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 int num_sms();
 

@@ -1,0 +1,217 @@
+// Layout kernels at the two ends of the backbone: image -> patch rows (the A operand of the patch-embed GEMM), and
+// token-major feature matrices <-> the NCHW maps the decoders consume, including the pixel-shuffle of the k2/s2
+// transposed convolutions (a ConvTranspose2d(k2,s2) is the GEMM [T,Cin] x [Cin,4Cout] whose output row (b,y,x) holds the
+// four sub-pixels (dy,dx) side by side; nesting two of them gives level 2).        [V]:529-540, 640-654, 807-811
+#include <algorithm>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mtp {
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------------------------------------------- patchify
+// out[(b, py, px), c*256 + ky*16 + kx] = img[b, c, py*16+ky, px*16+kx]   (Conv2d weight (C, cin, 16, 16) flattens the same way)
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int cin, int H, int W, int gh, int gw) {
+  const int chunks_per_tok = cin * 16 * 4;                 // 4-element chunks per token row
+  const size_t total = (size_t)B * gh * gw * chunks_per_tok;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks_per_tok);
+    const size_t tok = i / chunks_per_tok;
+    const int kx4 = ch & 3, ky = (ch >> 2) & 15, c = ch >> 6;
+    const int px = (int)(tok % gw), py = (int)((tok / gw) % gh), b = (int)(tok / ((size_t)gw * gh));
+    const TIn* src = img + (((size_t)b * cin + c) * H + py * 16 + ky) * W + px * 16 + kx4 * 4;
+    uint2 u;
+    u.x = pack_bf16x2(to_f32(src[0]), to_f32(src[1]));
+    u.y = pack_bf16x2(to_f32(src[2]), to_f32(src[3]));
+    *reinterpret_cast<uint2*>(out + tok * (size_t)(cin * 256) + c * 256 + ky * 16 + kx4 * 4) = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- tok <-> NCHW
+struct MapGeom { int B, h, w, C, L; };      // base grid h x w, channels C, pixel-shuffle level L (0, 1, 2)
+
+// (row, column base) of output pixel (b, Y, X) of the level-L map inside the token-major matrix
+__device__ __forceinline__ void map_index(const MapGeom& g, int b, int Y, int X, size_t& row, int& colbase) {
+  if (g.L == 0) { row = ((size_t)b * g.h + Y) * g.w + X; colbase = 0; }
+  else if (g.L == 1) { row = ((size_t)b * g.h + (Y >> 1)) * g.w + (X >> 1); colbase = (((Y & 1) << 1) | (X & 1)) * g.C; }
+  else {
+    row = (((size_t)b * g.h + (Y >> 2)) * g.w + (X >> 2)) * 4 + ((((Y >> 1) & 1) << 1) | ((X >> 1) & 1));
+    colbase = (((Y & 1) << 1) | (X & 1)) * g.C;
+  }
+}
+
+// NCHW out[b, c, Y, X] = tok[row(b,Y,X), colbase + c];   32(X) x 32(c) tiles through shared memory
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+tok_to_nchw_kernel(const TIn* __restrict__ tok, int ld, TOut* __restrict__ out, const MapGeom g) {
+  __shared__ float tile[32][33];
+  const int Ho = g.h << g.L, Wo = g.w << g.L;
+  const int x_tiles = ceil_div(Wo, 32);
+  const int xt = blockIdx.x % x_tiles, Y = blockIdx.x / x_tiles;
+  const int c0 = blockIdx.y * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (int i = ty; i < 32; i += 8) {                            // i = X within tile, tx = channel
+    const int X = xt * 32 + i;
+    if (X < Wo && c0 + tx < g.C) {
+      size_t row; int cb;
+      map_index(g, b, Y, X, row, cb);
+      tile[i][tx] = to_f32(tok[row * ld + cb + c0 + tx]);
+    }
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {                            // i = channel within tile, tx = X
+    const int X = xt * 32 + tx, c = c0 + i;
+    if (X < Wo && c < g.C) out[(((size_t)b * g.C + c) * Ho + Y) * Wo + X] = from_f32<TOut>(tile[tx][i]);
+  }
+}
+
+// tok[row(b,Y,X), colbase + c] (+)= in[b, c, Y, X]
+template <typename TIn, typename TOut, bool ACC>
+__global__ void __launch_bounds__(256)
+nchw_to_tok_kernel(const TIn* __restrict__ in, TOut* __restrict__ tok, int ld, const MapGeom g) {
+  __shared__ float tile[32][33];
+  const int Ho = g.h << g.L, Wo = g.w << g.L;
+  const int x_tiles = ceil_div(Wo, 32);
+  const int xt = blockIdx.x % x_tiles, Y = blockIdx.x / x_tiles;
+  const int c0 = blockIdx.y * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {                            // i = channel, tx = X
+    const int X = xt * 32 + tx, c = c0 + i;
+    if (X < Wo && c < g.C) tile[tx][i] = to_f32(in[(((size_t)b * g.C + c) * Ho + Y) * Wo + X]);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {                            // i = X, tx = channel
+    const int X = xt * 32 + i;
+    if (X < Wo && c0 + tx < g.C) {
+      size_t row; int cb;
+      map_index(g, b, Y, X, row, cb);
+      TOut* dst = tok + row * ld + cb + c0 + tx;
+      if (ACC) *dst = from_f32<TOut>(to_f32(*dst) + tile[i][tx]);
+      else *dst = from_f32<TOut>(tile[i][tx]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- 2x2 max pool (fpn4)
+// token-major f32 [B, h, w, C] -> token-major f32 [B, h/2, w/2, C]                                   [V]:654
+__global__ void __launch_bounds__(256)
+maxpool2_tok_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int h, int w, int C) {
+  const int ho = h / 2, wo = w / 2, c4n = C / 4;
+  const size_t total = (size_t)B * ho * wo * c4n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    const size_t p = i / c4n;
+    const int xo = (int)(p % wo), yo = (int)((p / wo) % ho), b = (int)(p / ((size_t)wo * ho));
+    const float* s = x + (((size_t)b * h + 2 * yo) * w + 2 * xo) * C + c;
+    const float4 a = *reinterpret_cast<const float4*>(s), bq = *reinterpret_cast<const float4*>(s + C);
+    const float4 cq = *reinterpret_cast<const float4*>(s + (size_t)w * C), d = *reinterpret_cast<const float4*>(s + (size_t)w * C + C);
+    float4 m;
+    m.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(cq.x, d.x));
+    m.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, d.y));
+    m.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, d.z));
+    m.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, d.w));
+    *reinterpret_cast<float4*>(y + p * C + c) = m;
+  }
+}
+
+// dx[argmax position] += dy   (first maximum in scan order wins, as in ATen's max_pool2d backward)
+__global__ void __launch_bounds__(256)
+maxpool2_tok_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int h, int w, int C) {
+  const int ho = h / 2, wo = w / 2;
+  const size_t total = (size_t)B * ho * wo * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t p = i / C;
+    const int xo = (int)(p % wo), yo = (int)((p / wo) % ho), b = (int)(p / ((size_t)wo * ho));
+    const size_t base = (((size_t)b * h + 2 * yo) * w + 2 * xo) * C + c;
+    const size_t offs[4] = {0, (size_t)C, (size_t)w * C, (size_t)w * C + C};
+    int best = 0;
+    float bv = x[base];
+#pragma unroll
+    for (int t = 1; t < 4; ++t) {
+      const float v = x[base + offs[t]];
+      if (v > bv) { bv = v; best = t; }
+    }
+    dx[base + offs[best]] += dy[i];
+  }
+}
+
+static inline int grid_for(size_t n, int block) { return (int)std::min<size_t>((n + block - 1) / block, (size_t)num_sms() * 16); }
+
+}  // namespace mtp
+
+using namespace mtp;
+
+extern "C" int mtp_patchify(const void* img, int img_is_bf16, void* out_bf16, int B, int cin, int H, int W, mtp_stream_t stream) {
+  MTP_REQUIRE(img && out_bf16, "mtp_patchify: null pointer");
+  MTP_REQUIRE(B > 0 && cin > 0 && H >= 16 && W >= 16 && W % 4 == 0, "mtp_patchify: B=%d cin=%d H=%d W=%d unsupported", B, cin, H, W);
+  const int gh = H / 16, gw = W / 16;
+  const size_t total = (size_t)B * gh * gw * cin * 64;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (img_is_bf16)
+    patchify_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(img),
+                                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16), B, cin, H, W, gh, gw);
+  else
+    patchify_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(img),
+                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16), B, cin, H, W, gh, gw);
+  return check_launch("patchify_kernel");
+}
+
+extern "C" int mtp_tok_to_nchw(const void* tok, int tok_is_bf16, int ld, void* out, int out_is_bf16, int B, int h, int w, int C,
+                               int level, mtp_stream_t stream) {
+  MTP_REQUIRE(tok && out, "mtp_tok_to_nchw: null pointer");
+  MTP_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && level >= 0 && level <= 2 && ld >= (level ? 4 * C : C), "mtp_tok_to_nchw: bad geometry");
+  const MapGeom g{B, h, w, C, level};
+  const dim3 grid(ceil_div(w << level, 32) * (h << level), ceil_div(C, 32), B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define T2N(TI, TO) tok_to_nchw_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(tok), ld, reinterpret_cast<TO*>(out), g)
+  if (tok_is_bf16 && out_is_bf16) T2N(__nv_bfloat16, __nv_bfloat16);
+  else if (tok_is_bf16) T2N(__nv_bfloat16, float);
+  else if (out_is_bf16) T2N(float, __nv_bfloat16);
+  else T2N(float, float);
+#undef T2N
+  return check_launch("tok_to_nchw_kernel");
+}
+
+extern "C" int mtp_nchw_to_tok(const void* in, int in_is_bf16, void* tok, int tok_is_bf16, int ld, int accumulate, int B, int h, int w,
+                               int C, int level, mtp_stream_t stream) {
+  MTP_REQUIRE(in && tok, "mtp_nchw_to_tok: null pointer");
+  MTP_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && level >= 0 && level <= 2 && ld >= (level ? 4 * C : C), "mtp_nchw_to_tok: bad geometry");
+  const MapGeom g{B, h, w, C, level};
+  const dim3 grid(ceil_div(w << level, 32) * (h << level), ceil_div(C, 32), B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define N2T(TI, TO, A) nchw_to_tok_kernel<TI, TO, A><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(in), reinterpret_cast<TO*>(tok), ld, g)
+  if (accumulate) {
+    MTP_REQUIRE(!tok_is_bf16, "mtp_nchw_to_tok: accumulate needs an f32 destination");
+    if (in_is_bf16) N2T(__nv_bfloat16, float, true); else N2T(float, float, true);
+  } else if (tok_is_bf16) {
+    if (in_is_bf16) N2T(__nv_bfloat16, __nv_bfloat16, false); else N2T(float, __nv_bfloat16, false);
+  } else {
+    if (in_is_bf16) N2T(__nv_bfloat16, float, false); else N2T(float, float, false);
+  }
+#undef N2T
+  return check_launch("nchw_to_tok_kernel");
+}
+
+extern "C" int mtp_maxpool2_tok_fwd(const float* x, float* y, int B, int h, int w, int C, mtp_stream_t stream) {
+  MTP_REQUIRE(x && y && B > 0 && h >= 2 && w >= 2 && C % 4 == 0, "mtp_maxpool2_tok_fwd: bad args");
+  const size_t total = (size_t)B * (h / 2) * (w / 2) * (C / 4);
+  maxpool2_tok_fwd_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, h, w, C);
+  return check_launch("maxpool2_tok_fwd_kernel");
+}
+
+extern "C" int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, int B, int h, int w, int C, mtp_stream_t stream) {
+  MTP_REQUIRE(x && dy && dx && B > 0 && h >= 2 && w >= 2, "mtp_maxpool2_tok_bwd: bad args");
+  const size_t total = (size_t)B * (h / 2) * (w / 2) * C;
+  maxpool2_tok_bwd_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, dy, dx, B, h, w, C);
+  return check_launch("maxpool2_tok_bwd_kernel");
+}

@@ -76,3 +76,65 @@ def cast_f32_bf16(x):
 def add_bf16_into_f32(src, dst):
     L.call("mtp_add_bf16_into_f32", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
     return dst
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def rvsa_sampling_fwd(yn, w_off, b_off, w_sc, b_sc, w_ang, b_ang, B, h, w, nH, save_pooled=True):
+    C = yn.shape[-1]
+    nwin = ((h + 6) // 7) * ((w + 6) // 7)
+    params = torch.zeros(B * nwin, nH, 8, device=yn.device, dtype=F32)
+    pooled = torch.empty(B * nwin, C, device=yn.device, dtype=F32) if save_pooled else None
+    L.call("mtp_rvsa_sampling_fwd", yn.data_ptr(), w_off.data_ptr(), b_off.data_ptr(), w_sc.data_ptr(), b_sc.data_ptr(),
+           w_ang.data_ptr(), b_ang.data_ptr(), _p(pooled), params.data_ptr(), B, h, w, C, nH, _stream())
+    return params, pooled
+
+
+def rvsa_attn_fwd(qkv, params, rel_h, rel_w, table, B, h, w, nH, save_lse=True):
+    C = qkv.shape[-1] // 3
+    out = torch.empty(qkv.shape[0], C, device=qkv.device, dtype=BF16)
+    lse = torch.empty(params.shape[0] * nH, 49, device=qkv.device, dtype=F32) if save_lse else None
+    L.call("mtp_rvsa_attn_fwd", qkv.data_ptr(), params.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(), table.data_ptr(),
+           out.data_ptr(), _p(lse), B, h, w, C, nH, _stream())
+    return out, lse
+
+
+def full_attn_fwd(qkv, rel_h, rel_w, B, gh, gw, nH, save_lse=True):
+    C = qkv.shape[-1] // 3
+    out = torch.empty(qkv.shape[0], C, device=qkv.device, dtype=BF16)
+    lse = torch.empty(B, nH, gh * gw, device=qkv.device, dtype=F32) if save_lse else None
+    L.call("mtp_full_attn_fwd", qkv.data_ptr(), _p(rel_h), _p(rel_w), out.data_ptr(), _p(lse), B, gh, gw, C, nH, _stream())
+    return out, lse
+
+
+# ---------------------------------------------------------------------------------------------- layout
+def patchify(img):
+    B, cin, H, W = img.shape
+    assert img.is_contiguous() and img.dtype in (F32, BF16)
+    out = torch.empty(B * (H // 16) * (W // 16), cin * 256, device=img.device, dtype=BF16)
+    L.call("mtp_patchify", img.data_ptr(), int(img.dtype == BF16), out.data_ptr(), B, cin, H, W, _stream())
+    return out
+
+
+def tok_to_nchw(tok, B, h, w, C, level, out_dtype):
+    out = torch.empty(B, C, h << level, w << level, device=tok.device, dtype=out_dtype)
+    L.call("mtp_tok_to_nchw", tok.data_ptr(), int(tok.dtype == BF16), int(tok.shape[-1]), out.data_ptr(), int(out_dtype == BF16),
+           B, h, w, C, level, _stream())
+    return out
+
+
+def nchw_to_tok(grad, tok, B, h, w, C, level, accumulate=False):
+    assert grad.is_contiguous()
+    L.call("mtp_nchw_to_tok", grad.data_ptr(), int(grad.dtype == BF16), tok.data_ptr(), int(tok.dtype == BF16), int(tok.shape[-1]),
+           int(accumulate), B, h, w, C, level, _stream())
+    return tok
+
+
+def maxpool2_tok_fwd(x, B, h, w, C):
+    y = torch.empty(B * (h // 2) * (w // 2), C, device=x.device, dtype=F32)
+    L.call("mtp_maxpool2_tok_fwd", x.data_ptr(), y.data_ptr(), B, h, w, C, _stream())
+    return y
+
+
+def maxpool2_tok_bwd(x, dy, dx, B, h, w, C):
+    L.call("mtp_maxpool2_tok_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), B, h, w, C, _stream())
+    return dx

@@ -1,0 +1,124 @@
+"""RVSA window attention and dense rel-pos attention kernels vs the oracle's pieces (fp32, same bf16-rounded qkv)."""
+import pytest
+import torch
+
+from oracle import rvsa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _attn_params(C, nH, gh, seed, big_sampling=1.0):
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    pre = "a."
+    P[pre + "qkv.weight"] = torch.randn(3 * C, C, generator=g) * 0.05
+    P[pre + "qkv.bias"] = torch.randn(3 * C, generator=g) * 0.1
+    P[pre + "proj.weight"] = torch.eye(C)
+    P[pre + "proj.bias"] = torch.zeros(C)
+    P[pre + "rel_pos_h"] = torch.randn(13, 64, generator=g) * 0.1
+    P[pre + "rel_pos_w"] = torch.randn(13, 64, generator=g) * 0.1
+    P[pre + "relative_position_bias_table"] = torch.randn(169, nH, generator=g) * 0.2
+    for name, oc in (("sampling_offsets", 2 * nH), ("sampling_scales", 2 * nH), ("sampling_angles", nH)):
+        P[pre + name + ".2.weight"] = torch.randn(oc, C, 1, 1, generator=g) * 0.05 * big_sampling
+        P[pre + name + ".2.bias"] = torch.randn(oc, generator=g) * 0.1 * big_sampling
+    P[pre + "full_attn_rel_pos_h"] = torch.randn(2 * gh - 1, 64, generator=g) * 0.1
+    P[pre + "full_attn_rel_pos_w"] = torch.randn(2 * gh - 1, 64, generator=g) * 0.1
+    return P
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("grid,B,nH,big", [(14, 2, 2, 1.0), (10, 3, 2, 1.0), (20, 1, 3, 1.0), (14, 2, 2, 6.0), (32, 1, 2, 3.0)])
+def test_rvsa_attention_vs_oracle(grid, B, nH, big):
+    """Covers no-pad (14), pad 2+2 (10->14), pad 0+1 (20->21), 1+2 (32->35) and large offsets that push taps out of the image."""
+    from mtp_b200 import ops
+    C = nH * 64
+    P = _attn_params(C, nH, grid, seed=grid + nH, big_sampling=big)
+    torch.manual_seed(0)
+    xn = _bf16_round(torch.randn(B, grid * grid, C))
+    # the oracle runs on the same bf16-rounded qkv the kernel reads
+    qkv = _bf16_round(xn @ P["a.qkv.weight"].t() + P["a.qkv.bias"])
+    want = _oracle_rvsa_from_qkv(xn, qkv, P, "a.", grid, grid, nH)
+    dev = "cuda"
+    d = lambda t: t.to(dev).contiguous()
+    params, pooled = ops.rvsa_sampling_fwd(d(xn.reshape(-1, C)).to(torch.bfloat16),
+                                           d(P["a.sampling_offsets.2.weight"].reshape(-1, C)), d(P["a.sampling_offsets.2.bias"]),
+                                           d(P["a.sampling_scales.2.weight"].reshape(-1, C)), d(P["a.sampling_scales.2.bias"]),
+                                           d(P["a.sampling_angles.2.weight"].reshape(-1, C)), d(P["a.sampling_angles.2.bias"]),
+                                           B, grid, grid, nH)
+    out, lse = ops.rvsa_attn_fwd(d(qkv.reshape(-1, 3 * C)).to(torch.bfloat16), params, d(P["a.rel_pos_h"]), d(P["a.rel_pos_w"]),
+                                 d(P["a.relative_position_bias_table"]), B, grid, grid, nH)
+    torch.cuda.synchronize()
+    got = out.float().cpu().reshape(B, grid * grid, C)
+    err = (got - want).abs()
+    assert err.max().item() < 2e-2          # bf16 output rounding of O(1) values
+    assert (err.norm() / want.norm()).item() < 4e-3
+    # sampling params against the oracle
+    pt, pb, pl, pr = O.window_padding(grid, grid)
+    xg = torch.nn.functional.pad(xn.reshape(B, grid, grid, C), (0, 0, pl, pr, pt, pb))
+    ox, oy, sx, sy, th = O.sampling_params(xg, P, "a.", nH, grid, grid)
+    ref = torch.stack([ox, oy, sx, sy, th], -1).reshape(-1, nH, 5)
+    assert (params[:, :, :5].cpu() - ref).abs().max().item() < 1e-4
+
+
+def _oracle_rvsa_from_qkv(xn, qkv, P, pre, h, w, nH):
+    """oracle.rvsa_attention with the qkv projection replaced by a given (bf16-rounded) qkv tensor."""
+    B, N, C = xn.shape
+    import torch.nn.functional as F
+    hd = C // nH
+    pt, pb, pl, pr = O.window_padding(h, w)
+    Hq, Wq = h + pt + pb, w + pl + pr
+    nh, nw = Hq // 7, Wq // 7
+    xg = F.pad(xn.reshape(B, h, w, C), (0, 0, pl, pr, pt, pb))
+    ox, oy, sx, sy, th = O.sampling_params(xg, P, pre, nH, h, w)
+    px, py = O.rvsa_coords(ox, oy, sx, sy, th, Hq, Wq)
+    q4 = F.pad(qkv.reshape(B, h, w, 3, nH, hd), (0, 0, 0, 0, 0, 0, pl, pr, pt, pb))
+    q, k, v = (q4[:, :, :, i].permute(0, 3, 1, 2, 4) for i in range(3))
+    G = B * nH
+    pxf, pyf = px.reshape(G, Hq * Wq), py.reshape(G, Hq * Wq)
+    ks = O.bilinear_gather(k.reshape(G, Hq, Wq, hd), pxf, pyf).reshape(B, nH, nh, 7, nw, 7, hd)
+    vs = O.bilinear_gather(v.reshape(G, Hq, Wq, hd), pxf, pyf).reshape(B, nH, nh, 7, nw, 7, hd)
+    win = lambda t: t.permute(0, 2, 4, 1, 3, 5, 6).reshape(B, nh, nw, nH, 49, hd)
+    qw, kw, vw = win(q.reshape(B, nH, nh, 7, nw, 7, hd)), win(ks), win(vs)
+    S = hd ** -0.5 * (qw @ kw.transpose(-1, -2))
+    iy = torch.arange(7).repeat_interleave(7)
+    ix = torch.arange(7).repeat(7)
+    Rh = P[pre + "rel_pos_h"][(iy[:, None] - torch.arange(7)[None, :]) + 6]
+    Rw = P[pre + "rel_pos_w"][(ix[:, None] - torch.arange(7)[None, :]) + 6]
+    S = S + torch.einsum("...qc,qkc->...qk", qw, Rh)[..., :, iy] + torch.einsum("...qc,qkc->...qk", qw, Rw)[..., :, ix]
+    idx = (iy[:, None] - iy[None, :] + 6) * 13 + (ix[:, None] - ix[None, :] + 6)
+    S = S + P[pre + "relative_position_bias_table"][idx.reshape(-1)].reshape(49, 49, nH).permute(2, 0, 1)
+    Oo = torch.softmax(S, -1) @ vw
+    Oo = Oo.reshape(B, nh, nw, nH, 7, 7, hd).permute(0, 1, 4, 2, 5, 3, 6).reshape(B, Hq, Wq, C)
+    return Oo[:, pt:pt + h, pl:pl + w].reshape(B, N, C)
+
+
+@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 3, 3, True), (14, 1, 2, False), (32, 1, 2, True)])
+def test_full_attention_vs_oracle(grid, B, nH, rel):
+    from mtp_b200 import ops
+    C = nH * 64
+    P = _attn_params(C, nH, grid, seed=7 + grid)
+    torch.manual_seed(1)
+    N = grid * grid
+    qkv = _bf16_round(torch.randn(B, N, 3 * C))
+    q, k, v = (qkv.reshape(B, N, 3, nH, 64).permute(2, 0, 3, 1, 4)[i] for i in range(3))
+    q = q * 0.125
+    S = q @ k.transpose(-1, -2)
+    if rel:
+        ty = torch.arange(grid).repeat_interleave(grid)
+        tx = torch.arange(grid).repeat(grid)
+        Rh = P["a.full_attn_rel_pos_h"][(ty[:, None] - torch.arange(grid)[None, :]) + grid - 1]
+        Rw = P["a.full_attn_rel_pos_w"][(tx[:, None] - torch.arange(grid)[None, :]) + grid - 1]
+        S = S + torch.einsum("bnqc,qkc->bnqk", q, Rh)[..., :, ty] + torch.einsum("bnqc,qkc->bnqk", q, Rw)[..., :, tx]
+    want = (torch.softmax(S, -1) @ v).transpose(1, 2).reshape(B, N, C)
+    want_lse = torch.logsumexp(S, -1)
+    d = lambda t: t.cuda().contiguous()
+    out, lse = ops.full_attn_fwd(d(qkv.reshape(-1, 3 * C)).to(torch.bfloat16),
+                                 d(P["a.full_attn_rel_pos_h"]) if rel else None, d(P["a.full_attn_rel_pos_w"]) if rel else None,
+                                 B, grid, grid, nH)
+    torch.cuda.synchronize()
+    got = out.float().cpu().reshape(B, N, C)
+    assert ((got - want).norm() / want.norm()).item() < 4e-3
+    assert (lse.cpu() - want_lse).abs().max().item() < 1e-3

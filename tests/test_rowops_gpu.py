@@ -59,7 +59,7 @@ def test_casts_and_colsums():
     cs = torch.zeros(C, device="cuda")
     y = ops.scale_cast_bf16(x, keep, ntok, cs)
     ref = x * keep.repeat_interleave(ntok)[:, None]
-    assert (y.float() - ref).abs().max().item() <= 0.02
+    assert ((y.float() - ref).abs() <= 4e-3 * ref.abs() + 1e-6).all()
     assert (cs - ref.sum(0)).abs().max().item() < 1e-3
     cs2 = torch.zeros(C, device="cuda")
     ops.colsum_bf16(y, cs2)
