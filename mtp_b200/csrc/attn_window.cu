@@ -251,7 +251,7 @@ extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, co
                                      const float* b_scale, const float* w_angle, const float* b_angle, float* pooled,
                                      float* params, int B, int h, int w, int C, int nH, mtp_stream_t stream) {
   MTP_REQUIRE(yn_bf16 && w_off && b_off && w_scale && b_scale && w_angle && b_angle && params, "mtp_rvsa_sampling_fwd: null pointer");
-  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C % 128 == 0 && C == nH * HD, "mtp_rvsa_sampling_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported (need h,w>=7, C==64*nH)", B, h, w, C, nH);
+  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD, "mtp_rvsa_sampling_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported (need h,w>=7, C==64*nH)", B, h, w, C, nH);
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   rvsa_sampling_fwd_kernel<<<B * g.nh * g.nw, 256, C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(yn_bf16), w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g);

@@ -30,7 +30,7 @@ def _bf16_round(t):
     return t.to(torch.bfloat16).float()
 
 
-@pytest.mark.parametrize("grid,B,nH,big", [(14, 2, 2, 1.0), (10, 3, 2, 1.0), (20, 1, 3, 1.0), (14, 2, 2, 6.0), (32, 1, 2, 3.0)])
+@pytest.mark.parametrize("grid,B,nH,big", [(14, 2, 2, 1.0), (10, 3, 2, 1.0), (20, 1, 4, 1.0), (14, 2, 2, 6.0), (32, 1, 2, 3.0)])
 def test_rvsa_attention_vs_oracle(grid, B, nH, big):
     """Covers no-pad (14), pad 2+2 (10->14), pad 0+1 (20->21), 1+2 (32->35) and large offsets that push taps out of the image."""
     from mtp_b200 import ops

@@ -56,4 +56,4 @@ def test_maxpool_fwd_bwd():
     ref.backward(dy)
     dx = torch.ones(B * h * w, C, device="cuda")
     ops.maxpool2_tok_bwd(x.reshape(-1, C), dy.permute(0, 2, 3, 1).reshape(-1, C).contiguous(), dx, B, h, w, C)
-    assert torch.equal(dx.reshape(B, h, w, C).permute(0, 3, 1, 2) - 1, xr.grad)
+    assert (dx.reshape(B, h, w, C).permute(0, 3, 1, 2) - 1 - xr.grad).abs().max().item() < 1e-6
