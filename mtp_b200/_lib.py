@@ -42,6 +42,14 @@ _SIGNATURES = {
     "mtp_nchw_to_tok": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_maxpool2_tok_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_maxpool2_tok_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_rvsa_attn_bwd": [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
+    "mtp_rvsa_sampling_bwd": [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
+    "mtp_full_attn_bwd": [c_void_p] * 10 + [c_int] * 5 + [c_void_p],
+}
+_SIZE_FNS = {
+    "mtp_rvsa_bwd_workspace_bytes": [c_int] * 5,
+    "mtp_rvsa_sampling_bwd_workspace_bytes": [c_int] * 5,
+    "mtp_full_attn_bwd_workspace_bytes": [c_int] * 4,
 }
 
 _lib = None
@@ -64,12 +72,16 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = c_int
+    for name, args in _SIZE_FNS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_size_t
     _lib = lib
     return lib
 
 
 def exported_symbols():
-    return ["mtp_last_error", "mtp_version", "mtp_num_sms"] + list(_SIGNATURES)
+    return ["mtp_last_error", "mtp_version", "mtp_num_sms"] + list(_SIGNATURES) + list(_SIZE_FNS)
 
 
 def check(rc, what=""):

@@ -1,0 +1,195 @@
+"""Backward pass of the backbone over the C-ABI kernels: the autograd of ViT_Win_RVSA_V3_WSZ7.forward_features
+([V]:787-813) written out by hand, block by block in reverse.
+
+Per block (cotangent of the fp32 residual stream comes in as ``dx``):
+  MLP branch   g = bf16(keep * dx) [+ fc2 bias grad]  ->  fc2 wgrad (MN,MN GEMM)  ->  fc2 dgrad fused with GELU' (K,MN GEMM)
+               -> fc1 bias grad, fc1 wgrad, fc1 dgrad -> LayerNorm backward fused with the residual-path add
+  attn branch  g = bf16(keep * dx) [+ proj bias grad] ->  proj wgrad / dgrad -> attention backward (RVSA or dense)
+               -> qkv bias grad, wgrad, dgrad (+ pooled sampling-head path) -> LayerNorm backward + residual add
+Feature-pyramid cotangents are folded into ``dx`` lazily at the block they were tapped from (their last kernel
+accumulates straight into the residual-stream gradient).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import engine, ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class GradStore:
+    """fp32 gradient tensors, one per parameter, carved out of a single flat buffer (16-byte aligned views)."""
+
+    def __init__(self, module, device):
+        self.names, self.views = [], {}
+        offs, total = [], 0
+        plist = list(module.named_parameters())
+        for name, p in plist:
+            offs.append(total)
+            total += (p.numel() + 63) // 64 * 64
+        self.flat = torch.zeros(total, device=device, dtype=F32)
+        for (name, p), o in zip(plist, offs):
+            self.names.append(name)
+            self.views[name] = self.flat[o:o + p.numel()].view(p.shape)
+        self.touched = set()
+
+    def g(self, name):
+        self.touched.add(name)
+        return self.views[name]
+
+
+def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_BF16, aux=None, want_dx=True):
+    """y = x W^T + b with x [T, n_in], W [n_out, n_in], cotangent g [T, n_out].
+    dW = g^T x (both operands MN-major, K = T); dx = g W (B operand MN-major)."""
+    ops.gemm(g_bf16, x_bf16, n_out, n_in, T, dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=n_out, ldb=n_in, ldo=n_in)
+    if not want_dx:
+        return None
+    dx = torch.empty(T, n_in, device=g_bf16.device, dtype=BF16)
+    ops.gemm(g_bf16, w_bf16, T, n_in, n_out, dx, b_mn=True, mode=dgrad_mode, aux=aux, lda=n_out, ldb=n_in)
+    return dx
+
+
+def _block_backward(i, d, s, dx2, G, B, gh, gw, nH, keep):
+    pre = f"blocks.{i}."
+    T, C = dx2.shape
+    N = gh * gw
+    hid = d["fc1_w"].shape[0]
+    km = keep[i, 1] if keep is not None else None
+    ka = keep[i, 0] if keep is not None else None
+    # ---- MLP branch ([V]:509)
+    g2 = ops.scale_cast_bf16(dx2, km, N, colsum=G.g(pre + "mlp.fc2.bias"))
+    dh = _linear_bwd(g2, s["a"], d["fc2_w"], G.g(pre + "mlp.fc2.weight"), T, C, hid, dgrad_mode=L.EPI_BF16_DGELU, aux=s["hpre"])
+    ops.colsum_bf16(dh, G.g(pre + "mlp.fc1.bias"))
+    dy2 = _linear_bwd(dh, s["y2"], d["fc1_w"], G.g(pre + "mlp.fc1.weight"), T, hid, C)
+    dx1 = ops.layernorm_bwd(dy2, s["x1"], s["mean2"], s["rstd2"], d["norm2_w"], None, dx2, G.g(pre + "norm2.weight"), G.g(pre + "norm2.bias"))
+    # ---- attention branch ([V]:508)
+    g1 = ops.scale_cast_bf16(dx1, ka, N, colsum=G.g(pre + "attn.proj.bias"))
+    do = _linear_bwd(g1, s["o"], d["proj_w"], G.g(pre + "attn.proj.weight"), T, C, C)
+    if d["window"]:
+        dqkv, dparams = ops.rvsa_attn_bwd(s["qkv"], s["params"], d["rel_h"], d["rel_w"], d["table"], s["lse"], do,
+                                          G.g(pre + "attn.rel_pos_h"), G.g(pre + "attn.rel_pos_w"),
+                                          G.g(pre + "attn.relative_position_bias_table"), B, gh, gw, nH)
+    else:
+        has_rel = d["rel_h"] is not None
+        dqkv = ops.full_attn_bwd(s["qkv"], d["rel_h"], d["rel_w"], s["lse"], s["o"], do,
+                                 G.g(pre + "attn.full_attn_rel_pos_h") if has_rel else None,
+                                 G.g(pre + "attn.full_attn_rel_pos_w") if has_rel else None, B, gh, gw, nH)
+    ops.colsum_bf16(dqkv, G.g(pre + "attn.qkv.bias"))
+    dy1 = _linear_bwd(dqkv, s["y1"], d["qkv_w"], G.g(pre + "attn.qkv.weight"), T, 3 * C, C)
+    if d["window"]:
+        a = pre + "attn.sampling_"
+        ops.rvsa_sampling_bwd(dparams, s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],
+                              G.g(a + "offsets.2.weight"), G.g(a + "offsets.2.bias"), G.g(a + "scales.2.weight"), G.g(a + "scales.2.bias"),
+                              G.g(a + "angles.2.weight"), G.g(a + "angles.2.bias"), dy1, B, gh, gw, nH)
+    dx0 = ops.layernorm_bwd(dy1, s["x0"], s["mean1"], s["rstd1"], d["norm1_w"], None, dx1, G.g(pre + "norm1.weight"), G.g(pre + "norm1.bias"))
+    return dx0
+
+
+def _convt_grads(G, wname, bname, dWp, colsum4):
+    """Unpack the GEMM-layout gradients of a ConvTranspose2d(k2,s2): dWp [4*Cout, Cin] -> (Cin, Cout, 2, 2); bias = sum of 4 groups."""
+    cout = dWp.shape[0] // 4
+    G.g(wname).copy_(dWp.view(2, 2, cout, dWp.shape[1]).permute(3, 2, 0, 1))
+    G.g(bname).copy_(colsum4.view(4, cout).sum(0))
+
+
+def _fpn_tap_backward(m, W, S, k, grad, dx, G, B, gh, gw):
+    """Fold the cotangent of pyramid level k into dx (fp32 [T, C], accumulated in place)."""
+    C = W.C
+    T = B * gh * gw
+    grad = grad.contiguous()
+    dev = dx.device
+    if not m.apply_fpn or k == 2:
+        ops.nchw_to_tok(grad, dx, B, gh, gw, C, 0, accumulate=True)
+        return
+    F_, sv = W.fpn, S["fpn"]
+    if k == 3:
+        ho, wo = gh // 2, gw // 2
+        dp = torch.empty(B * ho * wo, C, device=dev, dtype=F32)
+        ops.nchw_to_tok(grad, dp, B, ho, wo, C, 0)
+        ops.maxpool2_tok_bwd(sv["f3"], dp, dx, B, gh, gw, C)
+        return
+    if k == 1:
+        dv1 = torch.empty(T, 4 * C, device=dev, dtype=BF16)
+        ops.nchw_to_tok(grad, dv1, B, gh, gw, C, 1)
+        cs = torch.zeros(4 * C, device=dev, dtype=F32)
+        ops.colsum_bf16(dv1, cs)
+        dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
+        ops.gemm(dv1, sv["a1"], 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C)
+        _convt_grads(G, "fpn2.0.weight", "fpn2.0.bias", dWp, cs)
+        ops.gemm(dv1, F_["fpn2_0_w"], T, C, 4 * C, dx, b_mn=True, mode=L.EPI_F32, accumulate=True, lda=4 * C, ldb=C)
+        return
+    # k == 0: ConvT -> LN -> GELU -> ConvT
+    du2 = torch.empty(4 * T, 4 * C, device=dev, dtype=BF16)
+    ops.nchw_to_tok(grad, du2, B, gh, gw, C, 2)
+    cs = torch.zeros(4 * C, device=dev, dtype=F32)
+    ops.colsum_bf16(du2, cs)
+    dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
+    ops.gemm(du2, sv["z"], 4 * C, C, 4 * T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C)
+    _convt_grads(G, "fpn1.3.weight", "fpn1.3.bias", dWp, cs)
+    dz = torch.empty(4 * T, C, device=dev, dtype=BF16)
+    ops.gemm(du2, F_["fpn1_3_w"], 4 * T, C, 4 * C, dz, b_mn=True, lda=4 * C, ldb=C)
+    du1 = ops.layernorm_bwd(dz, sv["u1"].view(4 * T, C), sv["mean"], sv["rstd"], F_["ln_w"], F_["ln_b"], None,
+                            G.g("fpn1.1.ln.weight"), G.g("fpn1.1.ln.bias"), gelu=True).view(T, 4 * C)
+    cs = torch.zeros(4 * C, device=dev, dtype=F32)
+    ops.colsum_bf16(du1, cs)
+    dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
+    ops.gemm(du1, sv["a0"], 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C)
+    _convt_grads(G, "fpn1.0.weight", "fpn1.0.bias", dWp, cs)
+    ops.gemm(du1, F_["fpn1_0_w"], T, C, 4 * C, dx, b_mn=True, mode=L.EPI_F32, accumulate=True, lda=4 * C, ldb=C)
+
+
+def backward_impl(m, x, S, grad_outs):
+    """Returns fp32 gradients in ``m.parameters()`` order (None where a parameter does not take part)."""
+    W = S["W"]
+    B, gh, gw, keep = S["B"], S["gh"], S["gw"], S["keep"]
+    C, nH = W.C, W.nH
+    T = B * gh * gw
+    dev = x.device
+    G = GradStore(m, dev)
+    grad_outs = list(grad_outs)
+
+    dx = None
+    if m.feature_mode == "last_norm":
+        acc = torch.zeros(T, C, device=dev, dtype=F32)
+        for k, g in enumerate(grad_outs):
+            if g is not None:
+                _fpn_tap_backward(m, W, S, k, g, acc, G, B, gh, gw)
+        fin = S["final"]
+        dyl = ops.scale_cast_bf16(acc)
+        dx = ops.layernorm_bwd(dyl, fin["x"], fin["mean"], fin["rstd"], W.norm_w, None, None, G.g("norm.weight"), G.g("norm.bias"))
+        taps = {}
+    else:
+        taps = {blk: k for k, blk in enumerate(m.out_indices)}
+
+    for i in range(W.depth - 1, -1, -1):
+        if i in taps and grad_outs[taps[i]] is not None:
+            if dx is None:
+                dx = torch.zeros(T, C, device=dev, dtype=F32)
+            _fpn_tap_backward(m, W, S, taps[i], grad_outs[taps[i]], dx, G, B, gh, gw)
+        if dx is None:
+            continue                      # blocks above the highest tapped block receive no gradient
+        s = S["blocks"][i]
+        if S["ckpt"]:                     # activation checkpointing: recompute this block's activations ([V]:799-800)
+            ka = keep[i, 0] if keep is not None else None
+            km = keep[i, 1] if keep is not None else None
+            _, s = engine._block_forward(W.blocks[i], s["x0"], B, gh, gw, nH, ka, km, save=True)
+        dx = _block_backward(i, W.blocks[i], s, dx, G, B, gh, gw, nH, keep)
+        S["blocks"][i] = None             # release activations as we go
+
+    if dx is not None:
+        # patch embed + pos_embed ([V]:790-794)
+        g = ops.scale_cast_bf16(dx, None, 0, colsum=G.g("patch_embed.proj.bias"))
+        if W.pos is not None:
+            dpos = G.g("pos_embed").view(-1)
+            scratch = torch.empty(B, gh * gw * C, device=dev, dtype=BF16)
+            L.call("mtp_scale_cast_bf16", dx.data_ptr(), 0, 0, scratch.data_ptr(), dpos.data_ptr(), B, gh * gw * C, ops._stream())
+        K0 = S["patches"].shape[1]
+        ops.gemm(g, S["patches"], C, K0, T, G.g("patch_embed.proj.weight").view(C, K0), a_mn=True, b_mn=True, mode=L.EPI_F32,
+                 lda=C, ldb=K0, ldo=K0)
+
+    out = []
+    for (name, p) in m.named_parameters():
+        out.append(G.views[name] if (p.requires_grad and name in G.touched) else None)
+    return out

@@ -138,3 +138,37 @@ def maxpool2_tok_fwd(x, B, h, w, C):
 def maxpool2_tok_bwd(x, dy, dx, B, h, w, C):
     L.call("mtp_maxpool2_tok_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), B, h, w, C, _stream())
     return dx
+
+
+# ---------------------------------------------------------------------------------------------- attention backward
+def _workspace(nbytes, device):
+    return torch.empty((nbytes + 3) // 4, device=device, dtype=F32)
+
+
+def rvsa_attn_bwd(qkv, params, rel_h, rel_w, table, lse, dout, d_rel_h, d_rel_w, d_table, B, h, w, nH):
+    C = qkv.shape[-1] // 3
+    dqkv = torch.empty_like(qkv)
+    dparams = torch.zeros_like(params)
+    ws = _workspace(L.load().mtp_rvsa_bwd_workspace_bytes(B, h, w, C, nH), qkv.device)
+    L.call("mtp_rvsa_attn_bwd", qkv.data_ptr(), params.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(), table.data_ptr(), lse.data_ptr(),
+           dout.data_ptr(), dqkv.data_ptr(), dparams.data_ptr(), d_rel_h.data_ptr(), d_rel_w.data_ptr(), d_table.data_ptr(),
+           ws.data_ptr(), B, h, w, C, nH, _stream())
+    return dqkv, dparams
+
+
+def rvsa_sampling_bwd(dparams, pooled, w_off, w_sc, w_ang, dw_off, db_off, dw_sc, db_sc, dw_ang, db_ang, dyn, B, h, w, nH):
+    C = pooled.shape[-1]
+    ws = _workspace(L.load().mtp_rvsa_sampling_bwd_workspace_bytes(B, h, w, C, nH), pooled.device)
+    L.call("mtp_rvsa_sampling_bwd", dparams.data_ptr(), pooled.data_ptr(), w_off.data_ptr(), w_sc.data_ptr(), w_ang.data_ptr(),
+           dw_off.data_ptr(), db_off.data_ptr(), dw_sc.data_ptr(), db_sc.data_ptr(), dw_ang.data_ptr(), db_ang.data_ptr(),
+           dyn.data_ptr(), ws.data_ptr(), B, h, w, C, nH, _stream())
+    return dyn
+
+
+def full_attn_bwd(qkv, rel_h, rel_w, lse, out, dout, d_rel_h, d_rel_w, B, gh, gw, nH):
+    C = qkv.shape[-1] // 3
+    dqkv = torch.empty_like(qkv)
+    ws = _workspace(L.load().mtp_full_attn_bwd_workspace_bytes(B, gh, gw, nH), qkv.device)
+    L.call("mtp_full_attn_bwd", qkv.data_ptr(), _p(rel_h), _p(rel_w), lse.data_ptr(), out.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
+           _p(d_rel_h), _p(d_rel_w), ws.data_ptr(), B, gh, gw, C, nH, _stream())
+    return dqkv

@@ -122,3 +122,96 @@ def test_full_attention_vs_oracle(grid, B, nH, rel):
     got = out.float().cpu().reshape(B, N, C)
     assert ((got - want).norm() / want.norm()).item() < 4e-3
     assert (lse.cpu() - want_lse).abs().max().item() < 1e-3
+
+
+def _close(got, want, rel, name):
+    err = (got - want).norm().item() / max(want.norm().item(), 1e-20)
+    assert err < rel, f"{name}: rel-L2 {err:.3e} >= {rel}"
+    return err
+
+
+@pytest.mark.parametrize("grid,B,nH,big", [(14, 2, 2, 1.0), (10, 2, 2, 2.0), (20, 1, 4, 1.0), (14, 1, 2, 6.0)])
+def test_rvsa_backward_vs_oracle_autograd(grid, B, nH, big):
+    from mtp_b200 import ops
+    C = nH * 64
+    P = _attn_params(C, nH, grid, seed=100 + grid + nH, big_sampling=big)
+    torch.manual_seed(5)
+    N = grid * grid
+    xn = _bf16_round(torch.randn(B, N, C)).requires_grad_(True)
+    qkv = _bf16_round(torch.randn(B, N, 3 * C)).requires_grad_(True)
+    leaf_names = ["a.rel_pos_h", "a.rel_pos_w", "a.relative_position_bias_table"] + \
+        [f"a.sampling_{k}.2.{w}" for k in ("offsets", "scales", "angles") for w in ("weight", "bias")]
+    Pl = dict(P)
+    for k in leaf_names:
+        Pl[k] = P[k].clone().requires_grad_(True)
+    out = _oracle_rvsa_from_qkv(xn, qkv, Pl, "a.", grid, grid, nH)
+    gout = _bf16_round(torch.randn(B, N, C))
+    (out * gout).sum().backward()
+
+    d = lambda t: t.detach().cuda().contiguous()
+    params, pooled = ops.rvsa_sampling_fwd(d(xn.reshape(-1, C)).to(torch.bfloat16),
+                                           d(P["a.sampling_offsets.2.weight"].reshape(-1, C)), d(P["a.sampling_offsets.2.bias"]),
+                                           d(P["a.sampling_scales.2.weight"].reshape(-1, C)), d(P["a.sampling_scales.2.bias"]),
+                                           d(P["a.sampling_angles.2.weight"].reshape(-1, C)), d(P["a.sampling_angles.2.bias"]),
+                                           B, grid, grid, nH)
+    qkv_d = d(qkv.reshape(-1, 3 * C)).to(torch.bfloat16)
+    rel_h, rel_w, table = d(P["a.rel_pos_h"]), d(P["a.rel_pos_w"]), d(P["a.relative_position_bias_table"])
+    _, lse = ops.rvsa_attn_fwd(qkv_d, params, rel_h, rel_w, table, B, grid, grid, nH)
+    z = lambda t: torch.zeros_like(t)
+    g_rel_h, g_rel_w, g_table = z(rel_h), z(rel_w), z(table)
+    dqkv, dparams = ops.rvsa_attn_bwd(qkv_d, params, rel_h, rel_w, table, lse, d(gout.reshape(-1, C)).to(torch.bfloat16),
+                                      g_rel_h, g_rel_w, g_table, B, grid, grid, nH)
+    w = {k: d(P[f"a.sampling_{k}.2.weight"].reshape(-1, C)) for k in ("offsets", "scales", "angles")}
+    gw = {k: z(v) for k, v in w.items()}
+    gb = {k: torch.zeros(v.shape[0], device="cuda") for k, v in w.items()}
+    dyn = torch.zeros(B * N, C, device="cuda", dtype=torch.bfloat16)
+    ops.rvsa_sampling_bwd(dparams, pooled, w["offsets"], w["scales"], w["angles"], gw["offsets"], gb["offsets"], gw["scales"], gb["scales"],
+                          gw["angles"], gb["angles"], dyn, B, grid, grid, nH)
+    torch.cuda.synchronize()
+    errs = {}
+    errs["dqkv"] = _close(dqkv.float().cpu().reshape(B, N, 3 * C), qkv.grad, 1.5e-2, "dqkv")
+    errs["rel_h"] = _close(g_rel_h.cpu(), Pl["a.rel_pos_h"].grad, 2e-3, "d rel_pos_h")
+    errs["rel_w"] = _close(g_rel_w.cpu(), Pl["a.rel_pos_w"].grad, 2e-3, "d rel_pos_w")
+    errs["table"] = _close(g_table.cpu(), Pl["a.relative_position_bias_table"].grad, 2e-3, "d bias table")
+    for k in ("offsets", "scales", "angles"):
+        errs[k + "_w"] = _close(gw[k].cpu(), Pl[f"a.sampling_{k}.2.weight"].grad.reshape(-1, C), 5e-3, f"d sampling_{k}.weight")
+        errs[k + "_b"] = _close(gb[k].cpu(), Pl[f"a.sampling_{k}.2.bias"].grad, 5e-3, f"d sampling_{k}.bias")
+    errs["dyn"] = _close(dyn.float().cpu().reshape(B, N, C), xn.grad, 1.5e-2, "pooled-path grad")
+    print("rvsa bwd", grid, {k: "%.1e" % v for k, v in errs.items()})
+
+
+@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 1, 3, True), (14, 1, 2, False), (20, 1, 2, True)])
+def test_full_attention_backward_vs_autograd(grid, B, nH, rel):
+    from mtp_b200 import ops
+    C = nH * 64
+    P = _attn_params(C, nH, grid, seed=200 + grid)
+    torch.manual_seed(6)
+    N = grid * grid
+    qkv = _bf16_round(torch.randn(B, N, 3 * C)).requires_grad_(True)
+    Rh_p = P["a.full_attn_rel_pos_h"].clone().requires_grad_(True)
+    Rw_p = P["a.full_attn_rel_pos_w"].clone().requires_grad_(True)
+    q, k, v = (qkv.reshape(B, N, 3, nH, 64).permute(2, 0, 3, 1, 4)[i] for i in range(3))
+    q = q * 0.125
+    S = q @ k.transpose(-1, -2)
+    if rel:
+        ty = torch.arange(grid).repeat_interleave(grid)
+        tx = torch.arange(grid).repeat(grid)
+        Rh = Rh_p[(ty[:, None] - torch.arange(grid)[None, :]) + grid - 1]
+        Rw = Rw_p[(tx[:, None] - torch.arange(grid)[None, :]) + grid - 1]
+        S = S + torch.einsum("bnqc,qkc->bnqk", q, Rh)[..., :, ty] + torch.einsum("bnqc,qkc->bnqk", q, Rw)[..., :, tx]
+    out = (torch.softmax(S, -1) @ v).transpose(1, 2).reshape(B, N, C)
+    gout = _bf16_round(torch.randn(B, N, C))
+    (out * gout).sum().backward()
+    d = lambda t: t.detach().cuda().contiguous()
+    qkv_d = d(qkv.reshape(-1, 3 * C)).to(torch.bfloat16)
+    rh, rw = (d(Rh_p), d(Rw_p)) if rel else (None, None)
+    o, lse = ops.full_attn_fwd(qkv_d, rh, rw, B, grid, grid, nH)
+    g_rh = torch.zeros_like(rh) if rel else None
+    g_rw = torch.zeros_like(rw) if rel else None
+    dqkv = ops.full_attn_bwd(qkv_d, rh, rw, lse, o, d(gout.reshape(-1, C)).to(torch.bfloat16), g_rh, g_rw, B, grid, grid, nH)
+    torch.cuda.synchronize()
+    e = _close(dqkv.float().cpu().reshape(B, N, 3 * C), qkv.grad, 1.5e-2, "dqkv")
+    if rel:
+        _close(g_rh.cpu(), Rh_p.grad, 1e-2, "d full_attn_rel_pos_h")
+        _close(g_rw.cpu(), Rw_p.grad, 1e-2, "d full_attn_rel_pos_w")
+    print("full bwd", grid, "%.1e" % e)
