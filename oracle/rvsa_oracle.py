@@ -44,6 +44,10 @@ class OracleConfig:
     feature_mode: str = "multi"          # "multi" ([V]:804) | "last_norm" (mmdet RVSA_MTP)
     apply_fpn: bool = True               # mmpretrain / opencd twins skip the fpn ops
     ln_eps: float = 1e-6
+    # Test aid, not part of the reference: round to bf16 (straight-through for autograd) at exactly the points where the
+    # CUDA path stores bf16 (GEMM operands: weights, LN outputs, qkv, attention output, GELU output, fpn intermediates).
+    # With it the oracle predicts the CUDA path's forward to ~1e-3 and shares its bilinear-tap cell decisions.
+    emulate_bf16: bool = False
 
     @property
     def grid(self) -> int:
@@ -66,6 +70,15 @@ def vit_l_config(img_size=224, **kw) -> OracleConfig:      # [V]:843-865
 # ----------------------------------------------------------------------------------------------
 # elementary pieces
 # ----------------------------------------------------------------------------------------------
+
+def _ste_bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 in the forward pass, identity in the backward pass."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def _ident(t: torch.Tensor) -> torch.Tensor:
+    return t
+
 
 def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
     """nn.LayerNorm(eps=1e-6) over the last dim ([V]:596)."""
@@ -169,8 +182,9 @@ def rvsa_coords(ox, oy, sx, sy, th, Hq: int, Wq: int):
     return px, py
 
 
-def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: int, w: int, nH: int) -> torch.Tensor:
-    """RotatedVariedSizeWindowAttention.forward, [V]:287-433 / SURVEY.md A.1.  xn: LN'd (B, N, C)."""
+def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: int, w: int, nH: int, r=_ident) -> torch.Tensor:
+    """RotatedVariedSizeWindowAttention.forward, [V]:287-433 / SURVEY.md A.1.  xn: LN'd (B, N, C).
+    ``r`` is the identity (reference arithmetic) or the bf16 straight-through rounding of ``emulate_bf16``."""
     B, N, C = xn.shape
     hd = C // nH
     scale = hd ** -0.5
@@ -182,7 +196,7 @@ def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: in
     ox, oy, sx, sy, th = sampling_params(xg, P, pre, nH, h, w)
     px, py = rvsa_coords(ox, oy, sx, sy, th, Hq, Wq)                           # (B,nH,nh,7,nw,7)
 
-    qkv = xn @ P[pre + "qkv.weight"].t() + P[pre + "qkv.bias"]               # [V]:390
+    qkv = r(xn @ r(P[pre + "qkv.weight"]).t() + P[pre + "qkv.bias"])         # [V]:390
     qkv = qkv.reshape(B, h, w, 3, nH, hd)
     qkv = F.pad(qkv, (0, 0, 0, 0, 0, 0, pl, pr, pt, pb))                        # zero pad AFTER bias [V]:392
     q, k, v = (qkv[:, :, :, i].permute(0, 3, 1, 2, 4) for i in range(3))        # (B,nH,Hq,Wq,hd)
@@ -215,17 +229,17 @@ def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: in
     A = torch.softmax(S, dim=-1)
     O = A @ vw                                                                  # (B,nh,nw,nH,49,hd)
     O = O.reshape(B, nh, nw, nH, WS, WS, hd).permute(0, 1, 4, 2, 5, 3, 6).reshape(B, Hq, Wq, C)
-    O = O[:, pt:pt + h, pl:pl + w].reshape(B, N, C)                             # crop  [V]:426
-    return O @ P[pre + "proj.weight"].t() + P[pre + "proj.bias"]
+    O = r(O[:, pt:pt + h, pl:pl + w].reshape(B, N, C))                          # crop  [V]:426
+    return O @ r(P[pre + "proj.weight"]).t() + P[pre + "proj.bias"]
 
 
 def full_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: int, w: int, nH: int,
-                   use_rel_pos: bool = True) -> torch.Tensor:
+                   use_rel_pos: bool = True, r=_ident) -> torch.Tensor:
     """Attention.forward + calc_rel_pos_spatial, [V]:90-111,142-193 / SURVEY.md A.2."""
     B, N, C = xn.shape
     hd = C // nH
     scale = hd ** -0.5
-    qkv = xn @ P[pre + "qkv.weight"].t() + P[pre + "qkv.bias"]
+    qkv = r(xn @ r(P[pre + "qkv.weight"]).t() + P[pre + "qkv.bias"])
     qkv = qkv.reshape(B, N, 3, nH, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0] * scale, qkv[1], qkv[2]                                     # q scaled first [V]:100
     S = q @ k.transpose(-1, -2)
@@ -238,14 +252,14 @@ def full_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: in
         rel_w = torch.einsum("bnqc,qkc->bnqk", q, Rw)
         S = S + rel_h[..., :, ty] + rel_w[..., :, tx]
     A = torch.softmax(S, dim=-1)
-    O = (A @ v).transpose(1, 2).reshape(B, N, C)
-    return O @ P[pre + "proj.weight"].t() + P[pre + "proj.bias"]
+    O = r((A @ v).transpose(1, 2).reshape(B, N, C))
+    return O @ r(P[pre + "proj.weight"]).t() + P[pre + "proj.bias"]
 
 
-def mlp(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str) -> torch.Tensor:
+def mlp(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, r=_ident) -> torch.Tensor:
     """Mlp.forward, [V]:55-62."""
-    hdn = gelu_erf(xn @ P[pre + "fc1.weight"].t() + P[pre + "fc1.bias"])
-    return hdn @ P[pre + "fc2.weight"].t() + P[pre + "fc2.bias"]
+    hdn = r(gelu_erf(xn @ r(P[pre + "fc1.weight"]).t() + P[pre + "fc1.bias"]))
+    return hdn @ r(P[pre + "fc2.weight"]).t() + P[pre + "fc2.bias"]
 
 
 def conv_transpose_2x2(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -256,12 +270,12 @@ def conv_transpose_2x2(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> tor
     return o + b[None, :, None, None]
 
 
-def fpn_tail(feats: List[torch.Tensor], P: Dict[str, torch.Tensor], eps: float) -> List[torch.Tensor]:
+def fpn_tail(feats: List[torch.Tensor], P: Dict[str, torch.Tensor], eps: float, r=_ident) -> List[torch.Tensor]:
     """fpn1..fpn4 for patch_size 16 ([V]:640-654,807-811); Norm2d = LN over channels ([V]:576-584)."""
-    f1 = conv_transpose_2x2(feats[0], P["fpn1.0.weight"], P["fpn1.0.bias"])
+    f1 = r(conv_transpose_2x2(r(feats[0]), r(P["fpn1.0.weight"]), P["fpn1.0.bias"]))
     f1 = layer_norm(f1.permute(0, 2, 3, 1), P["fpn1.1.ln.weight"], P["fpn1.1.ln.bias"], eps).permute(0, 3, 1, 2)
-    f1 = conv_transpose_2x2(gelu_erf(f1), P["fpn1.3.weight"], P["fpn1.3.bias"])
-    f2 = conv_transpose_2x2(feats[1], P["fpn2.0.weight"], P["fpn2.0.bias"])
+    f1 = r(conv_transpose_2x2(r(gelu_erf(f1)), r(P["fpn1.3.weight"]), P["fpn1.3.bias"]))
+    f2 = r(conv_transpose_2x2(r(feats[1]), r(P["fpn2.0.weight"]), P["fpn2.0.bias"]))
     f3 = feats[2]
     B, C, H, W = feats[3].shape
     f4 = feats[3][:, :, :H // 2 * 2, :W // 2 * 2].reshape(B, C, H // 2, 2, W // 2, 2).amax(dim=(3, 5))
@@ -283,34 +297,35 @@ def backbone_forward(P: Dict[str, torch.Tensor], cfg: OracleConfig, x: torch.Ten
     B = x.shape[0]
     hp = wp = None
     C, nH = cfg.embed_dim, cfg.num_heads
-    t = patch_embed(x, P["patch_embed.proj.weight"], P["patch_embed.proj.bias"], cfg.patch_size)
+    r = _ste_bf16 if cfg.emulate_bf16 else _ident
+    t = patch_embed(r(x), r(P["patch_embed.proj.weight"]), P["patch_embed.proj.bias"], cfg.patch_size)
     hp, wp = x.shape[2] // cfg.patch_size, x.shape[3] // cfg.patch_size
     if "pos_embed" in P:
         t = t + P["pos_embed"]                                                   # [V]:793-794
     feats = []
     for i in range(cfg.depth):
         pre = f"blocks.{i}."
-        xn = layer_norm(t, P[pre + "norm1.weight"], P[pre + "norm1.bias"], cfg.ln_eps)
+        xn = r(layer_norm(t, P[pre + "norm1.weight"], P[pre + "norm1.bias"], cfg.ln_eps))
         if cfg.is_window_block(i):
-            a = rvsa_attention(xn, P, pre + "attn.", hp, wp, nH)
+            a = rvsa_attention(xn, P, pre + "attn.", hp, wp, nH, r)
         else:
-            a = full_attention(xn, P, pre + "attn.", hp, wp, nH, cfg.full_attn_rel_pos)
+            a = full_attention(xn, P, pre + "attn.", hp, wp, nH, cfg.full_attn_rel_pos, r)
         if keep is not None:
             a = a * keep[i, 0].reshape(B, 1, 1)
         t = t + a                                                                # [V]:508
-        xn = layer_norm(t, P[pre + "norm2.weight"], P[pre + "norm2.bias"], cfg.ln_eps)
-        m = mlp(xn, P, pre + "mlp.")
+        xn = r(layer_norm(t, P[pre + "norm2.weight"], P[pre + "norm2.bias"], cfg.ln_eps))
+        m = mlp(xn, P, pre + "mlp.", r)
         if keep is not None:
             m = m * keep[i, 1].reshape(B, 1, 1)
         t = t + m                                                                # [V]:509
         if cfg.feature_mode == "multi" and i in cfg.out_indices:
             feats.append(t)
     if cfg.feature_mode == "last_norm":                                          # mmdet RVSA_MTP twin
-        last = layer_norm(t, P["norm.weight"], P["norm.bias"], cfg.ln_eps)
+        last = r(layer_norm(t, P["norm.weight"], P["norm.bias"], cfg.ln_eps))
         feats = [last, last, last, last]
     feats = [f.permute(0, 2, 1).reshape(B, C, hp, wp) for f in feats]            # [V]:807
     if cfg.apply_fpn:
-        return fpn_tail(feats, P, cfg.ln_eps)
+        return fpn_tail(feats, P, cfg.ln_eps, r)
     return [f.contiguous() for f in feats]
 
 
