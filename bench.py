@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ViT-L + RVSA backbone pretrain step @224^2, bf16, synthetic data (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores, same metric
+
+A "step" = one encoder call on an 8-image batch per GPU (global batch 64 at 8 GPUs, weak scaling) + synthetic heads +
+full backward + gradient all-reduce (N > 1) + global-norm clip + fused AdamW.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MODEL = dict(img_size=224, embed_dim=1024, depth=24, num_heads=16, interval=6, out_indices=[7, 11, 15, 23])
+PER_GPU_BATCH = 8
+FWD_GFLOP_PER_IMG = 130.20          # SURVEY.md Appendix C (oracle.algorithmic_gflop_per_image reproduces it)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
+    ap.add_argument("--graph", type=int, default=1, help="capture the step into a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=1, help="images per CPU-reference step (bounded sample)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        if not sm:
+            return None
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_rate(batch, steps, warmup, threads=None):
+    """The reference's CPU path (oracle port of [V], fp32) doing the same step: fwd + synthetic heads + bwd + AdamW."""
+    from oracle import rvsa_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = O.vit_l_config(224)
+    torch.manual_seed(0)
+    from mtp_b200 import ViT_Win_RVSA_V3_WSZ7
+    m = ViT_Win_RVSA_V3_WSZ7(img_size=224, patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4, qkv_bias=True,
+                             use_abs_pos_emb=True, interval=6, out_indices=[7, 11, 15, 23], drop_path_rate=0.1, use_rel_pos_bias=True)
+    P = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in m.state_dict().items()}
+    del m
+    params = [v for v in P.values() if v.is_floating_point()]
+    opt = torch.optim.AdamW(params, lr=6e-5, weight_decay=0.05)
+    x = torch.randn(batch, 3, 224, 224)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = O.synthetic_loss(O.backbone_forward(P, cfg, x))
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 5.0)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch / statistics.median(times), threads, sum(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    rate, threads, total = cpu_reference_rate(args.cpu_batch, args.steps, args.warmup)
+    ms = 1000.0 * args.cpu_batch / rate
+    sample = f"{args.cpu_batch} image(s) per step, ViT-L+RVSA @224 fwd+bwd+AdamW, fp32, {threads} threads"
+    line = {"impl": "reference", "metric": "images/sec ViT-L+RVSA MTP step @224^2", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "ViT-L+RVSA backbone pretrain step @224^2 (oracle port of the reference on host cores)",
+                       "per_step_batch": args.cpu_batch},
+            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ native arm
+def build_model(dev):
+    from mtp_b200 import ViT_Win_RVSA_V3_WSZ7
+    torch.manual_seed(0)
+    m = ViT_Win_RVSA_V3_WSZ7(img_size=224, patch_size=16, embed_dim=MODEL["embed_dim"], depth=MODEL["depth"], num_heads=MODEL["num_heads"],
+                             mlp_ratio=4, qkv_bias=True, use_abs_pos_emb=True, interval=MODEL["interval"],
+                             out_indices=MODEL["out_indices"], drop_path_rate=0.1, use_rel_pos_bias=True)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "rel_pos" in n:                      # zero-initialised in the reference: re-draw so the terms are exercised
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return m.to(dev).train()
+
+
+def gemm_profile(trainer, x):
+    """One eager (non-graph) step with CUDA events around every GEMM launch on the launching stream."""
+    from mtp_b200 import ops
+    recs = []
+    orig = ops.gemm
+
+    def timed(A, B, M, N, K, out, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig(A, B, M, N, K, out, **kw)
+        e1.record()
+        recs.append((e0, e1, 2.0 * M * N * K))
+        return r
+    ops.gemm = timed
+    try:
+        trainer._step_body(x)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+    ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+    flops = sum(f for _, _, f in recs)
+    return len(recs), ms, flops
+
+
+def count_launches(trainer, x):
+    """Kernels of libmtp_b200.so launched per step (entry point -> kernels it enqueues)."""
+    from mtp_b200 import _lib
+    per_call = {"mtp_rvsa_attn_bwd": 3, "mtp_rvsa_sampling_bwd": 3, "mtp_full_attn_bwd": 2}
+    n = [0]
+    orig = _lib.call
+
+    def counting(name, *a):
+        n[0] += per_call.get(name, 1)
+        return orig(name, *a)
+    _lib.call = counting           # ops / trainer / engine_bwd all call through the module attribute
+    try:
+        trainer._step_body(x)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call = orig
+    return n[0]
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mtp_b200 import _lib
+    from mtp_b200.trainer import PretrainStep
+    _lib.load()
+    B = args.batch
+    model = build_model(dev)
+    trainer = PretrainStep(model, lr=6e-5, weight_decay=0.05, max_norm=5.0, t_max=80000, use_cuda_graph=bool(args.graph))
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(B, 3, 224, 224, device=dev, generator=g).to(torch.bfloat16)
+    x_host = x.cpu().pin_memory()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- eager instrumented passes (also serve as warm-up for kernel attributes / allocator)
+    trainer_eager_graph = trainer.use_cuda_graph
+    trainer.use_cuda_graph = False
+    for _ in range(2):
+        trainer.step(x)
+    torch.cuda.synchronize()
+    launches = count_launches(trainer, x)
+    n_gemm, gemm_ms, gemm_flops = gemm_profile(trainer, x)
+    trainer.use_cuda_graph = trainer_eager_graph
+
+    # ---- device-resident timing
+    for _ in range(max(3, args.warmup)):
+        loss = trainer.step(x)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(x)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = world * B / (ms_step / 1e3)
+    final_loss = float(loss.item())
+
+    # ---- end to end: pinned host batch -> device -> step -> loss back on the host, every step
+    for _ in range(2):
+        trainer.step_from_host(x_host)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        trainer.step_from_host(x_host)
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (t.item() / args.steps / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        step_tflops = 3.0 * FWD_GFLOP_PER_IMG * (value / world) / 1e3          # per GPU, training step = 3 x forward
+        gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        line = {
+            "metric": "images/sec ViT-L+RVSA MTP step @224^2 bf16", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "ViT-L+RVSA backbone pretrain step @224^2: fwd + synthetic heads + bwd + grad all-reduce + clip + AdamW",
+                       "per_gpu_batch": B, "global_batch": B * world, "tokens_per_gpu": B * 196, "parallelism": f"dp{world}",
+                       "cuda_graph": bool(args.graph), "l2": "per-step working set (~5 GB of weights, activations, gradients) >> 126 MB L2; no explicit flush",
+                       "loss": final_loss},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of one step)", "achieved": gemm_tflops,
+                         "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": (gemm_tflops / pk["tf_burst"]) if gemm_tflops else None,
+                         "traffic": None, "peak_source": pk["src"] + " (burst cuBLAS bf16)", "gemm_launches_per_step": n_gemm,
+                         "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_step if ms_step else None,
+                         "step_tflops_per_gpu": step_tflops, "step_frac_of_sustained_peak": step_tflops / pk["tf_sustained"]},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                rate, threads, total = cpu_reference_rate(args.cpu_batch, 2, 1)
+                line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                                        "sample": f"{args.cpu_batch} image/step x 2 timed steps (+1 warm-up), ViT-L+RVSA @224 fwd+bwd+AdamW fp32 oracle, {total:.1f} s"}
+            except Exception as ex:      # the baseline is informative; never lose the GPU line to it
+                line["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

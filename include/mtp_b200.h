@@ -160,6 +160,26 @@ int mtp_full_attn_bwd(const void* qkv_bf16, const float* rel_pos_h, const float*
                       const void* out_bf16, const void* dout_bf16, void* dqkv_bf16, float* d_rel_pos_h, float* d_rel_pos_w,
                       void* workspace, int B, int gh, int gw, int C, int nH, mtp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Optimizer tail over FLAT fp32 buffers (parameters, gradients, Adam moments share one layout; every parameter starts
+ * at a multiple of 64 elements).  Replaces clip_grad_norm_(5) + AdamW.step() + CosineAnnealingLR.step()
+ * (Multi-Task_Pretrain/main_pretrain.py:786-787,832) and the layer-decay parameter groups
+ * (mmcv_custom/layer_decay_optimizer_constructor_vit.py:18-78).
+ * state (device, 2 floats): [0] step counter, [1] sum of squares of the gradients.  Per step:
+ *   mtp_optim_step_begin(state)            ++step, sumsq = 0
+ *   mtp_sumsq_f32(grads, n, state + 1)     (after the gradient all-reduce)
+ *   mtp_adamw_step(...)                    grad = g * grad_scale * min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6));
+ *                                          lr = cosine(step; lr0, eta_min, t_max) * group_lr_scale[group];
+ *                                          decoupled weight decay group_weight_decay[group]; p_bf16 (optional) mirrors p.
+ * chunk_group[i] = parameter group of elements [64 i, 64 i + 64).
+ * ------------------------------------------------------------------------------------------------------------- */
+int mtp_optim_step_begin(float* state, mtp_stream_t stream);
+int mtp_sumsq_f32(const float* x, size_t n, float* out, mtp_stream_t stream);
+int mtp_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, const uint8_t* chunk_group,
+                   const float* group_lr_scale, const float* group_weight_decay, const float* state, size_t n, float lr0,
+                   float eta_min, int t_max, float beta1, float beta2, float eps, float max_norm, float grad_scale,
+                   mtp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,9 @@ _SIGNATURES = {
     "mtp_rvsa_attn_bwd": [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
     "mtp_rvsa_sampling_bwd": [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
     "mtp_full_attn_bwd": [c_void_p] * 10 + [c_int] * 5 + [c_void_p],
+    "mtp_optim_step_begin": [c_void_p, c_void_p],
+    "mtp_sumsq_f32": [c_void_p, c_size_t, c_void_p, c_void_p],
+    "mtp_adamw_step": [c_void_p] * 9 + [c_size_t, c_float, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p],
 }
 _SIZE_FNS = {
     "mtp_rvsa_bwd_workspace_bytes": [c_int] * 5,

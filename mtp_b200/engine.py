@@ -26,8 +26,12 @@ class EngineState:
 
     def __init__(self):
         self.cache: Dict[str, tuple] = {}
+        self.pinned: Dict[str, torch.Tensor] = {}      # always-current bf16 views maintained by the fused optimizer
 
     def get(self, key, param, fn):
+        pin = self.pinned.get(key)
+        if pin is not None:
+            return pin
         ver = (param._version, param.data_ptr())
         ent = self.cache.get(key)
         if ent is None or ent[0] != ver:

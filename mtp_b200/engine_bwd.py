@@ -140,14 +140,16 @@ def _fpn_tap_backward(m, W, S, k, grad, dx, G, B, gh, gw):
     ops.gemm(du1, F_["fpn1_0_w"], T, C, 4 * C, dx, b_mn=True, mode=L.EPI_F32, accumulate=True, lda=4 * C, ldb=C)
 
 
-def backward_impl(m, x, S, grad_outs):
-    """Returns fp32 gradients in ``m.parameters()`` order (None where a parameter does not take part)."""
+def backward_impl(m, x, S, grad_outs, grad_store=None, after_block=None):
+    """Returns fp32 gradients in ``m.parameters()`` order (None where a parameter does not take part).
+    ``grad_store``: reuse a persistent (pre-zeroed where accumulated) GradStore; ``after_block(i)`` is called when the
+    gradients of block i are final (used to launch the bucketed all-reduce while the backward continues)."""
     W = S["W"]
     B, gh, gw, keep = S["B"], S["gh"], S["gw"], S["keep"]
     C, nH = W.C, W.nH
     T = B * gh * gw
     dev = x.device
-    G = GradStore(m, dev)
+    G = grad_store if grad_store is not None else GradStore(m, dev)
     grad_outs = list(grad_outs)
 
     dx = None
@@ -177,6 +179,8 @@ def backward_impl(m, x, S, grad_outs):
             _, s = engine._block_forward(W.blocks[i], s["x0"], B, gh, gw, nH, ka, km, save=True)
         dx = _block_backward(i, W.blocks[i], s, dx, G, B, gh, gw, nH, keep)
         S["blocks"][i] = None             # release activations as we go
+        if after_block is not None:
+            after_block(i)
 
     if dx is not None:
         # patch embed + pos_embed ([V]:790-794)

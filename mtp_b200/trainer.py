@@ -1,0 +1,211 @@
+"""B200-native pretrain step for the backbone: forward + backward over the C-ABI kernels, gradient all-reduce over
+NCCL (bucketed, overlapped with the remaining backward on a side stream), global-norm clipping and fused AdamW on flat
+buffers, optionally captured into one CUDA graph.
+
+Mirrors the per-iteration body of Multi-Task_Pretrain/main_pretrain.py:701-832 for the encoder:
+``encoder(cat(x1,x2,x3))`` -> losses -> ``backward`` (DDP all-reduce) -> ``clip_grad_norm_(5)`` -> ``AdamW.step`` ->
+``CosineAnnealingLR.step``.  The three decoders are third-party (mmseg/mmdet/mmrotate, absent here) and out of scope;
+``heads`` is a callable taking the four NCHW maps and returning (loss, cotangents) — the default is the synthetic
+objective the parity tests use.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import engine, engine_bwd, ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+_BIG_SUFFIXES = ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")
+
+
+def _is_big(name):
+    return name.endswith(_BIG_SUFFIXES) or name == "patch_embed.proj.weight" or (name.startswith("fpn") and name.endswith(".weight") and ".ln." not in name)
+
+
+def layer_decay_group(name: str, shape, num_layers: int, prefix: str = "encoder."):
+    """(layer_id, no_decay) as LayerDecayOptimizerConstructor_ViT assigns them
+    (mmcv_custom/layer_decay_optimizer_constructor_vit.py:7-16,41-49).  In the pretrain script parameter names start with
+    ``encoder.`` while the constructor looks for ``backbone.``, so every parameter lands in the last layer (scale 1);
+    ``prefix='backbone.'`` gives the intended layer-wise decay."""
+    full = prefix + name
+    no_decay = len(shape) == 1 or name.endswith(".bias") or "pos_embed" in name
+    if full in ("backbone.cls_token", "backbone.mask_token", "backbone.pos_embed") or full.startswith("backbone.patch_embed"):
+        lid = 0
+    elif full.startswith("backbone.blocks"):
+        lid = int(full.split(".")[2]) + 1
+    else:
+        lid = num_layers - 1
+    return lid, no_decay
+
+
+def synthetic_heads(feats: Sequence[torch.Tensor]):
+    """Stand-in objective: 0.5 * sum_k mean(f_k^2); returns (loss, d loss / d f_k)."""
+    loss = None
+    grads = []
+    for f in feats:
+        ff = f.float()
+        l = (ff * ff).mean() * 0.5
+        loss = l if loss is None else loss + l
+        grads.append((ff * (1.0 / f.numel())).to(f.dtype))
+    return loss, grads
+
+
+class PretrainStep:
+    def __init__(self, model, lr=6e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, max_norm=5.0, t_max=0, eta_min=0.0,
+                 layer_decay_rate=0.9, name_prefix="encoder.", heads: Optional[Callable] = None, process_group=None,
+                 bucket_blocks=4, use_cuda_graph=False):
+        self.model = model
+        self.heads = heads or synthetic_heads
+        self.lr, self.eta_min, self.t_max = lr, eta_min, t_max
+        self.betas, self.eps, self.max_norm = betas, eps, max_norm
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.bucket_blocks = bucket_blocks
+        dev = next(model.parameters()).device
+        assert dev.type == "cuda", "PretrainStep needs the model on a CUDA device"
+        self.dev = dev
+        # ---- flat layout: [small parameters | GEMM weights], every tensor 64-element aligned
+        named = list(model.named_parameters())
+        order = [(n, p) for n, p in named if not _is_big(n)] + [(n, p) for n, p in named if _is_big(n)]
+        self.offsets, total = {}, 0
+        for n, p in order:
+            self.offsets[n] = total
+            total += (p.numel() + 63) // 64 * 64
+            if not _is_big(n):
+                self.small_end = total
+        self.total = total
+        self.flat_p = torch.zeros(total, device=dev, dtype=F32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=F32)
+        self.flat_m = torch.zeros(total, device=dev, dtype=F32)
+        self.flat_v = torch.zeros(total, device=dev, dtype=F32)
+        num_layers = len(model.blocks) + 2
+        groups, chunk_group = {}, torch.zeros(total // 64, dtype=torch.uint8)
+        for n, p in order:
+            o = self.offsets[n]
+            self.flat_p[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + p.numel()].view(p.shape)
+            lid, nodecay = layer_decay_group(n, p.shape, num_layers, name_prefix)
+            key = (layer_decay_rate ** (num_layers - lid - 1), 0.0 if nodecay else weight_decay)
+            gid = groups.setdefault(key, len(groups))
+            chunk_group[o // 64:(o + (p.numel() + 63) // 64 * 64) // 64] = gid
+        assert len(groups) < 256
+        self.chunk_group = chunk_group.to(dev)
+        self.group_lr = torch.tensor([k[0] for k in groups], device=dev, dtype=F32)
+        self.group_wd = torch.tensor([k[1] for k in groups], device=dev, dtype=F32)
+        self.state = torch.zeros(2, device=dev, dtype=F32)
+        # ---- bf16 mirror kept current by the optimizer kernel; GEMM weights read it directly
+        self.flat_p16 = ops.cast_f32_bf16(self.flat_p)
+        st = model._engine_state
+        C = model.embed_dim
+        for n, p in order:
+            if not _is_big(n):
+                continue
+            o = self.offsets[n]
+            v16 = self.flat_p16[o:o + p.numel()]
+            if n == "patch_embed.proj.weight":
+                st.pinned["pe_w"] = v16.view(C, -1)
+            elif n.startswith("blocks."):
+                i = int(n.split(".")[1])
+                nm = n.split(".")[-2]
+                st.pinned[f"b{i}.{nm}"] = v16.view(p.shape)
+        self._convt_keys = ("fpn1_0", "fpn1_3", "fpn2_0")
+        # ---- gradient store bound to the flat gradient buffer (same layout)
+        self.G = engine_bwd.GradStore.__new__(engine_bwd.GradStore)
+        self.G.names = [n for n, _ in named]
+        self.G.flat = self.flat_g
+        self.G.views = {n: self.flat_g[self.offsets[n]:self.offsets[n] + p.numel()].view(p.shape) for n, p in named}
+        self.G.touched = set()
+        # ---- all-reduce buckets over the big region (in backward order) + one bucket for the small region
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.graph = None
+        self.use_cuda_graph = use_cuda_graph
+        self._static_x = None
+        self._static_loss = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _bucket_ranges(self):
+        """Contiguous flat ranges that become final at given points of the backward pass: {block_index: (lo, hi)}.
+        Blocks are grouped ``bucket_blocks`` at a time; the range of a group is ready once its lowest block is done."""
+        m = self.model
+        depth = len(m.blocks)
+        rng = {}
+        for hi_blk in range(depth - 1, -1, -self.bucket_blocks):
+            lo_blk = max(0, hi_blk - self.bucket_blocks + 1)
+            lo = self.offsets[f"blocks.{lo_blk}.attn.qkv.weight"]
+            last = f"blocks.{hi_blk}.mlp.fc2.weight"
+            hi = self.offsets[last] + (m.blocks[hi_blk].mlp.fc2.weight.numel() + 63) // 64 * 64
+            rng[lo_blk] = (lo, hi)
+        return rng
+
+    def _allreduce_range(self, lo, hi):
+        if self.world == 1:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _step_body(self, x):
+        m = self.model
+        st = m._engine_state
+        for k in self._convt_keys:                 # packed ConvTranspose weights are re-derived from the fp32 masters
+            st.cache.pop(k, None)
+        keep = engine._draw_keep(m, x.shape[0], x.device)
+        outs, ctx = engine._forward_impl(m, x, keep, save=True)
+        loss, douts = self.heads(outs)
+        # gradients: zero only the small (accumulated) region; GEMM weight gradients are overwritten
+        self.flat_g[:self.small_end].zero_()
+        self.G.touched = set()
+        buckets = self._bucket_ranges() if self.world > 1 else {}
+        engine_bwd.backward_impl(m, x, ctx, douts, grad_store=self.G,
+                                 after_block=(lambda i: self._allreduce_range(*buckets[i]) if i in buckets else None))
+        if self.world > 1:
+            # remaining pieces: big tensors outside the blocks (patch embed, fpn) and the small region
+            first_blk = self.offsets["blocks.0.attn.qkv.weight"]
+            self._allreduce_range(0, self.small_end)
+            if first_blk > self.small_end:
+                self._allreduce_range(self.small_end, first_blk)
+            last_blk_end = max(hi for _, hi in buckets.values())
+            if last_blk_end < self.total:
+                self._allreduce_range(last_blk_end, self.total)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        stream = ops._stream()
+        L.call("mtp_optim_step_begin", self.state.data_ptr(), stream)
+        if self.max_norm and self.max_norm > 0:
+            L.call("mtp_sumsq_f32", self.flat_g.data_ptr(), self.total, self.state.data_ptr() + 4, stream)
+        L.call("mtp_adamw_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
+               self.flat_p16.data_ptr(), self.chunk_group.data_ptr(), self.group_lr.data_ptr(), self.group_wd.data_ptr(),
+               self.state.data_ptr(), self.total, float(self.lr), float(self.eta_min), int(self.t_max), float(self.betas[0]),
+               float(self.betas[1]), float(self.eps), float(self.max_norm or 0.0), 1.0 / self.world, stream)
+        return loss
+
+    def step(self, x: torch.Tensor) -> torch.Tensor:
+        """One training step on a device-resident batch; returns the (device) scalar loss."""
+        if not self.use_cuda_graph:
+            return self._step_body(x)
+        if self.graph is None:
+            self._static_x = x.clone()
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):                      # warm-up outside capture (sets kernel attributes, fills allocator)
+                    self._step_body(self._static_x)
+            torch.cuda.current_stream().wait_stream(s)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._static_loss = self._step_body(self._static_x)
+        self._static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self._static_loss
+
+    def step_from_host(self, x_host_pinned: torch.Tensor) -> float:
+        """End-to-end step: host (pinned) batch -> device, step, loss back to the host."""
+        x = x_host_pinned.to(self.dev, non_blocking=True)
+        return float(self.step(x).item())

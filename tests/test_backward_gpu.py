@@ -68,7 +68,7 @@ def test_param_grads_match_golden_and_oracle(name):
     O.synthetic_loss(ref_outs).backward()
     fwd = [float((o.detach().float().cpu() - r.detach()).norm() / r.detach().norm()) for o, r in zip(outs, ref_outs)]
     print(name, "forward vs bf16-faithful oracle rel-L2:", ["%.2e" % e for e in fwd])
-    assert max(fwd) < 2.5e-3, fwd
+    assert max(fwd) < 1.5e-3, fwd            # north-star target: forward within 1e-3 rel at bf16
     errs2 = {}
     for k, p in m.named_parameters():
         if P[k].grad is None:
@@ -76,7 +76,7 @@ def test_param_grads_match_golden_and_oracle(name):
         errs2[k] = float((p.grad.float().cpu() - P[k].grad).norm() / P[k].grad.norm().clamp_min(1e-20))
     worst = sorted(errs2.items(), key=lambda kv: -kv[1])[:6]
     print(name, "vs bf16-faithful oracle, worst:", [(k, "%.2e" % v) for k, v in worst])
-    bad = {k: v for k, v in errs2.items() if v > (0.25 if _coordinate_sensitive(k, window_blocks) else GRAD_REL_L2)}
+    bad = {k: v for k, v in errs2.items() if v > 1e-2}
     assert not bad, bad
 
 
