@@ -145,7 +145,7 @@ class ViT_Win_RVSA_V3_WSZ7(nn.Module):
         if feature_mode == "multi" and len(self.out_indices) != 4:
             raise ValueError("out_indices must name four blocks (one per pyramid level, [V]:804-811)")
         self.pos_embed = nn.Parameter(torch.zeros(1, num_patches, embed_dim)) if use_abs_pos_emb else None
-        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]          # [V]:619
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth, device='cpu')]          # [V]:619
         self.use_rel_pos_bias = use_rel_pos_bias
         self.use_checkpoint = use_checkpoint
         self.blocks = nn.ModuleList([

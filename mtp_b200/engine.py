@@ -27,6 +27,7 @@ class EngineState:
     def __init__(self):
         self.cache: Dict[str, tuple] = {}
         self.pinned: Dict[str, torch.Tensor] = {}      # always-current bf16 views maintained by the fused optimizer
+        self.consts: Dict[tuple, torch.Tensor] = {}    # small device constants (DropPath keep probabilities)
 
     def get(self, key, param, fn):
         pin = self.pinned.get(key)
@@ -232,8 +233,12 @@ def _draw_keep(m, B, device):
     probs = [blk.drop_path_prob for blk in m.blocks]
     if not m.training or all(p == 0.0 for p in probs):
         return None
-    kp = torch.tensor([1.0 - p for p in probs], device=device, dtype=F32).view(-1, 1, 1).expand(len(probs), 2, B)
-    return (torch.bernoulli(kp) / kp).contiguous()
+    key = ("keep_prob", tuple(probs), B, str(device))
+    kp = m._engine_state.consts.get(key)
+    if kp is None:      # built once (an H2D copy is not capturable in a CUDA graph); bernoulli itself is graph-safe
+        kp = torch.tensor([1.0 - p for p in probs], dtype=F32).view(-1, 1, 1).expand(len(probs), 2, B).contiguous().to(device)
+        m._engine_state.consts = {key: kp}
+    return torch.bernoulli(kp) / kp
 
 
 def backbone_apply(m, x, keep=None):

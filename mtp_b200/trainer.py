@@ -18,14 +18,9 @@ import torch.distributed as dist
 
 from . import _lib as L
 from . import engine, engine_bwd, ops
+from .flat import FlatLayout, is_gemm_weight as _is_big
 
 BF16, F32 = torch.bfloat16, torch.float32
-
-_BIG_SUFFIXES = ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")
-
-
-def _is_big(name):
-    return name.endswith(_BIG_SUFFIXES) or name == "patch_embed.proj.weight" or (name.startswith("fpn") and name.endswith(".weight") and ".ln." not in name)
 
 
 def layer_decay_group(name: str, shape, num_layers: int, prefix: str = "encoder."):
@@ -72,13 +67,10 @@ class PretrainStep:
         self.dev = dev
         # ---- flat layout: [small parameters | GEMM weights], every tensor 64-element aligned
         named = list(model.named_parameters())
-        order = [(n, p) for n, p in named if not _is_big(n)] + [(n, p) for n, p in named if _is_big(n)]
-        self.offsets, total = {}, 0
-        for n, p in order:
-            self.offsets[n] = total
-            total += (p.numel() + 63) // 64 * 64
-            if not _is_big(n):
-                self.small_end = total
+        self.layout = FlatLayout([(n, tuple(p.shape)) for n, p in named])
+        pmap = dict(named)
+        order = [(n, pmap[n]) for n in self.layout.order]
+        self.offsets, self.small_end, total = self.layout.offsets, self.layout.small_end, self.layout.total
         self.total = total
         self.flat_p = torch.zeros(total, device=dev, dtype=F32)
         self.flat_g = torch.zeros(total, device=dev, dtype=F32)
@@ -130,18 +122,7 @@ class PretrainStep:
 
     # ------------------------------------------------------------------------------------------------------------
     def _bucket_ranges(self):
-        """Contiguous flat ranges that become final at given points of the backward pass: {block_index: (lo, hi)}.
-        Blocks are grouped ``bucket_blocks`` at a time; the range of a group is ready once its lowest block is done."""
-        m = self.model
-        depth = len(m.blocks)
-        rng = {}
-        for hi_blk in range(depth - 1, -1, -self.bucket_blocks):
-            lo_blk = max(0, hi_blk - self.bucket_blocks + 1)
-            lo = self.offsets[f"blocks.{lo_blk}.attn.qkv.weight"]
-            last = f"blocks.{hi_blk}.mlp.fc2.weight"
-            hi = self.offsets[last] + (m.blocks[hi_blk].mlp.fc2.weight.numel() + 63) // 64 * 64
-            rng[lo_blk] = (lo, hi)
-        return rng
+        return self.layout.block_buckets(len(self.model.blocks), self.bucket_blocks)
 
     def _allreduce_range(self, lo, hi):
         if self.world == 1:
@@ -167,14 +148,9 @@ class PretrainStep:
         engine_bwd.backward_impl(m, x, ctx, douts, grad_store=self.G,
                                  after_block=(lambda i: self._allreduce_range(*buckets[i]) if i in buckets else None))
         if self.world > 1:
-            # remaining pieces: big tensors outside the blocks (patch embed, fpn) and the small region
-            first_blk = self.offsets["blocks.0.attn.qkv.weight"]
-            self._allreduce_range(0, self.small_end)
-            if first_blk > self.small_end:
-                self._allreduce_range(self.small_end, first_blk)
-            last_blk_end = max(hi for _, hi in buckets.values())
-            if last_blk_end < self.total:
-                self._allreduce_range(last_blk_end, self.total)
+            # remaining pieces: the small region and the GEMM weights outside the blocks (patch embed, fpn)
+            for lo, hi in self.layout.tail_ranges(len(m.blocks), self.bucket_blocks):
+                self._allreduce_range(lo, hi)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         stream = ops._stream()
         L.call("mtp_optim_step_begin", self.state.data_ptr(), stream)
@@ -192,15 +168,20 @@ class PretrainStep:
             return self._step_body(x)
         if self.graph is None:
             self._static_x = x.clone()
+            # warm-up (kernel attributes, allocator) must not advance the training state: snapshot and restore it
+            snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.flat_p16, self.state)]
             s = torch.cuda.Stream(device=self.dev)
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                for _ in range(2):                      # warm-up outside capture (sets kernel attributes, fills allocator)
+                for _ in range(2):
                     self._step_body(self._static_x)
             torch.cuda.current_stream().wait_stream(s)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._static_loss = self._step_body(self._static_x)
+            for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.flat_p16, self.state), snap):
+                dst.copy_(src)
+            del snap
         self._static_x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self._static_loss

@@ -1,0 +1,79 @@
+"""Host logic of the data-parallel path on CPU: flat layout invariants and the bucketed all-reduce with gloo (world 2)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import mtp_b200
+from mtp_b200.flat import FlatLayout, is_gemm_weight
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _layout(depth=4):
+    with torch.device("meta"):
+        m = mtp_b200.ViT_Win_RVSA_V3_WSZ7(img_size=160, embed_dim=128, depth=depth, num_heads=2, qkv_bias=True, use_abs_pos_emb=True,
+                                          interval=2, out_indices=list(range(depth))[-4:], drop_path_rate=0.1)
+    return FlatLayout([(n, tuple(p.shape)) for n, p in m.named_parameters()]), m
+
+
+def test_layout_is_aligned_disjoint_and_small_first():
+    lay, m = _layout()
+    spans = sorted(lay.span(n) for n in lay.order)
+    assert spans[0][0] == 0 and spans[-1][1] == lay.total
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 == b0 and a0 % 64 == 0
+    for n in lay.order:
+        assert (lay.offsets[n] < lay.small_end) == (not is_gemm_weight(n))
+    big = sum(p.numel() for n, p in m.named_parameters() if is_gemm_weight(n))
+    assert big > 0.95 * sum(p.numel() for p in m.parameters())       # zeroing only the small region skips >95% of the bytes
+
+
+@pytest.mark.parametrize("depth,bb", [(4, 1), (4, 3), (8, 4), (6, 4)])
+def test_buckets_cover_everything_once(depth, bb):
+    lay, _ = _layout(depth)
+    ranges = list(lay.block_buckets(depth, bb).values()) + lay.tail_ranges(depth, bb)
+    ranges.sort()
+    assert ranges[0][0] == 0 and ranges[-1][1] == lay.total
+    for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+        assert a1 == b0
+    # a bucket keyed by block b holds exactly the GEMM weights of blocks b .. b+bb-1
+    for lo_blk, (lo, hi) in lay.block_buckets(depth, bb).items():
+        inside = {n for n in lay.order if lo <= lay.offsets[n] < hi}
+        blocks = {int(n.split(".")[1]) for n in inside}
+        assert min(blocks) == lo_blk and all(n.startswith("blocks.") and is_gemm_weight(n) for n in inside)
+
+
+def _worker(rank, world, port, total, ranges, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.arange(total, dtype=torch.float32) * (rank + 1)
+    for lo, hi in ranges:                       # same call pattern as PretrainStep._allreduce_range, issue order = backward order
+        dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM)
+    flat *= 1.0 / world
+    if rank == 0:
+        q.put(flat.clone())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_gloo_world2():
+    lay, _ = _layout(4)
+    b = lay.block_buckets(4, 2)
+    ranges = [b[k] for k in sorted(b, reverse=True)] + lay.tail_ranges(4, 2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, lay.total, ranges, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = torch.arange(lay.total, dtype=torch.float32) * 1.5       # mean of rank-scaled buffers
+    assert torch.equal(got, want)
