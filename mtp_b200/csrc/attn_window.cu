@@ -243,6 +243,9 @@ rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   }
 }
 
+int launch_rvsa_attn_fwd_tc(const void* qkv, const float* params, const float* rel_h, const float* rel_w, const float* table, void* out,
+                            float* lse, const RvsaGeom& g, cudaStream_t st);     // attn_window_tc.cu
+
 }  // namespace mtp
 
 using namespace mtp;
@@ -264,6 +267,8 @@ extern "C" int mtp_rvsa_attn_fwd(const void* qkv_bf16, const float* params, cons
   MTP_REQUIRE(qkv_bf16 && params && rel_pos_h && rel_pos_w && bias_table && out_bf16, "mtp_rvsa_attn_fwd: null pointer");
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD, "mtp_rvsa_attn_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported", B, h, w, C, nH);
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
+  if (nH % 2 == 0)       // tensor-core path: two heads of a window per 128-row UMMA tile
+    return launch_rvsa_attn_fwd_tc(qkv_bf16, params, rel_pos_h, rel_pos_w, bias_table, out_bf16, lse, g, reinterpret_cast<cudaStream_t>(stream));
   static bool attr = false;
   const int smem = RVSA_SMEM_FLOATS * sizeof(float);
   if (!attr) {

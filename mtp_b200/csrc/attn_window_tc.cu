@@ -1,0 +1,228 @@
+// RVSA window attention forward on tcgen05 tensor cores.                    [V]:372-428, SURVEY.md K5
+//
+// One CTA (128 threads) handles TWO (window, head) problems of the same window stacked on the 128 rows of one UMMA tile
+// (rows 0..48 = head 2p, rows 64..112 = head 2p+1; 15 padding rows each):
+//   gather : threads blend the 4 bilinear taps of every sampled K / V row in fp32 and write bf16 rows straight into
+//            128B-swizzled shared-memory tiles (the layout the UMMA descriptors read) together with the Q rows
+//   S      : tcgen05.mma  S[128x128] = Q K~^T (K = 64) into TMEM; only the two diagonal 64x64 blocks are meaningful
+//   softmax: thread r owns row r: tcgen05.ld its diagonal block, add scale / decomposed rel-pos (fp32, unscaled q) /
+//            bias table, softmax over the 49 keys, write P (bf16) block-diagonally into a [128 x 128] tile
+//   O      : tcgen05.mma  O[128x64] = P V~ (K = 128; the zero off-diagonal blocks keep the two problems apart)
+//   store  : tcgen05.ld O row -> bf16 -> token-major output (padding tokens are never written: the crop is free)
+#include "common.h"
+#include "ptx.cuh"
+#include "rvsa_geom.cuh"
+#include "tc_tile.cuh"
+
+namespace mtp {
+
+constexpr int WTC_THREADS = 128;
+constexpr int WTC_TILE = 128 * 128;                       // bytes of one 128-row tile
+// smem: Q | K~ | V~ | P (2 atoms) | rel_h,rel_w fp32 [2][13][64] | table [2][169] | coords [2][98] | mbar | tmem slot
+constexpr int WTC_SMEM = 5 * WTC_TILE + 2 * 13 * 64 * 4 + 2 * 169 * 4 + 2 * 98 * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(WTC_THREADS)
+rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
+                        const float* __restrict__ rel_w, const float* __restrict__ bias_table, __nv_bfloat16* __restrict__ out,
+                        float* __restrict__ lse, const RvsaGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = sm;
+  uint8_t* Ks = Qs + WTC_TILE;
+  uint8_t* Vs = Ks + WTC_TILE;
+  uint8_t* Ps = Vs + WTC_TILE;                            // two atoms of 128 rows x 128 B
+  float* relt = reinterpret_cast<float*>(Ps + 2 * WTC_TILE);   // [2][13][64]: rel_pos_h then rel_pos_w
+  float* tabs = relt + 2 * 13 * 64;                       // [2 heads][169]
+  float* cpx = tabs + 2 * 169;                            // [98]
+  float* cpy = cpx + 98;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(cpy + 98);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half_heads = g.nH >> 1;
+  const int hp = blockIdx.x % half_heads;
+  const int bw = blockIdx.x / half_heads;
+  const int nwin = g.nh * g.nw;
+  const int b = bw / nwin, win = bw % nwin;
+  const int wy = win / g.nw, wx = win % g.nw;
+  const int C = g.C, C3 = 3 * g.C;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (tid == 32) {
+    mbar_init(mbar, 1);
+    fence_barrier_init();
+  }
+  smem_zero(Qs, 3 * WTC_TILE, tid, WTC_THREADS);          // padding rows of Q / K~ / V~ must be zero
+  for (int i = tid; i < 2 * 13 * 64; i += WTC_THREADS) relt[i] = i < 13 * 64 ? rel_h[i] : rel_w[i - 13 * 64];
+  for (int i = tid; i < 2 * 169; i += WTC_THREADS) tabs[i] = bias_table[(i % 169) * g.nH + 2 * hp + i / 169];
+  if (tid < 98) {
+    const int p = tid / NTOK, j = tid % NTOK;
+    const float* prm = params + ((size_t)bw * g.nH + 2 * hp + p) * 8;
+    float px, py;
+    rvsa_sample_coord(g, wy, wx, j / WS, j % WS, prm[0], prm[1], prm[2], prm[3], prm[4], px, py);
+    cpx[tid] = px;
+    cpy[tid] = py;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- gather: one warp per (problem, token) row, lane = 2 head dims
+  for (int i = warp; i < 2 * NTOK; i += WTC_THREADS / 32) {
+    const int p = i / NTOK, j = i % NTOK, r = 64 * p + j;
+    const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + (2 * hp + p) * HD;
+    const uint32_t soff = tile_chunk_off(r, lane >> 2) + (lane & 3) * 4;
+    const int y = wy * WS + j / WS - g.pt, x = wx * WS + j % WS - g.pl;
+    if (y >= 0 && y < g.h && x >= 0 && x < g.w)
+      *reinterpret_cast<uint32_t*>(Qs + soff) = *reinterpret_cast<const uint32_t*>(qkv_b + (size_t)(y * g.w + x) * C3 + lane * 2);
+    const float px = cpx[i], py = cpy[i];
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float ax = px - fx0, ay = py - fy0;
+    const int x0 = (int)fx0 - g.pl, y0 = (int)fy0 - g.pt;
+    float2 ka = make_float2(0.f, 0.f), va = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+      const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
+      if (xx >= 0 && xx < g.w && yy >= 0 && yy < g.h) {
+        const __nv_bfloat16* src = qkv_b + (size_t)(yy * g.w + xx) * C3 + lane * 2;
+        const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C));
+        const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C));
+        ka.x += wgt * kv.x; ka.y += wgt * kv.y;
+        va.x += wgt * vv.x; va.y += wgt * vv.y;
+      }
+    }
+    *reinterpret_cast<uint32_t*>(Ks + soff) = pack_bf16x2(ka.x, ka.y);
+    *reinterpret_cast<uint32_t*>(Vs + soff) = pack_bf16x2(va.x, va.y);
+  }
+  fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  __syncthreads();
+
+  // ---- S = Q K~^T  (M = 128, N = 128, K = 64) -> TMEM columns [0, 128)
+  if (tid == 0) {
+    tc_fence_after();
+    tc_mma_tiles<false, false>(tmem, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, 128, 64, false);
+    umma_commit(mbar);
+  }
+  // meanwhile: decomposed rel-pos terms of this thread's row (fp32, UNscaled q)
+  const int p = tid >> 6, q = tid & 63;
+  const bool qvalid = q < NTOK;
+  const int qy = q / WS, qx = q % WS;
+  float rh[WS], rw[WS];
+#pragma unroll
+  for (int k = 0; k < WS; ++k) { rh[k] = 0.f; rw[k] = 0.f; }
+  if (qvalid) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(Qs + tile_chunk_off(tid, c));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+      float qv[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
+#pragma unroll
+      for (int k = 0; k < WS; ++k) {
+        const float* th = relt + (qy - k + WS - 1) * HD + c * 8;
+        const float* tw = relt + 13 * 64 + (qx - k + WS - 1) * HD + c * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { rh[k] += qv[e] * th[e]; rw[k] += qv[e] * tw[e]; }
+      }
+    }
+  }
+  mbar_wait(mbar, 0);
+  tc_fence_after();
+
+  // ---- softmax of this thread's row over its problem's 49 keys
+  {
+    uint32_t r0[32], r1[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 64 * p;
+    tmem_ld_32x32(taddr, r0);
+    tmem_ld_32x32(taddr + 32, r1);
+    tmem_ld_wait();
+    float s[NTOK];
+    float m = -INFINITY;
+    const float* tab = tabs + p * 169;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) {
+      const float acc = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
+      const int jy = j / WS, jx = j % WS;
+      s[j] = 0.125f * acc + rh[jy] + rw[jx] + (qvalid ? tab[(qy - jy + WS - 1) * (2 * WS - 1) + (qx - jx + WS - 1)] : 0.f);
+      m = fmaxf(m, s[j]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) { s[j] = __expf(s[j] - m); sum += s[j]; }
+    const float inv = qvalid ? 1.0f / sum : 0.f;          // padding rows: P = 0
+    if (qvalid && lse) lse[((size_t)bw * g.nH + 2 * hp + p) * NTOK + q] = m + __logf(sum);
+    uint8_t* prow_mine = Ps + p * WTC_TILE;
+    uint8_t* prow_other = Ps + (1 - p) * WTC_TILE;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (c * 8 + e < NTOK) ? s[(c * 8 + e < NTOK) ? c * 8 + e : 0] * inv : 0.f;
+      uint4 u;
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(prow_mine + tile_chunk_off(tid, c)) = u;
+      *reinterpret_cast<uint4*>(prow_other + tile_chunk_off(tid, c)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tc_fence_before();
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // ---- O = P V~  (M = 128, N = 64, K = 128; V~ read MN-major: rows = key index) -> TMEM columns [128, 192)
+  if (tid == 0) {
+    tc_fence_after();
+    tc_mma_tiles<false, true>(tmem + 128, smem_u32(Ps), WTC_TILE, smem_u32(Vs), 0, 128, 64, 128, false);
+    umma_commit(mbar);
+  }
+  mbar_wait(mbar, 1);
+  tc_fence_after();
+  {
+    uint32_t r0[32], r1[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 128;
+    tmem_ld_32x32(taddr, r0);
+    tmem_ld_32x32(taddr + 32, r1);
+    tmem_ld_wait();
+    const int y = wy * WS + qy - g.pt, x = wx * WS + qx - g.pl;
+    if (qvalid && y >= 0 && y < g.h && x >= 0 && x < g.w) {
+      __nv_bfloat16* dst = out + ((size_t)(b * g.h + y) * g.w + x) * C + (2 * hp + p) * HD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(r0[8 * c]), __uint_as_float(r0[8 * c + 1]));
+        u.y = pack_bf16x2(__uint_as_float(r0[8 * c + 2]), __uint_as_float(r0[8 * c + 3]));
+        u.z = pack_bf16x2(__uint_as_float(r0[8 * c + 4]), __uint_as_float(r0[8 * c + 5]));
+        u.w = pack_bf16x2(__uint_as_float(r0[8 * c + 6]), __uint_as_float(r0[8 * c + 7]));
+        *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+        u.x = pack_bf16x2(__uint_as_float(r1[8 * c]), __uint_as_float(r1[8 * c + 1]));
+        u.y = pack_bf16x2(__uint_as_float(r1[8 * c + 2]), __uint_as_float(r1[8 * c + 3]));
+        u.z = pack_bf16x2(__uint_as_float(r1[8 * c + 4]), __uint_as_float(r1[8 * c + 5]));
+        u.w = pack_bf16x2(__uint_as_float(r1[8 * c + 6]), __uint_as_float(r1[8 * c + 7]));
+        *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+int launch_rvsa_attn_fwd_tc(const void* qkv, const float* params, const float* rel_h, const float* rel_w, const float* table, void* out,
+                            float* lse, const RvsaGeom& g, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(rvsa_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTC_SMEM);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_fwd_tc smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  rvsa_attn_fwd_tc_kernel<<<g.B * g.nh * g.nw * (g.nH / 2), WTC_THREADS, WTC_SMEM, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), params, rel_h, rel_w, table, reinterpret_cast<__nv_bfloat16*>(out), lse, g);
+  return check_launch("rvsa_attn_fwd_tc_kernel");
+}
+
+}  // namespace mtp

@@ -14,8 +14,11 @@ shapes = [  # name, M, N, K, a_mn, b_mn, mode
     ("qkv wgrad", 3 * C, C, T, True, True, "f32"), ("proj wgrad", C, C, T, True, True, "f32"),
     ("fpn1.3 fwd", 4 * T, 4 * C, C, False, False, "bf16"), ("big square", 8192, 8192, 8192, False, False, "bf16"),
 ]
+only = sys.argv[1].split(",") if len(sys.argv) > 1 else None
 res = []
 for name, M, N, K, a_mn, b_mn, mode in shapes:
+    if only and name not in only:
+        continue
     A = torch.randn((K, M) if a_mn else (M, K), device="cuda").to(torch.bfloat16)
     B = torch.randn((K, N) if b_mn else (N, K), device="cuda").to(torch.bfloat16)
     bias = torch.randn(N, device="cuda")
@@ -36,7 +39,7 @@ for name, M, N, K, a_mn, b_mn, mode in shapes:
         out = torch.empty(M, N, device="cuda")
         kw["mode"] = L.EPI_F32
     row = {"name": name, "M": M, "N": N, "K": K}
-    for bn in (0, 64, 128, 192, 256):
+    for bn in ((0,) if only else (0, 64, 128, 192, 256)):
         try:
             for _ in range(3):
                 ops.gemm(A, B, M, N, K, out, a_mn=a_mn, b_mn=b_mn, force_bn=bn, **kw)
