@@ -3,7 +3,8 @@
 //
 //   warp 0      : TMA producer (one elected lane)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  : epilogue (tcgen05.ld 32 lanes x 32 columns per warp, fused bias/GELU/residual/..., vector stores)
+//   warps 2..9  : epilogue (two warps per TMEM lane quarter taking alternate 32-column chunks; tcgen05.ld pipelined
+//                 one chunk ahead, bias staged in smem per tile, aux operands loaded before the TMEM wait)
 //
 // Both operands may be K-major (row = m or n, k contiguous) or MN-major (row = k, m/n contiguous), which covers
 // forward (K,K), dgrad (K,MN) and wgrad (MN,MN) without materialising any transpose.  See include/mtp_b200.h.
@@ -18,7 +19,8 @@ namespace mtp {
 
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int EPI_THREADS = 256;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 template <int BN>
@@ -29,7 +31,7 @@ struct GemmCfg {
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 };
 
 struct EpiParams {
@@ -52,15 +54,35 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[32], int m, int n, int N) {
-  if (ep.bias != nullptr) {
-    const float* bp = ep.bias + (ep.mode == MTP_EPI_BF16_PIXSHUF ? (n % ep.ps_cout) : n);
+// aux operand of one 32-column chunk, fetched BEFORE waiting on the TMEM load so the two latencies overlap
+struct AuxRegs { float4 f[8]; };
+
+__device__ __forceinline__ void load_aux(const EpiParams& ep, AuxRegs& a, int m, int n, int N) {
+  if (ep.mode == MTP_EPI_F32_RESID) {
+    const float* r = reinterpret_cast<const float*>(ep.aux) + (size_t)m * ep.ldo + n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (n + 4 * j < N) a.f[j] = *reinterpret_cast<const float4*>(r + 4 * j);
+  } else if (ep.mode == MTP_EPI_F32_POS) {
+    const float* r = reinterpret_cast<const float*>(ep.aux) + (size_t)(m % ep.pos_rows) * N + n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (n + 4 * j < N) a.f[j] = __ldg(reinterpret_cast<const float4*>(r + 4 * j));
+  } else if (ep.mode == MTP_EPI_BF16_DGELU) {
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)m * ep.ldo + n;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (n + 8 * j < N) a.f[j] = *reinterpret_cast<const float4*>(h + 8 * j);
+  } else if (ep.mode == MTP_EPI_F32 && ep.accumulate) {
+    const float* o = reinterpret_cast<const float*>(ep.out) + (size_t)m * ep.ldo + n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (n + 4 * j < N) a.f[j] = *reinterpret_cast<const float4*>(o + 4 * j);
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[32], const AuxRegs& a, const float* bias_s, int m, int n, int N) {
+  if (bias_s != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      if (n + j < N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bp + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + j);      // smem broadcast; columns >= N hold zeros
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
   switch (ep.mode) {
@@ -86,24 +108,22 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[3
     } break;
     case MTP_EPI_F32_RESID: {
       const float s = ep.row_scale ? __ldg(ep.row_scale + m / ep.rows_per_group) : 1.0f;
-      const float* r = reinterpret_cast<const float*>(ep.aux) + (size_t)m * ep.ldo + n;
       float* o = reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldo + n;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         if (n + j < N) {
-          float4 x = *reinterpret_cast<const float4*>(r + j);
+          float4 x = a.f[j >> 2];
           x.x += s * v[j]; x.y += s * v[j + 1]; x.z += s * v[j + 2]; x.w += s * v[j + 3];
           *reinterpret_cast<float4*>(o + j) = x;
         }
       }
     } break;
     case MTP_EPI_F32_POS: {
-      const float* r = reinterpret_cast<const float*>(ep.aux) + (size_t)(m % ep.pos_rows) * N + n;
       float* o = reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldo + n;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         if (n + j < N) {
-          float4 x = __ldg(reinterpret_cast<const float4*>(r + j));
+          float4 x = a.f[j >> 2];
           x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
           *reinterpret_cast<float4*>(o + j) = x;
         }
@@ -116,7 +136,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[3
         if (n + j < N) {
           float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           if (ep.accumulate) {
-            const float4 y = *reinterpret_cast<const float4*>(o + j);
+            const float4 y = a.f[j >> 2];
             x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
           }
           *reinterpret_cast<float4*>(o + j) = x;
@@ -124,13 +144,12 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[3
       }
     } break;
     case MTP_EPI_BF16_DGELU: {
-      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)m * ep.ldo + n;
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)m * ep.ldo + n;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         if (n + j < N) {
-          const uint4 u = *reinterpret_cast<const uint4*>(h + j);
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          const float4 hv = a.f[j >> 3];
+          const uint32_t w[4] = {__float_as_uint(hv.x), __float_as_uint(hv.y), __float_as_uint(hv.z), __float_as_uint(hv.w)};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 f = unpack_bf16x2(w[t]);
@@ -171,6 +190,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -186,7 +206,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], EPI_THREADS / 32);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -259,28 +279,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hsel = (warp - 2) >> 2;       // which alternate chunks this warp takes
+    const int et = threadIdx.x - 64;        // 0..255 within the epilogue group
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % tiles_m) * BM;
       const int n0 = (tile / tiles_m) * BN;
+      float* bsm = bias_s + acc * BN;
+      if (ep.bias != nullptr) {             // stage this tile's bias slice once (zeros beyond N)
+        for (int i = et; i < BN; i += EPI_THREADS) {
+          const int n = n0 + i;
+          bsm[i] = n < N ? __ldg(ep.bias + (ep.mode == MTP_EPI_BF16_PIXSHUF ? n % ep.ps_cout : n)) : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= N) break;               // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c0, r);
+      const int n_chunks = (min(BN, N - n0) + 31) / 32;
+      uint32_t r[32];
+      int c = hsel;
+      if (c < n_chunks) tmem_ld_32x32(taddr + c * 32, r);
+      for (; c < n_chunks; c += 2) {
+        AuxRegs aux;
+        if (row_ok) load_aux(ep, aux, m, n0 + c * 32, N);
         tmem_ld_wait();
-        if (m < M) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_chunk(ep, v, m, n0 + c0, N);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (c + 2 < n_chunks) tmem_ld_32x32(taddr + (c + 2) * 32, r);      // next chunk streams in while this one is processed
+        if (row_ok) epilogue_chunk(ep, v, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, m, n0 + c * 32, N);
       }
       tc_fence_before();
       __syncwarp();

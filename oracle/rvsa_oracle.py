@@ -204,8 +204,9 @@ def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: in
     G = B * nH
     pxf = px.reshape(G, Hq * Wq)
     pyf = py.reshape(G, Hq * Wq)
-    ks = bilinear_gather(k.reshape(G, Hq, Wq, hd), pxf, pyf).reshape(B, nH, nh, WS, nw, WS, hd)
-    vs = bilinear_gather(v.reshape(G, Hq, Wq, hd), pxf, pyf).reshape(B, nH, nh, WS, nw, WS, hd)
+    # (r: the tensor-core path stages the blended K~/V~ rows and the probabilities P as bf16 MMA operands)
+    ks = r(bilinear_gather(k.reshape(G, Hq, Wq, hd), pxf, pyf)).reshape(B, nH, nh, WS, nw, WS, hd)
+    vs = r(bilinear_gather(v.reshape(G, Hq, Wq, hd), pxf, pyf)).reshape(B, nH, nh, WS, nw, WS, hd)
 
     def win(t):  # (B,nH,nh,7,nw,7,hd) -> (B,nh,nw,nH,49,hd)
         return t.permute(0, 2, 4, 1, 3, 5, 6).reshape(B, nh, nw, nH, WS * WS, hd)
@@ -226,7 +227,7 @@ def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: in
     idx = (iy[:, None] - iy[None, :] + WS - 1) * (2 * WS - 1) + (ix[:, None] - ix[None, :] + WS - 1)
     bias = P[pre + "relative_position_bias_table"][idx.reshape(-1)].reshape(WS * WS, WS * WS, nH).permute(2, 0, 1)
     S = S + bias
-    A = torch.softmax(S, dim=-1)
+    A = r(torch.softmax(S, dim=-1))
     O = A @ vw                                                                  # (B,nh,nw,nH,49,hd)
     O = O.reshape(B, nh, nw, nH, WS, WS, hd).permute(0, 1, 4, 2, 5, 3, 6).reshape(B, Hq, Wq, C)
     O = r(O[:, pt:pt + h, pl:pl + w].reshape(B, N, C))                          # crop  [V]:426
