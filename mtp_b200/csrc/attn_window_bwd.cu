@@ -345,17 +345,17 @@ rvsa_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 // d_rel[2][13][64] += sum over CTAs ; d_table[169][nH] += sum over (image, window)
 __global__ void __launch_bounds__(256)
 rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __restrict__ part_table, float* __restrict__ d_rel_h,
-                            float* __restrict__ d_rel_w, float* __restrict__ d_table, int n_cta, int nH) {
+                            float* __restrict__ d_rel_w, float* __restrict__ d_table, int n_rel_parts, int n_bw, int nH) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int n_rel = 2 * (2 * WS - 1) * HD;
   if (i < n_rel) {
     float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += part_rel[(size_t)c * n_rel + i];
+    for (int c = 0; c < n_rel_parts; ++c) s += part_rel[(size_t)c * n_rel + i];
     if (i < n_rel / 2) d_rel_h[i] += s; else d_rel_w[i - n_rel / 2] += s;
   } else if (i < n_rel + 169 * nH) {
     const int e = i - n_rel, idx = e / nH, n = e % nH;
     float s = 0.f;
-    for (int bw = 0; bw < n_cta / nH; ++bw) s += part_table[((size_t)bw * nH + n) * 169 + idx];
+    for (int bw = 0; bw < n_bw; ++bw) s += part_table[((size_t)bw * nH + n) * 169 + idx];
     d_table[idx * nH + n] += s;
   }
 }
@@ -450,6 +450,10 @@ rvsa_pool_bwd_add_kernel(const float* __restrict__ dpooled, __nv_bfloat16* __res
   }
 }
 
+int launch_rvsa_attn_bwd_tc(const void* qkv, const float* params, const float* rel_h, const float* rel_w, const float* table,
+                            const float* lse, const void* dout, void* dqkv, float* dkv, float* dparams, float* part_rel,
+                            float* part_table, const RvsaGeom& g, cudaStream_t st);     // attn_window_bwd_tc.cu
+
 }  // namespace mtp
 
 using namespace mtp;
@@ -477,20 +481,29 @@ extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, cons
   const size_t T = (size_t)B * h * w;
   cudaError_t e = cudaMemsetAsync(dkv, 0, T * 2 * C * sizeof(float), st);
   if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa bwd memset: %s", cudaGetErrorString(e));
-  static bool attr = false;
-  const int smem = RVSA_BWD_SMEM_FLOATS * sizeof(float);
-  if (!attr) {
-    e = cudaFuncSetAttribute(rvsa_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_bwd smem attr: %s", cudaGetErrorString(e));
-    attr = true;
+  int rc, n_rel_parts;
+  if (nH % 2 == 0) {       // tensor-core path (two heads per UMMA tile); rel-pos partials are per CTA = per head pair
+    rc = launch_rvsa_attn_bwd_tc(qkv_bf16, params, rel_pos_h, rel_pos_w, bias_table, lse, dout_bf16, dqkv_bf16, dkv, dparams, part_rel,
+                                 part_table, g, st);
+    n_rel_parts = n_cta / 2;
+  } else {
+    static bool attr = false;
+    const int smem = RVSA_BWD_SMEM_FLOATS * sizeof(float);
+    if (!attr) {
+      e = cudaFuncSetAttribute(rvsa_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_bwd smem attr: %s", cudaGetErrorString(e));
+      attr = true;
+    }
+    rvsa_attn_bwd_kernel<<<n_cta, BW_THREADS, smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), params, rel_pos_h, rel_pos_w, bias_table, lse,
+        reinterpret_cast<const __nv_bfloat16*>(dout_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dkv, dparams, part_rel, part_table, g);
+    rc = check_launch("rvsa_attn_bwd_kernel");
+    n_rel_parts = n_cta;
   }
-  rvsa_attn_bwd_kernel<<<n_cta, BW_THREADS, smem, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), params, rel_pos_h, rel_pos_w, bias_table, lse,
-      reinterpret_cast<const __nv_bfloat16*>(dout_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dkv, dparams, part_rel, part_table, g);
-  int rc = check_launch("rvsa_attn_bwd_kernel");
   if (rc) return rc;
   const int n_red = 2 * (2 * WS - 1) * HD + 169 * nH;
-  rvsa_partials_reduce_kernel<<<ceil_div(n_red, 256), 256, 0, st>>>(part_rel, part_table, d_rel_pos_h, d_rel_pos_w, d_bias_table, n_cta, nH);
+  rvsa_partials_reduce_kernel<<<ceil_div(n_red, 256), 256, 0, st>>>(part_rel, part_table, d_rel_pos_h, d_rel_pos_w, d_bias_table, n_rel_parts,
+                                                                    n_cta / nH, nH);
   rc = check_launch("rvsa_partials_reduce_kernel");
   if (rc) return rc;
   const size_t n4 = T * (size_t)(2 * C / 4);

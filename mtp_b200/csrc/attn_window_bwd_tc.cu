@@ -1,0 +1,386 @@
+// RVSA window attention backward on tcgen05 tensor cores (autograd of attn_window_tc.cu; [V]:372-428).
+//
+// Same CTA shape as the forward: two (window, head) problems stacked on the 128 rows of one UMMA tile.
+//   gather : q, dO rows and the bilinearly blended k~, v~ rows -> bf16 swizzled tiles
+//   MMA 1  : S  = Q K~^T , dP = dO V~^T                              (M = N = 128, K = 64)
+//   rows   : thread r: P = exp(S - lse), D = sum P dP, dS = P (dP - D); P and dS written block-diagonally (bf16);
+//            row sums of dS per key row / key column (rel-pos), bias-table partials via shared-memory atomics
+//   MMA 2  : dQ = dS K~ ,  dK~ = dS^T Q ,  dV~ = P^T dO              (M = 128, N = 64, K = 128; transposes via MN-major A)
+//   tail   : thread r: dq row (+ rel-pos terms) -> dqkv; its dk~ / dv~ row scattered through the 4 bilinear taps with
+//            red.global.add.v4.f32 into the fp32 scratch; tap dot-products -> d(coords) -> d(ox, oy, sx, sy, theta)
+// Partials for rel_pos_h/w are written per CTA (both heads summed), bias-table partials per (window, head).
+#include "common.h"
+#include "ptx.cuh"
+#include "rvsa_geom.cuh"
+#include "tc_tile.cuh"
+
+namespace mtp {
+
+constexpr int WB_THREADS = 128;
+constexpr int WB_TILE = 128 * 128;
+// Q | K~ | V~ | dO | P (2 atoms) | dS (2 atoms) | rel tables | bias tables | coords | dSh,dSw | table partial | red | mbar | slot
+constexpr int WB_SMEM = 8 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 2 * 128 * 8 + 2 * 169 + 64) * 4 + 64 + 1024;
+
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ float tile_read(const uint8_t* tile, int row, int d) {     // bf16 element (row, d) of a swizzled tile
+  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + tile_chunk_off(row, d >> 3) + (d & 7) * 2));
+}
+
+__global__ void __launch_bounds__(WB_THREADS)
+rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
+                        const float* __restrict__ rel_w, const float* __restrict__ bias_table, const float* __restrict__ lse,
+                        const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dkv,
+                        float* __restrict__ dparams, float* __restrict__ part_rel, float* __restrict__ part_table, const RvsaGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = sm;
+  uint8_t* Ks = Qs + WB_TILE;
+  uint8_t* Vs = Ks + WB_TILE;
+  uint8_t* Gs = Vs + WB_TILE;
+  uint8_t* Pt = Gs + WB_TILE;                 // 2 atoms
+  uint8_t* St = Pt + 2 * WB_TILE;             // 2 atoms
+  float* relt = reinterpret_cast<float*>(St + 2 * WB_TILE);     // [2][13][64]
+  float* tabs = relt + 2 * 13 * 64;           // [2][169]
+  float* cpx = tabs + 2 * 169;                // [98]
+  float* cpy = cpx + 98;
+  float* dSh = cpy + 98;                      // [128][8]
+  float* dSw = dSh + 128 * 8;
+  float* ptab = dSw + 128 * 8;                // [2][169] bias-table partial
+  float* red = ptab + 2 * 169;                // [64]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half_heads = g.nH >> 1;
+  const int hp = blockIdx.x % half_heads;
+  const int bw = blockIdx.x / half_heads;
+  const int nwin = g.nh * g.nw;
+  const int b = bw / nwin, win = bw % nwin;
+  const int wy = win / g.nw, wx = win % g.nw;
+  const int C = g.C, C3 = 3 * g.C;
+  const float scale = 0.125f;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) {
+    mbar_init(mbar, 1);
+    fence_barrier_init();
+  }
+  smem_zero(Qs, 4 * WB_TILE, tid, WB_THREADS);
+  for (int i = tid; i < 2 * 13 * 64; i += WB_THREADS) relt[i] = i < 13 * 64 ? rel_h[i] : rel_w[i - 13 * 64];
+  for (int i = tid; i < 2 * 169; i += WB_THREADS) {
+    tabs[i] = bias_table[(i % 169) * g.nH + 2 * hp + i / 169];
+    ptab[i] = 0.f;
+  }
+  if (tid < 98) {
+    const int p = tid / NTOK, j = tid % NTOK;
+    const float* prm = params + ((size_t)bw * g.nH + 2 * hp + p) * 8;
+    float px, py;
+    rvsa_sample_coord(g, wy, wx, j / WS, j % WS, prm[0], prm[1], prm[2], prm[3], prm[4], px, py);
+    cpx[tid] = px;
+    cpy[tid] = py;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t T_S = tmem, T_DP = tmem + 128, T_DQ = tmem + 256, T_DK = tmem + 320, T_DV = tmem + 384;
+
+  // ---- gather
+  for (int i = warp; i < 2 * NTOK; i += WB_THREADS / 32) {
+    const int p = i / NTOK, j = i % NTOK, r = 64 * p + j;
+    const int head = 2 * hp + p;
+    const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + head * HD;
+    const uint32_t soff = tile_chunk_off(r, lane >> 2) + (lane & 3) * 4;
+    const int y = wy * WS + j / WS - g.pt, x = wx * WS + j % WS - g.pl;
+    if (y >= 0 && y < g.h && x >= 0 && x < g.w) {
+      const size_t t = (size_t)(b * g.h + y) * g.w + x;
+      *reinterpret_cast<uint32_t*>(Qs + soff) = *reinterpret_cast<const uint32_t*>(qkv + t * C3 + head * HD + lane * 2);
+      *reinterpret_cast<uint32_t*>(Gs + soff) = *reinterpret_cast<const uint32_t*>(dout + t * C + head * HD + lane * 2);
+    }
+    const float px = cpx[i], py = cpy[i];
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float ax = px - fx0, ay = py - fy0;
+    const int x0 = (int)fx0 - g.pl, y0 = (int)fy0 - g.pt;
+    float2 ka = make_float2(0.f, 0.f), va = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+      const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
+      if (xx >= 0 && xx < g.w && yy >= 0 && yy < g.h) {
+        const __nv_bfloat16* src = qkv_b + (size_t)(yy * g.w + xx) * C3 + lane * 2;
+        const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C));
+        const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C));
+        ka.x += wgt * kv.x; ka.y += wgt * kv.y;
+        va.x += wgt * vv.x; va.y += wgt * vv.y;
+      }
+    }
+    *reinterpret_cast<uint32_t*>(Ks + soff) = pack_bf16x2(ka.x, ka.y);
+    *reinterpret_cast<uint32_t*>(Vs + soff) = pack_bf16x2(va.x, va.y);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // ---- S = Q K~^T, dP = dO V~^T
+  if (tid == 0) {
+    tc_fence_after();
+    tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, 128, 64, false);
+    tc_mma_tiles<false, false>(T_DP, smem_u32(Gs), 0, smem_u32(Vs), 0, 128, 128, 64, false);
+    umma_commit(mbar);
+  }
+  const int p = tid >> 6, q = tid & 63;
+  const bool qvalid = q < NTOK;
+  const int qy = q / WS, qx = q % WS;
+  const int head = 2 * hp + p;
+  float rh[WS], rw[WS];
+#pragma unroll
+  for (int k = 0; k < WS; ++k) { rh[k] = 0.f; rw[k] = 0.f; }
+  if (qvalid) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(Qs + tile_chunk_off(tid, c));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+      float qv[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
+#pragma unroll
+      for (int k = 0; k < WS; ++k) {
+        const float* th = relt + (qy - k + WS - 1) * HD + c * 8;
+        const float* tw = relt + 13 * 64 + (qx - k + WS - 1) * HD + c * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { rh[k] += qv[e] * th[e]; rw[k] += qv[e] * tw[e]; }
+      }
+    }
+  }
+  mbar_wait(mbar, 0);
+  tc_fence_after();
+
+  // ---- P, dS of this thread's row
+  float sh[WS], sw[WS];
+#pragma unroll
+  for (int k = 0; k < WS; ++k) { sh[k] = 0.f; sw[k] = 0.f; }
+  {
+    uint32_t r0[32], r1[32];
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    tmem_ld_32x32(T_S + lane_base + 64 * p, r0);
+    tmem_ld_32x32(T_S + lane_base + 64 * p + 32, r1);
+    tmem_ld_wait();
+    float pr[NTOK];
+    const float l = qvalid ? lse[((size_t)bw * g.nH + head) * NTOK + q] : 0.f;
+    const float* tab = tabs + p * 169;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) {
+      const float acc = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
+      const int jy = j / WS, jx = j % WS;
+      const float s = scale * acc + rh[jy] + rw[jx] + (qvalid ? tab[(qy - jy + WS - 1) * (2 * WS - 1) + (qx - jx + WS - 1)] : 0.f);
+      pr[j] = qvalid ? __expf(s - l) : 0.f;
+    }
+    tmem_ld_32x32(T_DP + lane_base + 64 * p, r0);
+    tmem_ld_32x32(T_DP + lane_base + 64 * p + 32, r1);
+    tmem_ld_wait();
+    float D = 0.f;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) D += pr[j] * __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
+    float ds[NTOK];
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) {
+      ds[j] = pr[j] * (__uint_as_float(j < 32 ? r0[j] : r1[j - 32]) - D);
+      sh[j / WS] += ds[j];
+      sw[j % WS] += ds[j];
+    }
+    if (qvalid) {
+#pragma unroll
+      for (int j = 0; j < NTOK; ++j)
+        atomicAdd(&ptab[p * 169 + (qy - j / WS + WS - 1) * (2 * WS - 1) + (qx - j % WS + WS - 1)], ds[j]);
+    }
+#pragma unroll
+    for (int k = 0; k < WS; ++k) { dSh[tid * 8 + k] = sh[k]; dSw[tid * 8 + k] = sw[k]; }
+    uint8_t* p_mine = Pt + p * WB_TILE;
+    uint8_t* p_other = Pt + (1 - p) * WB_TILE;
+    uint8_t* s_mine = St + p * WB_TILE;
+    uint8_t* s_other = St + (1 - p) * WB_TILE;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float vp[8], vs[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = c * 8 + e;
+        vp[e] = j < NTOK ? pr[j < NTOK ? j : 0] : 0.f;
+        vs[e] = j < NTOK ? ds[j < NTOK ? j : 0] : 0.f;
+      }
+      uint4 u;
+      u.x = pack_bf16x2(vp[0], vp[1]); u.y = pack_bf16x2(vp[2], vp[3]); u.z = pack_bf16x2(vp[4], vp[5]); u.w = pack_bf16x2(vp[6], vp[7]);
+      *reinterpret_cast<uint4*>(p_mine + tile_chunk_off(tid, c)) = u;
+      u.x = pack_bf16x2(vs[0], vs[1]); u.y = pack_bf16x2(vs[2], vs[3]); u.z = pack_bf16x2(vs[4], vs[5]); u.w = pack_bf16x2(vs[6], vs[7]);
+      *reinterpret_cast<uint4*>(s_mine + tile_chunk_off(tid, c)) = u;
+      *reinterpret_cast<uint4*>(p_other + tile_chunk_off(tid, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(s_other + tile_chunk_off(tid, c)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tc_fence_before();
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // ---- dQ = dS K~ ; dK~ = dS^T Q ; dV~ = P^T dO
+  if (tid == 0) {
+    tc_fence_after();
+    tc_mma_tiles<false, true>(T_DQ, smem_u32(St), WB_TILE, smem_u32(Ks), 0, 128, 64, 128, false);
+    tc_mma_tiles<true, true>(T_DK, smem_u32(St), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
+    tc_mma_tiles<true, true>(T_DV, smem_u32(Pt), WB_TILE, smem_u32(Gs), 0, 128, 64, 128, false);
+    umma_commit(mbar);
+  }
+  // meanwhile: per-CTA partials of d rel_pos_h / d rel_pos_w (both heads summed) and the bias-table partials
+  for (int e = tid; e < 2 * (2 * WS - 1) * HD; e += WB_THREADS) {
+    const int d = e % HD, r = (e / HD) % (2 * WS - 1), which = e / (HD * (2 * WS - 1));
+    float s = 0.f;
+    for (int pp = 0; pp < 2; ++pp)
+      for (int qa = 0; qa < WS; ++qa) {
+        const int k = qa - (r - (WS - 1));
+        if (k < 0 || k >= WS) continue;
+        for (int qb = 0; qb < WS; ++qb) {
+          const int row = 64 * pp + (which == 0 ? qa * WS + qb : qb * WS + qa);
+          s += (which == 0 ? dSh : dSw)[row * 8 + k] * tile_read(Qs, row, d);
+        }
+      }
+    part_rel[(size_t)blockIdx.x * (2 * (2 * WS - 1) * HD) + e] = s;
+  }
+  for (int i = tid; i < 2 * 169; i += WB_THREADS) part_table[((size_t)bw * g.nH + 2 * hp + i / 169) * 169 + i % 169] = ptab[i];
+  mbar_wait(mbar, 1);
+  tc_fence_after();
+
+  // ---- dq row -> dqkv
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  {
+    const int y = wy * WS + qy - g.pt, x = wx * WS + qx - g.pl;
+    const bool tok_ok = qvalid && y >= 0 && y < g.h && x >= 0 && x < g.w;
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      uint32_t r0[32];
+      tmem_ld_32x32(T_DQ + lane_base + 32 * hb, r0);
+      tmem_ld_wait();
+      if (tok_ok) {
+        float o[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[e] = scale * __uint_as_float(r0[e]);
+#pragma unroll
+        for (int k = 0; k < WS; ++k) {
+          const float* th = relt + (qy - k + WS - 1) * HD + 32 * hb;
+          const float* tw = relt + 13 * 64 + (qx - k + WS - 1) * HD + 32 * hb;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] += sh[k] * th[e] + sw[k] * tw[e];
+        }
+        __nv_bfloat16* dst = dqkv + ((size_t)(b * g.h + y) * g.w + x) * C3 + head * HD + 32 * hb;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(o[8 * c], o[8 * c + 1]); u.y = pack_bf16x2(o[8 * c + 2], o[8 * c + 3]);
+          u.z = pack_bf16x2(o[8 * c + 4], o[8 * c + 5]); u.w = pack_bf16x2(o[8 * c + 6], o[8 * c + 7]);
+          *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+        }
+      }
+    }
+  }
+
+  // ---- scatter of this thread's dk~ / dv~ row (sample j = q of problem p) and its coordinate gradient
+  float gx = 0.f, gy = 0.f;
+  {
+    const float px = qvalid ? cpx[p * NTOK + q] : 0.f, py = qvalid ? cpy[p * NTOK + q] : 0.f;
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float ax = px - fx0, ay = py - fy0;
+    const int x0 = (int)fx0 - g.pl, y0 = (int)fy0 - g.pt;
+    const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + head * HD;
+    float* dk_b = dkv + (size_t)b * g.h * g.w * 2 * C + head * HD;
+    float tapdot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      uint32_t rk[32], rv[32];
+      tmem_ld_32x32(T_DK + lane_base + 32 * hb, rk);
+      tmem_ld_32x32(T_DV + lane_base + 32 * hb, rv);
+      tmem_ld_wait();
+      if (qvalid) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+          const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
+          if (xx >= 0 && xx < g.w && yy >= 0 && yy < g.h) {
+            const size_t pix = (size_t)(yy * g.w + xx);
+            const __nv_bfloat16* src = qkv_b + pix * C3 + 32 * hb;
+            float* dst = dk_b + pix * 2 * C + 32 * hb;
+            float td = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 ku = *reinterpret_cast<const uint4*>(src + C + 8 * c);
+              const uint4 vu = *reinterpret_cast<const uint4*>(src + 2 * C + 8 * c);
+              const uint32_t kw4[4] = {ku.x, ku.y, ku.z, ku.w}, vw4[4] = {vu.x, vu.y, vu.z, vu.w};
+              float gk[8], gv[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { gk[e] = scale * __uint_as_float(rk[8 * c + e]); gv[e] = __uint_as_float(rv[8 * c + e]); }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 kf = unpack_bf16x2(kw4[e]), vf = unpack_bf16x2(vw4[e]);
+                td += gk[2 * e] * kf.x + gk[2 * e + 1] * kf.y + gv[2 * e] * vf.x + gv[2 * e + 1] * vf.y;
+              }
+              red_add_f32x4(dst + 8 * c, wgt * gk[0], wgt * gk[1], wgt * gk[2], wgt * gk[3]);
+              red_add_f32x4(dst + 8 * c + 4, wgt * gk[4], wgt * gk[5], wgt * gk[6], wgt * gk[7]);
+              red_add_f32x4(dst + C + 8 * c, wgt * gv[0], wgt * gv[1], wgt * gv[2], wgt * gv[3]);
+              red_add_f32x4(dst + C + 8 * c + 4, wgt * gv[4], wgt * gv[5], wgt * gv[6], wgt * gv[7]);
+            }
+            tapdot[t] += td;
+          }
+        }
+      }
+    }
+    gx = (1.f - ay) * (tapdot[1] - tapdot[0]) + ay * (tapdot[3] - tapdot[2]);
+    gy = (1.f - ax) * (tapdot[2] - tapdot[0]) + ax * (tapdot[3] - tapdot[1]);
+  }
+  // ---- chain to (ox, oy, sx, sy, theta) and reduce over the 49 samples of each problem (2 warps per problem)
+  float v5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (qvalid) {
+    const float* prm = params + ((size_t)bw * g.nH + head) * 8;
+    const float inv_w = 2.0f / (float)(g.Wq - 1), inv_h = 2.0f / (float)(g.Hq - 1);
+    const float bx = (float)(qx - WS / 2) * inv_w, by = (float)(qy - WS / 2) * inv_h;
+    const float X = (1.f + prm[2]) * bx, Y = (1.f + prm[3]) * by;
+    float s, c;
+    sincosf(prm[4], &s, &c);
+    const float dcx = gx * 0.5f * (float)(g.Wq - 1), dcy = gy * 0.5f * (float)(g.Hq - 1);
+    v5[0] = dcx;
+    v5[1] = dcy;
+    v5[2] = (dcx * c + dcy * s) * bx;
+    v5[3] = (-dcx * s + dcy * c) * by;
+    v5[4] = dcx * (-X * s - Y * c) + dcy * (-Y * s + X * c);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float r = warp_sum(v5[k]);
+    if (lane == 0) red[warp * 8 + k] = r;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 10) {
+    const int pp = tid / 5, k = tid % 5;
+    dparams[((size_t)bw * g.nH + 2 * hp + pp) * 8 + k] = red[(2 * pp) * 8 + k] + red[(2 * pp + 1) * 8 + k];
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int launch_rvsa_attn_bwd_tc(const void* qkv, const float* params, const float* rel_h, const float* rel_w, const float* table,
+                            const float* lse, const void* dout, void* dqkv, float* dkv, float* dparams, float* part_rel,
+                            float* part_table, const RvsaGeom& g, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(rvsa_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WB_SMEM);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_bwd_tc smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  rvsa_attn_bwd_tc_kernel<<<g.B * g.nh * g.nw * (g.nH / 2), WB_THREADS, WB_SMEM, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), params, rel_h, rel_w, table, lse, reinterpret_cast<const __nv_bfloat16*>(dout),
+      reinterpret_cast<__nv_bfloat16*>(dqkv), dkv, dparams, part_rel, part_table, g);
+  return check_launch("rvsa_attn_bwd_tc_kernel");
+}
+
+}  // namespace mtp
