@@ -166,6 +166,9 @@ full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   }
 }
 
+int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* rel_w, void* out, float* lse, int B, int gh, int gw, int C,
+                            int nH, cudaStream_t st);      // attn_full_tc.cu
+
 }  // namespace mtp
 
 using namespace mtp;
@@ -176,6 +179,8 @@ extern "C" int mtp_full_attn_fwd(const void* qkv_bf16, const float* rel_pos_h, c
   MTP_REQUIRE((rel_pos_h == nullptr) == (rel_pos_w == nullptr), "mtp_full_attn_fwd: give both rel-pos tables or neither");
   MTP_REQUIRE(B > 0 && gh > 0 && gw > 0 && C == nH * FA_HD, "mtp_full_attn_fwd: B=%d grid=%dx%d C=%d nH=%d unsupported (hd must be 64)", B, gh, gw, C, nH);
   const int N = gh * gw;
+  if (N <= 256 && gh <= 16 && gw <= 16)       // tensor-core path: K/V of a head resident in shared memory
+    return launch_full_attn_fwd_tc(qkv_bf16, rel_pos_h, rel_pos_w, out_bf16, lse, B, gh, gw, C, nH, reinterpret_cast<cudaStream_t>(stream));
   const int smem = fa_smem_floats(gh, gw) * (int)sizeof(float);
   MTP_REQUIRE(smem <= 220 * 1024, "mtp_full_attn_fwd: grid %dx%d too large for the rel-pos tables in shared memory", gh, gw);
   static int attr_smem = 0;

@@ -322,6 +322,9 @@ full_attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
   }
 }
 
+int launch_full_attn_bwd_tc(const void* qkv, const float* rel_h, const float* rel_w, const float* lse, const void* out, const void* dout,
+                            void* dqkv, float* d_rel_h, float* d_rel_w, int B, int gh, int gw, int C, int nH, cudaStream_t st);   // attn_full_tc.cu
+
 }  // namespace mtp
 
 using namespace mtp;
@@ -338,6 +341,9 @@ extern "C" int mtp_full_attn_bwd(const void* qkv_bf16, const float* rel_pos_h, c
   MTP_REQUIRE(B > 0 && gh > 0 && gw > 0 && C == nH * FB_HD, "mtp_full_attn_bwd: unsupported geometry");
   const int N = gh * gw;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N <= 256 && gh <= 16 && gw <= 16)       // tensor-core path (one CTA per image-head, K/V resident, dK/dV accumulated in TMEM)
+    return launch_full_attn_bwd_tc(qkv_bf16, rel_pos_h, rel_pos_w, lse, out_bf16, dout_bf16, dqkv_bf16, d_rel_pos_h, d_rel_pos_w, B, gh, gw,
+                                   C, nH, st);
   float* Dbuf = reinterpret_cast<float*>(workspace);
   const int smem_dq = (5 * FB_T * FB_LD + 2 * FB_T + 2 * FB_T * (gh + gw)) * (int)sizeof(float);
   const int smem_dkv = (6 * FB_T * FB_LD + 2 * FB_T + FB_T * (gh + gw)) * (int)sizeof(float);

@@ -1,0 +1,517 @@
+// Dense attention with decomposed rel-pos bias on tcgen05 tensor cores, forward and backward, for token grids with
+// N = gh*gw <= 256 (224^2 and 256^2 inputs: the dense blocks of the headline configuration).  Larger grids use the
+// streaming SIMT kernels of attn_full.cu / attn_full_bwd.cu in this round.       [V]:90-111, 142-193; SURVEY.md K6
+//
+// One CTA (128 threads) per (image, head).  K and V of the head live in shared memory for the whole CTA as 128B-swizzled
+// bf16 tiles ([256 rows] x 128 B); query tiles of 128 rows are processed in turn:
+//   forward : S = Q K^T (UMMA M=128, N=N16, K=64) -> thread r owns row r: two passes over its TMEM row (max, then
+//             exp / sum / bf16 P into a [128 x 256] tile) with the rel-pos bias  scale * (q.Rh[qy-jy+gh-1] + q.Rw[qx-jx+gw-1])
+//             added in fp32 -> O = P V (K = N16) -> O / sum -> bf16; LSE saved.
+//   backward: per (query tile, key half of 128): S then dP into TMEM; rows give P = exp(S - lse), dS = P (dP - D);
+//             dQ += dS K (registers), dK_half += dS^T Q and dV_half += P^T dO accumulate in TMEM across query tiles
+//             (transposes via MN-major A operands); rel-pos table gradients reduced per CTA, then atomics.
+#include "common.h"
+#include "ptx.cuh"
+#include "tc_tile.cuh"
+
+namespace mtp {
+
+constexpr int FT_THREADS = 128;
+constexpr int FT_TILE = 128 * 128;       // bytes of a 128-row tile
+constexpr int FT_MAXG = 16;              // max grid side (N <= 256)
+constexpr int FT_TAB = (2 * FT_MAXG - 1) * 64;   // floats per rel-pos table
+
+// copy rows [row0, row0+nrows) of a head slice (64 bf16 per row, row pitch ld) into a swizzled tile; rows >= nvalid are zero
+__device__ __forceinline__ void ft_load_rows(uint8_t* tile, const __nv_bfloat16* src, size_t ld, int row0, int nrows, int nvalid) {
+  for (int i = threadIdx.x; i < nrows * 8; i += FT_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row0 + r < nvalid) v = *reinterpret_cast<const uint4*>(src + (size_t)(row0 + r) * ld + c * 8);
+    *reinterpret_cast<uint4*>(tile + tile_chunk_off(r, c)) = v;
+  }
+}
+
+// this thread's rel-pos terms: rh[k] = q . Rh[qy - k + gh - 1] (k < gh), rw[k] = q . Rw[qx - k + gw - 1] (k < gw), UNscaled q
+__device__ __forceinline__ void ft_rel_terms(const uint8_t* Qs, const float* relh_t, const float* relw_t, int row, int qy, int qx, int gh,
+                                             int gw, float* rh_s, float* rw_s) {
+  float qv[64];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(Qs + tile_chunk_off(row, c));
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[c * 8 + 2 * t] = f.x; qv[c * 8 + 2 * t + 1] = f.y; }
+  }
+  for (int k = 0; k < gh; ++k) {
+    const float* th = relh_t + (qy - k + gh - 1) * 64;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) s += qv[d] * th[d];
+    rh_s[k] = s;
+  }
+  for (int k = 0; k < gw; ++k) {
+    const float* tw = relw_t + (qx - k + gw - 1) * 64;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) s += qv[d] * tw[d];
+    rw_s[k] = s;
+  }
+}
+
+// ================================================================================================== forward
+constexpr int FTF_SMEM = FT_TILE /*Q*/ + 2 * 2 * FT_TILE /*K,V*/ + 4 * FT_TILE /*P*/ + (2 * FT_TAB + 2 * 128 * 17) * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(FT_THREADS)
+full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
+                        __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int gh, int gw, int C, int nH, int use_rel) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = sm;
+  uint8_t* Ks = Qs + FT_TILE;              // 256 rows
+  uint8_t* Vs = Ks + 2 * FT_TILE;
+  uint8_t* Pt = Vs + 2 * FT_TILE;          // 4 atoms of 128 rows
+  float* relh_t = reinterpret_cast<float*>(Pt + 4 * FT_TILE);
+  float* relw_t = relh_t + FT_TAB;
+  float* rh_s = relw_t + FT_TAB;           // [128][17] per-row rel terms
+  float* rw_s = rh_s + 128 * 17;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(rw_s + 128 * 17);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n = blockIdx.x % nH, b = blockIdx.x / nH;
+  const int C3 = 3 * C;
+  const float scale = 0.125f;
+  const __nv_bfloat16* base = qkv + (size_t)b * N * C3 + n * 64;
+  const int N16 = (N + 15) & ~15;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) { mbar_init(mbar, 1); fence_barrier_init(); }
+  ft_load_rows(Ks, base + C, C3, 0, 256, N);
+  ft_load_rows(Vs, base + 2 * C, C3, 0, 256, N);
+  if (use_rel) {
+    for (int i = tid; i < (2 * gh - 1) * 64; i += FT_THREADS) relh_t[i] = rel_h[i];
+    for (int i = tid; i < (2 * gw - 1) * 64; i += FT_THREADS) relw_t[i] = rel_w[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t T_S = tmem, T_O = tmem + 256;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  uint32_t phase = 0;
+
+  for (int q0 = 0; q0 < N; q0 += 128) {
+    ft_load_rows(Qs, base, C3, q0, 128, N);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, N16, 64, false);
+      umma_commit(mbar);
+    }
+    const int q = q0 + tid;
+    const bool qvalid = q < N;
+    const int qy = qvalid ? q / gw : 0, qx = qvalid ? q % gw : 0;
+    float* rh = rh_s + tid * 17;
+    float* rw = rw_s + tid * 17;
+    if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+
+    const int n_chunks = (N + 31) / 32;
+    // pass 1: row maximum
+    float m = -INFINITY;
+    {
+      int jy = 0, jx = 0;
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(T_S + lane_base + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = c * 32 + e;
+          if (j < N) {
+            float s = __uint_as_float(r[e]);
+            if (use_rel) s += rh[jy] + rw[jx];
+            m = fmaxf(m, s);
+            if (++jx == gw) { jx = 0; ++jy; }
+          }
+        }
+      }
+    }
+    // pass 2: exp, sum, P (bf16, unnormalised) -> smem
+    float sum = 0.f;
+    {
+      int jy = 0, jx = 0;
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(T_S + lane_base + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = c * 32 + e;
+          float p = 0.f;
+          if (j < N) {
+            float s = __uint_as_float(r[e]);
+            if (use_rel) s += rh[jy] + rw[jx];
+            p = qvalid ? __expf(scale * (s - m)) : 0.f;
+            if (++jx == gw) { jx = 0; ++jy; }
+          }
+          pv[e] = p;
+          sum += p;
+        }
+        uint8_t* atom = Pt + (c >> 1) * FT_TILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 u;
+          u.x = pack_bf16x2(pv[8 * k], pv[8 * k + 1]); u.y = pack_bf16x2(pv[8 * k + 2], pv[8 * k + 3]);
+          u.z = pack_bf16x2(pv[8 * k + 4], pv[8 * k + 5]); u.w = pack_bf16x2(pv[8 * k + 6], pv[8 * k + 7]);
+          *reinterpret_cast<uint4*>(atom + tile_chunk_off(tid, (c & 1) * 4 + k)) = u;
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      tc_mma_tiles<false, true>(T_O, smem_u32(Pt), FT_TILE, smem_u32(Vs), 0, 128, 64, N16, false);
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(T_O + lane_base, r0);
+      tmem_ld_32x32(T_O + lane_base + 32, r1);
+      tmem_ld_wait();
+      if (qvalid) {
+        const float inv = 1.0f / sum;
+        __nv_bfloat16* dst = out + ((size_t)b * N + q) * C + n * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r0[8 * c]) * inv, __uint_as_float(r0[8 * c + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(r0[8 * c + 2]) * inv, __uint_as_float(r0[8 * c + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(r0[8 * c + 4]) * inv, __uint_as_float(r0[8 * c + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(r0[8 * c + 6]) * inv, __uint_as_float(r0[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+          u.x = pack_bf16x2(__uint_as_float(r1[8 * c]) * inv, __uint_as_float(r1[8 * c + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(r1[8 * c + 2]) * inv, __uint_as_float(r1[8 * c + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(r1[8 * c + 4]) * inv, __uint_as_float(r1[8 * c + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(r1[8 * c + 6]) * inv, __uint_as_float(r1[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
+        }
+        if (lse) lse[((size_t)b * nH + n) * N + q] = scale * m + __logf(sum);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();          // TMEM rows and the Q / P tiles are free for the next query tile
+    tc_fence_after();
+  }
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* rel_w, void* out, float* lse, int B, int gh, int gw, int C,
+                            int nH, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(full_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FTF_SMEM);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_fwd_tc smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  full_attn_fwd_tc_kernel<<<B * nH, FT_THREADS, FTF_SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
+                                                                reinterpret_cast<__nv_bfloat16*>(out), lse, gh * gw, gh, gw, C, nH,
+                                                                rel_h != nullptr);
+  return check_launch("full_attn_fwd_tc_kernel");
+}
+
+// ================================================================================================== backward
+// smem: Q | dO | K (256 rows) | V (256 rows) | P (2 atoms) | dS (2 atoms) | tables | per-row rel terms | dSh, dSw | D, lse
+constexpr int FTB_SMEM = 2 * FT_TILE + 4 * FT_TILE + 4 * FT_TILE + (2 * FT_TAB + 4 * 128 * 17 + 2 * 128) * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(FT_THREADS)
+full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
+                        const float* __restrict__ lse, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                        __nv_bfloat16* __restrict__ dqkv, float* __restrict__ d_rel_h, float* __restrict__ d_rel_w, int N, int gh, int gw,
+                        int C, int nH, int use_rel) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = sm;
+  uint8_t* Gs = Qs + FT_TILE;
+  uint8_t* Ks = Gs + FT_TILE;
+  uint8_t* Vs = Ks + 2 * FT_TILE;
+  uint8_t* Pt = Vs + 2 * FT_TILE;          // [128 q x 128 keys of the current half]: 2 atoms
+  uint8_t* St = Pt + 2 * FT_TILE;
+  float* relh_t = reinterpret_cast<float*>(St + 2 * FT_TILE);
+  float* relw_t = relh_t + FT_TAB;
+  float* rh_s = relw_t + FT_TAB;           // [128][17]
+  float* rw_s = rh_s + 128 * 17;
+  float* dSh = rw_s + 128 * 17;            // [128][17] row sums of dS per key row
+  float* dSw = dSh + 128 * 17;
+  float* D_s = dSw + 128 * 17;             // [128]
+  float* lse_s = D_s + 128;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(lse_s + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n = blockIdx.x % nH, b = blockIdx.x / nH;
+  const int C3 = 3 * C;
+  const float scale = 0.125f;
+  const __nv_bfloat16* base = qkv + (size_t)b * N * C3 + n * 64;
+  const int N16 = (N + 15) & ~15;
+  const int n_halves = (N + 127) / 128;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) { mbar_init(mbar, 1); fence_barrier_init(); }
+  ft_load_rows(Ks, base + C, C3, 0, 256, N);
+  ft_load_rows(Vs, base + 2 * C, C3, 0, 256, N);
+  if (use_rel) {
+    for (int i = tid; i < (2 * gh - 1) * 64; i += FT_THREADS) relh_t[i] = rel_h[i];
+    for (int i = tid; i < (2 * gw - 1) * 64; i += FT_THREADS) relw_t[i] = rel_w[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t T_S = tmem, T_DP = tmem + 128, T_DK = tmem + 256, T_DV = tmem + 384;     // dQ temp reuses T_S
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  uint32_t phase = 0;
+
+  // per-thread partial sums of the rel-pos table gradients: outputs e = tid, tid+128, ... over [(2gh-1) + (2gw-1)] x 64
+  const int rows_h = 2 * gh - 1, rows_w = 2 * gw - 1;
+  float relacc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) relacc[i] = 0.f;
+
+  for (int q0 = 0, qt = 0; q0 < N; q0 += 128, ++qt) {
+    ft_load_rows(Qs, base, C3, q0, 128, N);
+    ft_load_rows(Gs, dout + (size_t)b * N * C + n * 64, C, q0, 128, N);
+    const int q = q0 + tid;
+    const bool qvalid = q < N;
+    const int qy = qvalid ? q / gw : 0, qx = qvalid ? q % gw : 0;
+    {   // D = dO . O, lse
+      float dsum = 0.f;
+      if (qvalid) {
+        const size_t off = ((size_t)b * N + q) * C + n * 64;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 ou = *reinterpret_cast<const uint4*>(out + off + 8 * c);
+          const uint4 gu = *reinterpret_cast<const uint4*>(dout + off + 8 * c);
+          const uint32_t ow[4] = {ou.x, ou.y, ou.z, ou.w}, gw4[4] = {gu.x, gu.y, gu.z, gu.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 a = unpack_bf16x2(ow[t]), g2 = unpack_bf16x2(gw4[t]);
+            dsum += a.x * g2.x + a.y * g2.y;
+          }
+        }
+      }
+      D_s[tid] = dsum;
+      lse_s[tid] = qvalid ? lse[((size_t)b * nH + n) * N + q] : 0.f;
+    }
+    for (int k = 0; k < 17; ++k) { dSh[tid * 17 + k] = 0.f; dSw[tid * 17 + k] = 0.f; }
+    fence_proxy_async_smem();
+    __syncthreads();
+    float* rh = rh_s + tid * 17;
+    float* rw = rw_s + tid * 17;
+    if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
+    float dq[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) dq[d] = 0.f;
+
+    for (int h = 0; h < n_halves; ++h) {
+      const int k0 = h * 128;
+      const int nk16 = min(128, N16 - k0);                 // keys of this half, multiple of 16
+      if (tid == 0) {
+        tc_fence_after();
+        tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks) + h * FT_TILE, 0, 128, nk16, 64, false);
+        tc_mma_tiles<false, false>(T_DP, smem_u32(Gs), 0, smem_u32(Vs) + h * FT_TILE, 0, 128, nk16, 64, false);
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      {
+        const float l = lse_s[tid], D = D_s[tid];
+        int jy = k0 / gw, jx = k0 % gw;
+        const int n_chunks = (nk16 + 31) / 32;
+        for (int c = 0; c < 4; ++c) {
+          float pv[32], dv[32];
+          if (c < n_chunks) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(T_S + lane_base + c * 32, r0);
+            tmem_ld_32x32(T_DP + lane_base + c * 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int j = k0 + c * 32 + e;
+              float p = 0.f, ds = 0.f;
+              if (j < N && c * 32 + e < nk16) {
+                float s = __uint_as_float(r0[e]);
+                if (use_rel) s += rh[jy] + rw[jx];
+                p = qvalid ? __expf(scale * s - l) : 0.f;
+                ds = p * (__uint_as_float(r1[e]) - D);
+                if (use_rel) { dSh[tid * 17 + jy] += ds; dSw[tid * 17 + jx] += ds; }
+                if (++jx == gw) { jx = 0; ++jy; }
+              }
+              pv[e] = p;
+              dv[e] = ds;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) { pv[e] = 0.f; dv[e] = 0.f; }
+          }
+          uint8_t* pa = Pt + (c >> 1) * FT_TILE;
+          uint8_t* sa = St + (c >> 1) * FT_TILE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            u.x = pack_bf16x2(pv[8 * k], pv[8 * k + 1]); u.y = pack_bf16x2(pv[8 * k + 2], pv[8 * k + 3]);
+            u.z = pack_bf16x2(pv[8 * k + 4], pv[8 * k + 5]); u.w = pack_bf16x2(pv[8 * k + 6], pv[8 * k + 7]);
+            *reinterpret_cast<uint4*>(pa + tile_chunk_off(tid, (c & 1) * 4 + k)) = u;
+            u.x = pack_bf16x2(dv[8 * k], dv[8 * k + 1]); u.y = pack_bf16x2(dv[8 * k + 2], dv[8 * k + 3]);
+            u.z = pack_bf16x2(dv[8 * k + 4], dv[8 * k + 5]); u.w = pack_bf16x2(dv[8 * k + 6], dv[8 * k + 7]);
+            *reinterpret_cast<uint4*>(sa + tile_chunk_off(tid, (c & 1) * 4 + k)) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        // dQ_half = dS K_h (temp in T_S) ; dK_h += dS^T Q ; dV_h += P^T dO     (M = 128 keys/queries, N = 64, K = 128)
+        tc_mma_tiles<false, true>(T_S, smem_u32(St), FT_TILE, smem_u32(Ks) + h * FT_TILE, 0, 128, 64, 128, false);
+        tc_mma_tiles<true, true>(T_DK + 64 * h, smem_u32(St), FT_TILE, smem_u32(Qs), 0, 128, 64, 128, qt > 0);
+        tc_mma_tiles<true, true>(T_DV + 64 * h, smem_u32(Pt), FT_TILE, smem_u32(Gs), 0, 128, 64, 128, qt > 0);
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(T_S + lane_base, r0);
+        tmem_ld_32x32(T_S + lane_base + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) { dq[d] += __uint_as_float(r0[d]); dq[32 + d] += __uint_as_float(r1[d]); }
+      }
+      tc_fence_before();
+      __syncthreads();          // T_S, P and dS tiles are reused by the next half
+      tc_fence_after();
+    }
+
+    // dq = scale * (dS K + sum_k dSh[k] Rh[qy-k+gh-1] + sum_k dSw[k] Rw[qx-k+gw-1])
+    if (qvalid) {
+      if (use_rel) {
+        for (int k = 0; k < gh; ++k) {
+          const float ch = dSh[tid * 17 + k];
+          const float* th = relh_t + (qy - k + gh - 1) * 64;
+#pragma unroll
+          for (int d = 0; d < 64; ++d) dq[d] += ch * th[d];
+        }
+        for (int k = 0; k < gw; ++k) {
+          const float cw = dSw[tid * 17 + k];
+          const float* tw = relw_t + (qx - k + gw - 1) * 64;
+#pragma unroll
+          for (int d = 0; d < 64; ++d) dq[d] += cw * tw[d];
+        }
+      }
+      __nv_bfloat16* dst = dqkv + ((size_t)b * N + q) * C3 + n * 64;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(scale * dq[8 * c], scale * dq[8 * c + 1]); u.y = pack_bf16x2(scale * dq[8 * c + 2], scale * dq[8 * c + 3]);
+        u.z = pack_bf16x2(scale * dq[8 * c + 4], scale * dq[8 * c + 5]); u.w = pack_bf16x2(scale * dq[8 * c + 6], scale * dq[8 * c + 7]);
+        *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+      }
+    }
+    // rel-pos table gradients of this query tile: dR[r][d] += scale * sum_{q, k: axis(q) - k + g - 1 == r} dSx[q][k] q[q][d]
+    if (use_rel) {
+      __syncthreads();          // dSh / dSw of all rows complete
+      const int nq = min(128, N - q0);
+      int slot = 0;
+      for (int e = tid; e < (rows_h + rows_w) * 64; e += FT_THREADS, ++slot) {
+        const int d = e & 63, rr = e >> 6;
+        const bool is_h = rr < rows_h;
+        const int r = is_h ? rr : rr - rows_h;
+        const int g1 = is_h ? gh : gw;
+        float s = 0.f;
+        for (int i = 0; i < nq; ++i) {
+          const int qq = q0 + i;
+          const int k = (is_h ? qq / gw : qq % gw) - (r - (g1 - 1));
+          if (k >= 0 && k < g1) {
+            const float qd = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(Qs + tile_chunk_off(i, d >> 3) + (d & 7) * 2));
+            s += (is_h ? dSh : dSw)[i * 17 + k] * qd;
+          }
+        }
+        relacc[slot] += s;
+      }
+    }
+    __syncthreads();            // Q / dO tiles and dSh / dSw are rewritten by the next query tile
+  }
+
+  // ---- dK, dV rows (thread r = key 128 h + r)
+  for (int h = 0; h < n_halves; ++h) {
+    const int j = 128 * h + tid;
+    uint32_t r0[32], r1[32];
+    __nv_bfloat16* dst = dqkv + ((size_t)b * N + j) * C3 + n * 64;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {      // 0: dK (x scale), 1: dV
+      const uint32_t t0 = (part == 0 ? T_DK : T_DV) + 64 * h + lane_base;
+      tmem_ld_32x32(t0, r0);
+      tmem_ld_32x32(t0 + 32, r1);
+      tmem_ld_wait();
+      if (j < N) {
+        const float f = part == 0 ? scale : 1.0f;
+        __nv_bfloat16* o = dst + (part == 0 ? C : 2 * C);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(f * __uint_as_float(r0[8 * c]), f * __uint_as_float(r0[8 * c + 1]));
+          u.y = pack_bf16x2(f * __uint_as_float(r0[8 * c + 2]), f * __uint_as_float(r0[8 * c + 3]));
+          u.z = pack_bf16x2(f * __uint_as_float(r0[8 * c + 4]), f * __uint_as_float(r0[8 * c + 5]));
+          u.w = pack_bf16x2(f * __uint_as_float(r0[8 * c + 6]), f * __uint_as_float(r0[8 * c + 7]));
+          *reinterpret_cast<uint4*>(o + 8 * c) = u;
+          u.x = pack_bf16x2(f * __uint_as_float(r1[8 * c]), f * __uint_as_float(r1[8 * c + 1]));
+          u.y = pack_bf16x2(f * __uint_as_float(r1[8 * c + 2]), f * __uint_as_float(r1[8 * c + 3]));
+          u.z = pack_bf16x2(f * __uint_as_float(r1[8 * c + 4]), f * __uint_as_float(r1[8 * c + 5]));
+          u.w = pack_bf16x2(f * __uint_as_float(r1[8 * c + 6]), f * __uint_as_float(r1[8 * c + 7]));
+          *reinterpret_cast<uint4*>(o + 32 + 8 * c) = u;
+        }
+      }
+    }
+  }
+  if (use_rel) {
+    int slot = 0;
+    for (int e = tid; e < (rows_h + rows_w) * 64; e += FT_THREADS, ++slot) {
+      const int d = e & 63, rr = e >> 6;
+      float* dstp = rr < rows_h ? d_rel_h + (size_t)rr * 64 + d : d_rel_w + (size_t)(rr - rows_h) * 64 + d;
+      atomicAdd(dstp, scale * relacc[slot]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+int launch_full_attn_bwd_tc(const void* qkv, const float* rel_h, const float* rel_w, const float* lse, const void* out, const void* dout,
+                            void* dqkv, float* d_rel_h, float* d_rel_w, int B, int gh, int gw, int C, int nH, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(full_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FTB_SMEM);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_bwd_tc smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  full_attn_bwd_tc_kernel<<<B * nH, FT_THREADS, FTB_SMEM, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w, lse, reinterpret_cast<const __nv_bfloat16*>(out),
+      reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dqkv), d_rel_h, d_rel_w, gh * gw, gh, gw, C, nH,
+      rel_h != nullptr);
+  return check_launch("full_attn_bwd_tc_kernel");
+}
+
+}  // namespace mtp

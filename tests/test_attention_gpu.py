@@ -1,4 +1,6 @@
-"""RVSA window attention and dense rel-pos attention kernels vs the oracle's pieces (fp32, same bf16-rounded qkv)."""
+"""RVSA window attention and dense rel-pos attention kernels vs the oracle's pieces (fp32, same bf16-rounded qkv).
+
+The tensor-core kernels stage K~ / V~ / P / dS as bf16 MMA operands (fp32 accumulate); tolerances reflect that."""
 import pytest
 import torch
 
@@ -95,7 +97,7 @@ def _oracle_rvsa_from_qkv(xn, qkv, P, pre, h, w, nH):
     return Oo[:, pt:pt + h, pl:pl + w].reshape(B, N, C)
 
 
-@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 3, 3, True), (14, 1, 2, False), (32, 1, 2, True)])
+@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 3, 3, True), (14, 1, 2, False), (16, 1, 2, True), (13, 1, 2, True), (32, 1, 2, True)])
 def test_full_attention_vs_oracle(grid, B, nH, rel):
     from mtp_b200 import ops
     C = nH * 64
@@ -170,17 +172,17 @@ def test_rvsa_backward_vs_oracle_autograd(grid, B, nH, big):
     torch.cuda.synchronize()
     errs = {}
     errs["dqkv"] = _close(dqkv.float().cpu().reshape(B, N, 3 * C), qkv.grad, 1.5e-2, "dqkv")
-    errs["rel_h"] = _close(g_rel_h.cpu(), Pl["a.rel_pos_h"].grad, 2e-3, "d rel_pos_h")
-    errs["rel_w"] = _close(g_rel_w.cpu(), Pl["a.rel_pos_w"].grad, 2e-3, "d rel_pos_w")
-    errs["table"] = _close(g_table.cpu(), Pl["a.relative_position_bias_table"].grad, 2e-3, "d bias table")
+    errs["rel_h"] = _close(g_rel_h.cpu(), Pl["a.rel_pos_h"].grad, 1e-2, "d rel_pos_h")
+    errs["rel_w"] = _close(g_rel_w.cpu(), Pl["a.rel_pos_w"].grad, 1e-2, "d rel_pos_w")
+    errs["table"] = _close(g_table.cpu(), Pl["a.relative_position_bias_table"].grad, 1e-2, "d bias table")
     for k in ("offsets", "scales", "angles"):
-        errs[k + "_w"] = _close(gw[k].cpu(), Pl[f"a.sampling_{k}.2.weight"].grad.reshape(-1, C), 5e-3, f"d sampling_{k}.weight")
-        errs[k + "_b"] = _close(gb[k].cpu(), Pl[f"a.sampling_{k}.2.bias"].grad, 5e-3, f"d sampling_{k}.bias")
+        errs[k + "_w"] = _close(gw[k].cpu(), Pl[f"a.sampling_{k}.2.weight"].grad.reshape(-1, C), 1.5e-2, f"d sampling_{k}.weight")
+        errs[k + "_b"] = _close(gb[k].cpu(), Pl[f"a.sampling_{k}.2.bias"].grad, 1.5e-2, f"d sampling_{k}.bias")
     errs["dyn"] = _close(dyn.float().cpu().reshape(B, N, C), xn.grad, 1.5e-2, "pooled-path grad")
     print("rvsa bwd", grid, {k: "%.1e" % v for k, v in errs.items()})
 
 
-@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 1, 3, True), (14, 1, 2, False), (20, 1, 2, True)])
+@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 1, 3, True), (14, 1, 2, False), (16, 1, 2, True), (13, 1, 2, True), (20, 1, 2, True)])
 def test_full_attention_backward_vs_autograd(grid, B, nH, rel):
     from mtp_b200 import ops
     C = nH * 64
