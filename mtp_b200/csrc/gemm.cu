@@ -177,7 +177,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[3
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN>
+// CL2: clusters of two CTAs working on vertically adjacent m-tiles of the same n-tile; each CTA fetches HALF of the shared B
+// tile and TMA-multicasts it to both, which cuts the per-SM L2->smem traffic per MMA (the measured limiter) by 1/3.
+template <int BN, bool A_MN, bool B_MN, bool CL2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep,
                  const int M, const int N, const int K, const int tiles_m, const int tiles_n) {
@@ -194,15 +196,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = tiles_m * tiles_n;
   const int k_blocks = (K + BK - 1) / BK;
+  // work items: single tiles, or (CL2) pairs of m-tiles handled by the two CTAs of a cluster in lockstep
+  const int crank = CL2 ? (int)cluster_ctarank() : 0;
+  const int m_groups = CL2 ? (tiles_m + 1) / 2 : tiles_m;
+  const int num_items = m_groups * tiles_n;
+  const int item0 = CL2 ? blockIdx.x / 2 : blockIdx.x;
+  const int item_stride = CL2 ? gridDim.x / 2 : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL2 ? 2 : 1);        // CL2: both CTAs' MMAs must have drained a stage before either refills it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -213,6 +220,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();       // peer barriers are initialised before any multicast can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -221,9 +229,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * BM;
-        const int n0 = (tile / tiles_m) * BN;
+      for (int item = item0; item < num_items; item += item_stride) {
+        const int m0 = ((item % m_groups) * (CL2 ? 2 : 1) + crank) * BM;
+        const int n0 = (item / m_groups) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -235,11 +243,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
           }
-          if (!B_MN) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
-          } else {
+          if (!CL2) {
+            if (!B_MN) {
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+            }
+          } else {                       // my half of B, multicast to both CTAs of the cluster
+            if (!B_MN) {
+              tma_load_2d_mcast(sb + crank * (BN / 2) * 128, &tmB, &full_bar[stage], kb * BK, n0 + crank * (BN / 2), 0x3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = crank * (BN / 128) + j;
+                tma_load_2d_mcast(sb + jj * 8192, &tmB, &full_bar[stage], n0 + jj * 64, kb * BK, 0x3);
+              }
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -253,7 +273,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -270,7 +290,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t b_desc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
             umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
+          if (CL2) umma_commit_mcast(&empty_bar[stage], 0x3);   // releases the stage in BOTH CTAs (my B half lives in both)
+          else umma_commit(&empty_bar[stage]);                  // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);                // accumulator complete
@@ -284,9 +305,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 64;        // 0..255 within the epilogue group
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * BM;
-      const int n0 = (tile / tiles_m) * BN;
+    for (int item = item0; item < num_items; item += item_stride) {
+      const int m0 = ((item % m_groups) * (CL2 ? 2 : 1) + crank) * BM;
+      const int n0 = (item / m_groups) * BN;
       float* bsm = bias_s + acc * BN;
       if (ep.bias != nullptr) {             // stage this tile's bias slice once (zeros beyond N)
         for (int i = et; i < BN; i += EPI_THREADS) {
@@ -324,6 +345,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();       // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -362,7 +384,7 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int 
   return MTP_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool CL2>
 static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const EpiParams& ep,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -371,47 +393,74 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
   // K-major: matrix [M rows, K cols], box rows = BM.  MN-major: matrix [K rows, M cols], box = 64 k-rows x 64 cols.
   rc = A_MN ? make_tmap(&tmA, A, K, M, lda, BK) : make_tmap(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = B_MN ? make_tmap(&tmB, B, K, N, ldb, BK) : make_tmap(&tmB, B, N, K, ldb, BN);
+  rc = B_MN ? make_tmap(&tmB, B, K, N, ldb, BK) : make_tmap(&tmB, B, N, K, ldb, CL2 ? BN / 2 : BN);
   if (rc) return rc;
   static bool attr_set = false;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CL2>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
-  const int grid = std::min(tiles_m * tiles_n, num_sms());
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, ep, M, N, K, tiles_m, tiles_n);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (CL2) {
+    const int items = ((tiles_m + 1) / 2) * tiles_n;
+    cfg.gridDim = dim3(2 * std::min(items, num_sms() / 2));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(std::min(tiles_m * tiles_n, num_sms()));
+  }
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ep, M, N, K, tiles_m, tiles_n);
+  if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "gemm_bf16_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_kernel");
 }
 
-// Wave-quantisation-aware tile width: minimise waves(BN) * (BN + overhead).
-static int pick_bn(int M, int N) {
+// Tile width and clustering by a wave-quantisation cost model.  Per k-block a CTA needs max(MMA time, smem-fill time):
+// the MMA takes BN/2 cycles x 4; the fill is bounded by the measured ~64 B/clk/SM L2->smem rate, and a 2-CTA cluster halves the
+// B bytes each SM pulls.  Cost = waves x (per-tile mainloop + fixed overhead).
+static void pick_config(int M, int N, bool b_mn, int& bn_out, bool& cl2_out) {
   const int sms = num_sms();
+  const int tiles_m = ceil_div(M, BM);
   const int cand[4] = {256, 192, 128, 64};
-  int best = 128;
   double best_cost = 1e30;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cand[i];
-    const long tiles = (long)ceil_div(M, BM) * ceil_div(N, bn);
-    const long waves = (tiles + sms - 1) / sms;
-    const double cost = (double)waves * (bn + 40.0);   // +40: fixed per-tile cost (pipeline fill, epilogue tail)
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+  bn_out = 128;
+  cl2_out = false;
+  for (int cl = 0; cl < 2; ++cl) {
+    if (cl == 1 && tiles_m < 2) continue;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cand[i];
+      if (cl == 1 && b_mn && bn % 128 != 0) continue;          // MN-major B is fetched in 64-column boxes: need an even count
+      const long items = (long)(cl ? (tiles_m + 1) / 2 : tiles_m) * ceil_div(N, bn);
+      const long slots = cl ? sms / 2 : sms;
+      const long waves = (items + slots - 1) / slots;
+      const double mma = 2.0 * bn;                               // cycles per 64-deep k-block
+      const double fill = (16384.0 + (cl ? 64.0 : 128.0) * bn) / 64.0;
+      const double cost = (double)waves * (std::max(mma, fill) + 90.0);     // +90: amortised prologue / epilogue tail per k-block scale
+      if (cost < best_cost) { best_cost = cost; bn_out = bn; cl2_out = cl == 1; }
+    }
   }
-  return best;
 }
 
 }  // namespace mtp
 
 using namespace mtp;
 
-#define DISPATCH_LAYOUT(BN_)                                                                                   \
-  do {                                                                                                         \
-    if (!a_mn_major && !b_mn_major) return launch_gemm<BN_, false, false>(A, lda, B, ldb, M, N, K, p, stream); \
-    if (!a_mn_major && b_mn_major) return launch_gemm<BN_, false, true>(A, lda, B, ldb, M, N, K, p, stream);   \
-    if (a_mn_major && b_mn_major) return launch_gemm<BN_, true, true>(A, lda, B, ldb, M, N, K, p, stream);     \
-    return launch_gemm<BN_, true, false>(A, lda, B, ldb, M, N, K, p, stream);                                  \
+#define DISPATCH_LAYOUT(BN_, CL_)                                                                                   \
+  do {                                                                                                              \
+    if (!a_mn_major && !b_mn_major) return launch_gemm<BN_, false, false, CL_>(A, lda, B, ldb, M, N, K, p, stream); \
+    if (!a_mn_major && b_mn_major) return launch_gemm<BN_, false, true, CL_>(A, lda, B, ldb, M, N, K, p, stream);   \
+    if (a_mn_major && b_mn_major) return launch_gemm<BN_, true, true, CL_>(A, lda, B, ldb, M, N, K, p, stream);     \
+    return launch_gemm<BN_, true, false, CL_>(A, lda, B, ldb, M, N, K, p, stream);                                  \
   } while (0)
 
 extern "C" int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N,
@@ -436,12 +485,32 @@ extern "C" int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
   p.mode = ep->mode; p.ldo = ep->ldo; p.bias = ep->bias; p.out = ep->out; p.out2 = ep->out2; p.aux = ep->aux;
   p.row_scale = ep->row_scale; p.rows_per_group = ep->rows_per_group; p.pos_rows = ep->pos_rows;
   p.accumulate = ep->accumulate; p.ps_h = ep->ps_h; p.ps_w = ep->ps_w; p.ps_cout = ep->ps_cout;
-  const int bn = force_bn ? force_bn : pick_bn(M, N);
-  switch (bn) {
-    case 64: DISPATCH_LAYOUT(64);
-    case 128: DISPATCH_LAYOUT(128);
-    case 192: DISPATCH_LAYOUT(192);
-    case 256: DISPATCH_LAYOUT(256);
-    default: return set_error(MTP_ERR_INVALID, "mtp_gemm_bf16: unsupported tile width %d", bn);
+  // force_bn: 0 = heuristic; otherwise tile width, +1000 to force the 2-CTA multicast cluster variant (tests / tuning)
+  int bn;
+  bool cl2;
+  if (force_bn == 0) {
+    pick_config(M, N, b_mn_major != 0, bn, cl2);
+  } else {
+    cl2 = force_bn >= 1000;
+    bn = force_bn % 1000;
+    MTP_REQUIRE(!cl2 || !b_mn_major || bn % 128 == 0, "mtp_gemm_bf16: clustered MN-major B needs a tile width of 128 or 256");
   }
+  if (cl2) {
+    switch (bn) {
+      case 64: DISPATCH_LAYOUT(64, true);
+      case 128: DISPATCH_LAYOUT(128, true);
+      case 192: DISPATCH_LAYOUT(192, true);
+      case 256: DISPATCH_LAYOUT(256, true);
+      default: break;
+    }
+  } else {
+    switch (bn) {
+      case 64: DISPATCH_LAYOUT(64, false);
+      case 128: DISPATCH_LAYOUT(128, false);
+      case 192: DISPATCH_LAYOUT(192, false);
+      case 256: DISPATCH_LAYOUT(256, false);
+      default: break;
+    }
+  }
+  return set_error(MTP_ERR_INVALID, "mtp_gemm_bf16: unsupported tile width %d", bn);
 }
