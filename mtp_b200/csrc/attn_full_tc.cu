@@ -59,13 +59,12 @@ __device__ __forceinline__ void ft_rel_terms(const uint8_t* Qs, const float* rel
 }
 
 // ================================================================================================== forward
-constexpr int FTF_SMEM = FT_TILE /*Q*/ + 2 * 2 * FT_TILE /*K,V*/ + 4 * FT_TILE /*P*/ + (2 * FT_TAB + 2 * 128 * 17) * 4 + 64 + 1024;
+constexpr int FTF_SMEM = FT_TILE /*Q*/ + 2 * 2 * FT_TILE /*K,V*/ + 4 * FT_TILE /*P*/ + (2 * FT_TAB + 2 * 128 * 17) * 4 + 64;
 
 __global__ void __launch_bounds__(FT_THREADS)
 full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                         __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int gh, int gw, int C, int nH, int use_rel) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Qs = sm;
   uint8_t* Ks = Qs + FT_TILE;              // 256 rows
   uint8_t* Vs = Ks + 2 * FT_TILE;
@@ -231,15 +230,14 @@ int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* re
 
 // ================================================================================================== backward
 // smem: Q | dO | K (256 rows) | V (256 rows) | P (2 atoms) | dS (2 atoms) | tables | per-row rel terms | dSh, dSw | D, lse
-constexpr int FTB_SMEM = 2 * FT_TILE + 4 * FT_TILE + 4 * FT_TILE + (2 * FT_TAB + 4 * 128 * 17 + 2 * 128) * 4 + 64 + 1024;
+constexpr int FTB_SMEM = 2 * FT_TILE + 4 * FT_TILE + 4 * FT_TILE + (2 * FT_TAB + 4 * 128 * 17 + 2 * 128) * 4 + 64;
 
 __global__ void __launch_bounds__(FT_THREADS)
 full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                         const float* __restrict__ lse, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                         __nv_bfloat16* __restrict__ dqkv, float* __restrict__ d_rel_h, float* __restrict__ d_rel_w, int N, int gh, int gw,
                         int C, int nH, int use_rel) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Qs = sm;
   uint8_t* Gs = Qs + FT_TILE;
   uint8_t* Ks = Gs + FT_TILE;
@@ -283,9 +281,9 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
 
   // per-thread partial sums of the rel-pos table gradients: outputs e = tid, tid+128, ... over [(2gh-1) + (2gw-1)] x 64
   const int rows_h = 2 * gh - 1, rows_w = 2 * gw - 1;
-  float relacc[32];
+  float relacc[64];            // thread r < rows_h (+32 for w): its row of the rel-pos table gradients, accumulated over query tiles
 #pragma unroll
-  for (int i = 0; i < 32; ++i) relacc[i] = 0.f;
+  for (int i = 0; i < 64; ++i) relacc[i] = 0.f;
 
   for (int q0 = 0, qt = 0; q0 < N; q0 += 128, ++qt) {
     ft_load_rows(Qs, base, C3, q0, 128, N);
@@ -430,27 +428,47 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         *reinterpret_cast<uint4*>(dst + 8 * c) = u;
       }
     }
-    // rel-pos table gradients of this query tile: dR[r][d] += scale * sum_{q, k: axis(q) - k + g - 1 == r} dSx[q][k] q[q][d]
+    // rel-pos table gradients of this query tile as one more MMA:  dR[r][:] = sum_q W[q][r] q[q][:]  with
+    // W[q][r] = dSh[q][qy - r + gh - 1] for r < 2gh-1 and W[q][32 + r] = dSw[q][qx - r + gw - 1] (zero when out of range).
     if (use_rel) {
-      __syncthreads();          // dSh / dSw of all rows complete
-      const int nq = min(128, N - q0);
-      int slot = 0;
-      for (int e = tid; e < (rows_h + rows_w) * 64; e += FT_THREADS, ++slot) {
-        const int d = e & 63, rr = e >> 6;
-        const bool is_h = rr < rows_h;
-        const int r = is_h ? rr : rr - rows_h;
-        const int g1 = is_h ? gh : gw;
-        float s = 0.f;
-        for (int i = 0; i < nq; ++i) {
-          const int qq = q0 + i;
-          const int k = (is_h ? qq / gw : qq % gw) - (r - (g1 - 1));
-          if (k >= 0 && k < g1) {
-            const float qd = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(Qs + tile_chunk_off(i, d >> 3) + (d & 7) * 2));
-            s += (is_h ? dSh : dSw)[i * 17 + k] * qd;
-          }
+      float wv[64];
+#pragma unroll
+      for (int r = 0; r < 64; ++r) {
+        float v = 0.f;
+        if (qvalid) {
+          if (r < 32) { const int k = qy - r + gh - 1; if (r < rows_h && k >= 0 && k < gh) v = dSh[tid * 17 + k]; }
+          else { const int k = qx - (r - 32) + gw - 1; if (r - 32 < rows_w && k >= 0 && k < gw) v = dSw[tid * 17 + k]; }
         }
-        relacc[slot] += s;
+        wv[r] = v;
       }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(wv[8 * c], wv[8 * c + 1]); u.y = pack_bf16x2(wv[8 * c + 2], wv[8 * c + 3]);
+        u.z = pack_bf16x2(wv[8 * c + 4], wv[8 * c + 5]); u.w = pack_bf16x2(wv[8 * c + 6], wv[8 * c + 7]);
+        *reinterpret_cast<uint4*>(Pt + tile_chunk_off(tid, c)) = u;                       // P tile is free: reuse it for W
+        *reinterpret_cast<uint4*>(Pt + FT_TILE + tile_chunk_off(tid, c)) = make_uint4(0, 0, 0, 0);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        tc_mma_tiles<true, true>(T_S + 64, smem_u32(Pt), FT_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      if (warp < 2) {           // rows 0..63 of the result
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(T_S + 64 + lane_base, r0);
+        tmem_ld_32x32(T_S + 64 + lane_base + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) { relacc[d] += __uint_as_float(r0[d]); relacc[32 + d] += __uint_as_float(r1[d]); }
+      }
+      tc_fence_before();
     }
     __syncthreads();            // Q / dO tiles and dSh / dSw are rewritten by the next query tile
   }
@@ -486,12 +504,13 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       }
     }
   }
-  if (use_rel) {
-    int slot = 0;
-    for (int e = tid; e < (rows_h + rows_w) * 64; e += FT_THREADS, ++slot) {
-      const int d = e & 63, rr = e >> 6;
-      float* dstp = rr < rows_h ? d_rel_h + (size_t)rr * 64 + d : d_rel_w + (size_t)(rr - rows_h) * 64 + d;
-      atomicAdd(dstp, scale * relacc[slot]);
+  if (use_rel && tid < 64) {
+    float* dstp = nullptr;
+    if (tid < rows_h) dstp = d_rel_h + (size_t)tid * 64;
+    else if (tid >= 32 && tid - 32 < rows_w) dstp = d_rel_w + (size_t)(tid - 32) * 64;
+    if (dstp != nullptr) {
+#pragma unroll
+      for (int d = 0; d < 64; ++d) atomicAdd(dstp + d, scale * relacc[d]);
     }
   }
   tc_fence_before();

@@ -18,8 +18,8 @@ namespace mtp {
 
 constexpr int WB_THREADS = 128;
 constexpr int WB_TILE = 128 * 128;
-// Q | K~ | V~ | dO | P (2 atoms) | dS (2 atoms) | rel tables | bias tables | coords | dSh,dSw | table partial | red | mbar | slot
-constexpr int WB_SMEM = 8 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 2 * 128 * 8 + 2 * 169 + 64) * 4 + 64 + 1024;
+// Q | K~ | V~ | dO | P (2 atoms) | dS (2 atoms) | W (2 atoms) | rel tables | bias tables | coords | dSh,dSw | red | mbar | slot
+constexpr int WB_SMEM = 10 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 2 * 128 * 8 + 64) * 4 + 64;
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -34,22 +34,21 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                         const float* __restrict__ rel_w, const float* __restrict__ bias_table, const float* __restrict__ lse,
                         const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dkv,
                         float* __restrict__ dparams, float* __restrict__ part_rel, float* __restrict__ part_table, const RvsaGeom g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Qs = sm;
   uint8_t* Ks = Qs + WB_TILE;
   uint8_t* Vs = Ks + WB_TILE;
   uint8_t* Gs = Vs + WB_TILE;
   uint8_t* Pt = Gs + WB_TILE;                 // 2 atoms
   uint8_t* St = Pt + 2 * WB_TILE;             // 2 atoms
-  float* relt = reinterpret_cast<float*>(St + 2 * WB_TILE);     // [2][13][64]
+  uint8_t* Wt = St + 2 * WB_TILE;             // 2 atoms: row q, column r = weight of q in d rel table row r (second atom zero)
+  float* relt = reinterpret_cast<float*>(Wt + 2 * WB_TILE);     // [2][13][64]
   float* tabs = relt + 2 * 13 * 64;           // [2][169]
   float* cpx = tabs + 2 * 169;                // [98]
   float* cpy = cpx + 98;
   float* dSh = cpy + 98;                      // [128][8]
   float* dSw = dSh + 128 * 8;
-  float* ptab = dSw + 128 * 8;                // [2][169] bias-table partial
-  float* red = ptab + 2 * 169;                // [64]
+  float* red = dSw + 128 * 8;                 // [64]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
@@ -69,11 +68,9 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     fence_barrier_init();
   }
   smem_zero(Qs, 4 * WB_TILE, tid, WB_THREADS);
+  smem_zero(Wt + WB_TILE, WB_TILE, tid, WB_THREADS);
   for (int i = tid; i < 2 * 13 * 64; i += WB_THREADS) relt[i] = i < 13 * 64 ? rel_h[i] : rel_w[i - 13 * 64];
-  for (int i = tid; i < 2 * 169; i += WB_THREADS) {
-    tabs[i] = bias_table[(i % 169) * g.nH + 2 * hp + i / 169];
-    ptab[i] = 0.f;
-  }
+  for (int i = tid; i < 2 * 169; i += WB_THREADS) tabs[i] = bias_table[(i % 169) * g.nH + 2 * hp + i / 169];
   if (tid < 98) {
     const int p = tid / NTOK, j = tid % NTOK;
     const float* prm = params + ((size_t)bw * g.nH + 2 * hp + p) * 8;
@@ -86,39 +83,54 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t T_S = tmem, T_DP = tmem + 128, T_DQ = tmem + 256, T_DK = tmem + 320, T_DV = tmem + 384;
+  const uint32_t T_S = tmem, T_DP = tmem + 128, T_DQ = tmem + 256, T_DK = tmem + 320, T_DV = tmem + 384, T_DR = tmem + 448;
 
-  // ---- gather
-  for (int i = warp; i < 2 * NTOK; i += WB_THREADS / 32) {
+  // ---- gather: 8 lanes per row, 16 B per lane (see the forward kernel)
+  for (int i = tid >> 3; i < 2 * NTOK; i += WB_THREADS / 8) {
+    const int c = tid & 7;
     const int p = i / NTOK, j = i % NTOK, r = 64 * p + j;
     const int head = 2 * hp + p;
-    const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + head * HD;
-    const uint32_t soff = tile_chunk_off(r, lane >> 2) + (lane & 3) * 4;
+    const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + head * HD + c * 8;
+    const uint32_t soff = tile_chunk_off(r, c);
     const int y = wy * WS + j / WS - g.pt, x = wx * WS + j % WS - g.pl;
     if (y >= 0 && y < g.h && x >= 0 && x < g.w) {
       const size_t t = (size_t)(b * g.h + y) * g.w + x;
-      *reinterpret_cast<uint32_t*>(Qs + soff) = *reinterpret_cast<const uint32_t*>(qkv + t * C3 + head * HD + lane * 2);
-      *reinterpret_cast<uint32_t*>(Gs + soff) = *reinterpret_cast<const uint32_t*>(dout + t * C + head * HD + lane * 2);
+      *reinterpret_cast<uint4*>(Qs + soff) = *reinterpret_cast<const uint4*>(qkv + t * C3 + head * HD + c * 8);
+      *reinterpret_cast<uint4*>(Gs + soff) = *reinterpret_cast<const uint4*>(dout + t * C + head * HD + c * 8);
     }
     const float px = cpx[i], py = cpy[i];
     const float fx0 = floorf(px), fy0 = floorf(py);
     const float ax = px - fx0, ay = py - fy0;
     const int x0 = (int)fx0 - g.pl, y0 = (int)fy0 - g.pt;
-    float2 ka = make_float2(0.f, 0.f), va = make_float2(0.f, 0.f);
+    uint4 kt[4], vt[4];
+    float wgt[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
-      const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
-      if (xx >= 0 && xx < g.w && yy >= 0 && yy < g.h) {
-        const __nv_bfloat16* src = qkv_b + (size_t)(yy * g.w + xx) * C3 + lane * 2;
-        const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C));
-        const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C));
-        ka.x += wgt * kv.x; ka.y += wgt * kv.y;
-        va.x += wgt * vv.x; va.y += wgt * vv.y;
+      const bool ok = xx >= 0 && xx < g.w && yy >= 0 && yy < g.h;
+      wgt[t] = ok ? ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay) : 0.f;
+      const __nv_bfloat16* src = qkv_b + (size_t)(ok ? yy * g.w + xx : 0) * C3;
+      kt[t] = *reinterpret_cast<const uint4*>(src + C);
+      vt[t] = *reinterpret_cast<const uint4*>(src + 2 * C);
+    }
+    float ka[8], va[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ka[e] = 0.f; va[e] = 0.f; }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t kw4[4] = {kt[t].x, kt[t].y, kt[t].z, kt[t].w}, vw4[4] = {vt[t].x, vt[t].y, vt[t].z, vt[t].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 kf = unpack_bf16x2(kw4[e]), vf = unpack_bf16x2(vw4[e]);
+        ka[2 * e] += wgt[t] * kf.x; ka[2 * e + 1] += wgt[t] * kf.y;
+        va[2 * e] += wgt[t] * vf.x; va[2 * e + 1] += wgt[t] * vf.y;
       }
     }
-    *reinterpret_cast<uint32_t*>(Ks + soff) = pack_bf16x2(ka.x, ka.y);
-    *reinterpret_cast<uint32_t*>(Vs + soff) = pack_bf16x2(va.x, va.y);
+    uint4 u;
+    u.x = pack_bf16x2(ka[0], ka[1]); u.y = pack_bf16x2(ka[2], ka[3]); u.z = pack_bf16x2(ka[4], ka[5]); u.w = pack_bf16x2(ka[6], ka[7]);
+    *reinterpret_cast<uint4*>(Ks + soff) = u;
+    u.x = pack_bf16x2(va[0], va[1]); u.y = pack_bf16x2(va[2], va[3]); u.z = pack_bf16x2(va[4], va[5]); u.w = pack_bf16x2(va[6], va[7]);
+    *reinterpret_cast<uint4*>(Vs + soff) = u;
   }
   fence_proxy_async_smem();
   __syncthreads();
@@ -147,10 +159,11 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
 #pragma unroll
       for (int k = 0; k < WS; ++k) {
-        const float* th = relt + (qy - k + WS - 1) * HD + c * 8;
-        const float* tw = relt + 13 * 64 + (qx - k + WS - 1) * HD + c * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { rh[k] += qv[e] * th[e]; rw[k] += qv[e] * tw[e]; }
+        const float4* th = reinterpret_cast<const float4*>(relt + (qy - k + WS - 1) * HD + c * 8);
+        const float4* tw = reinterpret_cast<const float4*>(relt + 13 * 64 + (qx - k + WS - 1) * HD + c * 8);
+        const float4 h0 = th[0], h1 = th[1], w0 = tw[0], w1 = tw[1];
+        rh[k] += qv[0] * h0.x + qv[1] * h0.y + qv[2] * h0.z + qv[3] * h0.w + qv[4] * h1.x + qv[5] * h1.y + qv[6] * h1.z + qv[7] * h1.w;
+        rw[k] += qv[0] * w0.x + qv[1] * w0.y + qv[2] * w0.z + qv[3] * w0.w + qv[4] * w1.x + qv[5] * w1.y + qv[6] * w1.z + qv[7] * w1.w;
       }
     }
   }
@@ -190,13 +203,27 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       sh[j / WS] += ds[j];
       sw[j % WS] += ds[j];
     }
-    if (qvalid) {
-#pragma unroll
-      for (int j = 0; j < NTOK; ++j)
-        atomicAdd(&ptab[p * 169 + (qy - j / WS + WS - 1) * (2 * WS - 1) + (qx - j % WS + WS - 1)], ds[j]);
-    }
 #pragma unroll
     for (int k = 0; k < WS; ++k) { dSh[tid * 8 + k] = sh[k]; dSw[tid * 8 + k] = sw[k]; }
+    {   // row q of W: column r < 13 -> dSh[q][qy - r + 6], column 13 + r -> dSw[q][qx - r + 6] (0 when out of range)
+      float wv[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        float v = 0.f;
+        if (r < 13) { const int k = qy - r + WS - 1; if (qvalid && k >= 0 && k < WS) v = dSh[tid * 8 + k]; }
+        else if (r < 26) { const int k = qx - (r - 13) + WS - 1; if (qvalid && k >= 0 && k < WS) v = dSw[tid * 8 + k]; }
+        wv[r] = v;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (c < 4) {
+          u.x = pack_bf16x2(wv[8 * c], wv[8 * c + 1]); u.y = pack_bf16x2(wv[8 * c + 2], wv[8 * c + 3]);
+          u.z = pack_bf16x2(wv[8 * c + 4], wv[8 * c + 5]); u.w = pack_bf16x2(wv[8 * c + 6], wv[8 * c + 7]);
+        }
+        *reinterpret_cast<uint4*>(Wt + tile_chunk_off(tid, c)) = u;
+      }
+    }
     uint8_t* p_mine = Pt + p * WB_TILE;
     uint8_t* p_other = Pt + (1 - p) * WB_TILE;
     uint8_t* s_mine = St + p * WB_TILE;
@@ -229,29 +256,39 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     tc_mma_tiles<false, true>(T_DQ, smem_u32(St), WB_TILE, smem_u32(Ks), 0, 128, 64, 128, false);
     tc_mma_tiles<true, true>(T_DK, smem_u32(St), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
     tc_mma_tiles<true, true>(T_DV, smem_u32(Pt), WB_TILE, smem_u32(Gs), 0, 128, 64, 128, false);
+    tc_mma_tiles<true, true>(T_DR, smem_u32(Wt), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);     // d rel tables = W^T Q (both heads)
     umma_commit(mbar);
   }
-  // meanwhile: per-CTA partials of d rel_pos_h / d rel_pos_w (both heads summed) and the bias-table partials
-  for (int e = tid; e < 2 * (2 * WS - 1) * HD; e += WB_THREADS) {
-    const int d = e % HD, r = (e / HD) % (2 * WS - 1), which = e / (HD * (2 * WS - 1));
+  // meanwhile: bias-table partials, one output per (head, displacement): sum of dS over the pairs with that displacement
+  for (int i = tid; i < 2 * 169; i += WB_THREADS) {
+    const int pp = i / 169, idx = i % 169;
+    const int dy = idx / 13 - (WS - 1), dx = idx % 13 - (WS - 1);
+    const uint8_t* atom = St + pp * WB_TILE;
     float s = 0.f;
-    for (int pp = 0; pp < 2; ++pp)
-      for (int qa = 0; qa < WS; ++qa) {
-        const int k = qa - (r - (WS - 1));
-        if (k < 0 || k >= WS) continue;
-        for (int qb = 0; qb < WS; ++qb) {
-          const int row = 64 * pp + (which == 0 ? qa * WS + qb : qb * WS + qa);
-          s += (which == 0 ? dSh : dSw)[row * 8 + k] * tile_read(Qs, row, d);
-        }
-      }
-    part_rel[(size_t)blockIdx.x * (2 * (2 * WS - 1) * HD) + e] = s;
+    for (int qy2 = max(0, dy); qy2 < min(WS, WS + dy); ++qy2)
+      for (int qx2 = max(0, dx); qx2 < min(WS, WS + dx); ++qx2)
+        s += tile_read(atom, 64 * pp + qy2 * WS + qx2, (qy2 - dy) * WS + (qx2 - dx));
+    part_table[((size_t)bw * g.nH + 2 * hp + pp) * 169 + idx] = s;
   }
-  for (int i = tid; i < 2 * 169; i += WB_THREADS) part_table[((size_t)bw * g.nH + 2 * hp + i / 169) * 169 + i % 169] = ptab[i];
   mbar_wait(mbar, 1);
   tc_fence_after();
 
-  // ---- dq row -> dqkv
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  if (warp == 0) {          // rows 0..12 = d rel_pos_h partial, rows 13..25 = d rel_pos_w partial (both heads of this CTA)
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(T_DR + lane_base, r0);
+    tmem_ld_32x32(T_DR + lane_base + 32, r1);
+    tmem_ld_wait();
+    if (tid < 26) {
+      float* dst = part_rel + (size_t)blockIdx.x * (2 * (2 * WS - 1) * HD) + tid * HD;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(__uint_as_float(r0[4 * c]), __uint_as_float(r0[4 * c + 1]), __uint_as_float(r0[4 * c + 2]), __uint_as_float(r0[4 * c + 3]));
+        *reinterpret_cast<float4*>(dst + 32 + 4 * c) = make_float4(__uint_as_float(r1[4 * c]), __uint_as_float(r1[4 * c + 1]), __uint_as_float(r1[4 * c + 2]), __uint_as_float(r1[4 * c + 3]));
+      }
+    }
+  }
+  // ---- dq row -> dqkv
   {
     const int y = wy * WS + qy - g.pt, x = wx * WS + qx - g.pl;
     const bool tok_ok = qvalid && y >= 0 && y < g.h && x >= 0 && x < g.w;

@@ -19,14 +19,13 @@ namespace mtp {
 constexpr int WTC_THREADS = 128;
 constexpr int WTC_TILE = 128 * 128;                       // bytes of one 128-row tile
 // smem: Q | K~ | V~ | P (2 atoms) | rel_h,rel_w fp32 [2][13][64] | table [2][169] | coords [2][98] | mbar | tmem slot
-constexpr int WTC_SMEM = 5 * WTC_TILE + 2 * 13 * 64 * 4 + 2 * 169 * 4 + 2 * 98 * 4 + 64 + 1024;
+constexpr int WTC_SMEM = 5 * WTC_TILE + 2 * 13 * 64 * 4 + 2 * 169 * 4 + 2 * 98 * 4 + 64;
 
 __global__ void __launch_bounds__(WTC_THREADS)
 rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
                         const float* __restrict__ rel_w, const float* __restrict__ bias_table, __nv_bfloat16* __restrict__ out,
                         float* __restrict__ lse, const RvsaGeom g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t sm[];      // indexed directly so every access stays in the shared state space
   uint8_t* Qs = sm;
   uint8_t* Ks = Qs + WTC_TILE;
   uint8_t* Vs = Ks + WTC_TILE;
@@ -68,33 +67,48 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // ---- gather: one warp per (problem, token) row, lane = 2 head dims
-  for (int i = warp; i < 2 * NTOK; i += WTC_THREADS / 32) {
+  // ---- gather: 8 lanes per (problem, token) row, 16 B (8 head dims) per lane -> 16 rows per pass, 9 x 128-bit loads in flight
+  for (int i = tid >> 3; i < 2 * NTOK; i += WTC_THREADS / 8) {
+    const int c = tid & 7;
     const int p = i / NTOK, j = i % NTOK, r = 64 * p + j;
-    const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + (2 * hp + p) * HD;
-    const uint32_t soff = tile_chunk_off(r, lane >> 2) + (lane & 3) * 4;
+    const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + (2 * hp + p) * HD + c * 8;
+    const uint32_t soff = tile_chunk_off(r, c);
     const int y = wy * WS + j / WS - g.pt, x = wx * WS + j % WS - g.pl;
     if (y >= 0 && y < g.h && x >= 0 && x < g.w)
-      *reinterpret_cast<uint32_t*>(Qs + soff) = *reinterpret_cast<const uint32_t*>(qkv_b + (size_t)(y * g.w + x) * C3 + lane * 2);
+      *reinterpret_cast<uint4*>(Qs + soff) = *reinterpret_cast<const uint4*>(qkv_b + (size_t)(y * g.w + x) * C3);
     const float px = cpx[i], py = cpy[i];
     const float fx0 = floorf(px), fy0 = floorf(py);
     const float ax = px - fx0, ay = py - fy0;
     const int x0 = (int)fx0 - g.pl, y0 = (int)fy0 - g.pt;
-    float2 ka = make_float2(0.f, 0.f), va = make_float2(0.f, 0.f);
+    uint4 kt[4], vt[4];
+    float wgt[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
-      const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
-      if (xx >= 0 && xx < g.w && yy >= 0 && yy < g.h) {
-        const __nv_bfloat16* src = qkv_b + (size_t)(yy * g.w + xx) * C3 + lane * 2;
-        const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C));
-        const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C));
-        ka.x += wgt * kv.x; ka.y += wgt * kv.y;
-        va.x += wgt * vv.x; va.y += wgt * vv.y;
+      const bool ok = xx >= 0 && xx < g.w && yy >= 0 && yy < g.h;
+      wgt[t] = ok ? ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay) : 0.f;
+      const __nv_bfloat16* src = qkv_b + (size_t)(ok ? yy * g.w + xx : 0) * C3;
+      kt[t] = *reinterpret_cast<const uint4*>(src + C);
+      vt[t] = *reinterpret_cast<const uint4*>(src + 2 * C);
+    }
+    float ka[8], va[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ka[e] = 0.f; va[e] = 0.f; }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t kw4[4] = {kt[t].x, kt[t].y, kt[t].z, kt[t].w}, vw4[4] = {vt[t].x, vt[t].y, vt[t].z, vt[t].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 kf = unpack_bf16x2(kw4[e]), vf = unpack_bf16x2(vw4[e]);
+        ka[2 * e] += wgt[t] * kf.x; ka[2 * e + 1] += wgt[t] * kf.y;
+        va[2 * e] += wgt[t] * vf.x; va[2 * e + 1] += wgt[t] * vf.y;
       }
     }
-    *reinterpret_cast<uint32_t*>(Ks + soff) = pack_bf16x2(ka.x, ka.y);
-    *reinterpret_cast<uint32_t*>(Vs + soff) = pack_bf16x2(va.x, va.y);
+    uint4 u;
+    u.x = pack_bf16x2(ka[0], ka[1]); u.y = pack_bf16x2(ka[2], ka[3]); u.z = pack_bf16x2(ka[4], ka[5]); u.w = pack_bf16x2(ka[6], ka[7]);
+    *reinterpret_cast<uint4*>(Ks + soff) = u;
+    u.x = pack_bf16x2(va[0], va[1]); u.y = pack_bf16x2(va[2], va[3]); u.z = pack_bf16x2(va[4], va[5]); u.w = pack_bf16x2(va[6], va[7]);
+    *reinterpret_cast<uint4*>(Vs + soff) = u;
   }
   fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
   __syncthreads();
@@ -122,10 +136,11 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
 #pragma unroll
       for (int k = 0; k < WS; ++k) {
-        const float* th = relt + (qy - k + WS - 1) * HD + c * 8;
-        const float* tw = relt + 13 * 64 + (qx - k + WS - 1) * HD + c * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { rh[k] += qv[e] * th[e]; rw[k] += qv[e] * tw[e]; }
+        const float4* th = reinterpret_cast<const float4*>(relt + (qy - k + WS - 1) * HD + c * 8);
+        const float4* tw = reinterpret_cast<const float4*>(relt + 13 * 64 + (qx - k + WS - 1) * HD + c * 8);
+        const float4 h0 = th[0], h1 = th[1], w0 = tw[0], w1 = tw[1];
+        rh[k] += qv[0] * h0.x + qv[1] * h0.y + qv[2] * h0.z + qv[3] * h0.w + qv[4] * h1.x + qv[5] * h1.y + qv[6] * h1.z + qv[7] * h1.w;
+        rw[k] += qv[0] * w0.x + qv[1] * w0.y + qv[2] * w0.z + qv[3] * w0.w + qv[4] * w1.x + qv[5] * w1.y + qv[6] * w1.z + qv[7] * w1.w;
       }
     }
   }

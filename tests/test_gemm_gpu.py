@@ -39,6 +39,25 @@ def test_gemm_layouts_tiles(layout, bn):
     assert (out - ref).norm().item() / ref.norm().item() < 1e-5      # fp32 accumulate of exact bf16 products
 
 
+@pytest.mark.parametrize("layout", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+@pytest.mark.parametrize("M", [392, 700])          # odd (4) and even (6) numbers of m-tiles: the odd case runs a dummy partner tile
+def test_gemm_cluster_multicast(layout, bn, M):
+    """2-CTA clusters with TMA-multicast of the shared B tile (force_bn = 1000 + width)."""
+    from mtp_b200 import ops, _lib as L
+    a_mn, b_mn = layout
+    if b_mn and bn % 128 != 0:
+        pytest.skip("MN-major B is multicast in 64-column boxes: needs an even number of boxes")
+    N, K = 448, 456
+    A = _mk((K, M) if a_mn else (M, K), seed=21)
+    B = _mk((K, N) if b_mn else (N, K), seed=22)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    ops.gemm(A, B, M, N, K, out, a_mn=a_mn, b_mn=b_mn, mode=L.EPI_F32, force_bn=1000 + bn)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, a_mn, b_mn)
+    assert (out - ref).norm().item() / ref.norm().item() < 1e-5
+
+
 @pytest.mark.parametrize("shape", [(1568, 3072, 1024), (1568, 1024, 4096), (6272, 2304, 768), (128, 64, 64), (1, 8, 8)])
 def test_gemm_model_shapes_bias_bf16(shape):
     from mtp_b200 import ops, _lib as L

@@ -39,7 +39,7 @@ for name, M, N, K, a_mn, b_mn, mode in shapes:
         out = torch.empty(M, N, device="cuda")
         kw["mode"] = L.EPI_F32
     row = {"name": name, "M": M, "N": N, "K": K}
-    for bn in ((0,) if only else (0, 64, 128, 192, 256)):
+    for bn in ((0,) if only else (0, 128, 192, 256, 1128, 1192, 1256)):
         try:
             for _ in range(3):
                 ops.gemm(A, B, M, N, K, out, a_mn=a_mn, b_mn=b_mn, force_bn=bn, **kw)
