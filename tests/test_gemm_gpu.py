@@ -41,7 +41,7 @@ def test_gemm_layouts_tiles(layout, bn):
 
 @pytest.mark.parametrize("layout", [(False, False), (False, True), (True, True), (True, False)])
 @pytest.mark.parametrize("bn", [64, 128, 192, 256])
-@pytest.mark.parametrize("M", [392, 700])          # odd (4) and even (6) numbers of m-tiles: the odd case runs a dummy partner tile
+@pytest.mark.parametrize("M", [392, 704])          # odd (4) and even (6) numbers of m-tiles: the odd case runs a dummy partner tile
 def test_gemm_cluster_multicast(layout, bn, M):
     """2-CTA clusters with TMA-multicast of the shared B tile (force_bn = 1000 + width)."""
     from mtp_b200 import ops, _lib as L
