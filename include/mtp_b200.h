@@ -101,7 +101,7 @@ int mtp_add_bf16_into_f32(const void* in_bf16, float* out, size_t n, mtp_stream_
  * Rotated varied-size window attention (RVSA), forward.  RotatedVariedSizeWindowAttention.forward, [V]:287-433.
  * mtp_rvsa_sampling_fwd: AvgPool2d(7) over the zero-padded LN'd tokens -> LeakyReLU -> the three 1x1 convs
  *   ([V]:228-243,347,354-368).  yn_bf16 [T, C]; w_off/w_scale [2nH, C], w_angle [nH, C] (Conv2d weights flattened);
- *   pooled (optional out) [B*nWin, C] pre-activation means (saved for backward);
+ *   pooled (out) [B*nWin, C] pre-activation means (intermediate of the two kernels; saved for backward);
  *   params (out) [B*nWin, nH, 8] = (ox, oy, sx, sy, theta, -, -, -) with the [V]:359-360 divisions applied.
  * mtp_rvsa_attn_fwd: coords ([V]:372-385) -> bilinear K/V gather ([V]:397-404) -> scores + decomposed rel-pos with the
  *   UNscaled q ([V]:410-412) + bias table ([V]:414-418) -> softmax -> PV -> un-window + crop ([V]:420-428).

@@ -16,57 +16,62 @@
 namespace mtp {
 
 // ------------------------------------------------------------------------------------------------ sampling params
-__global__ void __launch_bounds__(256)
-rvsa_sampling_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float* __restrict__ w_off, const float* __restrict__ b_off,
-                         const float* __restrict__ w_sc, const float* __restrict__ b_sc, const float* __restrict__ w_ang,
-                         const float* __restrict__ b_ang, float* __restrict__ pooled_out, float* __restrict__ params,
-                         const RvsaGeom g) {
-  extern __shared__ float act[];                         // [C] LeakyReLU(pooled)
-  const int bw = blockIdx.x;                             // (image, window)
+// (1) zero-padded 7x7 mean of the LN'd tokens: CTA = (image-window, 256-channel slab), thread = 4 channels
+__global__ void __launch_bounds__(64)
+rvsa_pool_fwd_kernel(const __nv_bfloat16* __restrict__ yn, float* __restrict__ pooled, const RvsaGeom g) {
+  const int bw = blockIdx.x;
   const int b = bw / (g.nh * g.nw), win = bw % (g.nh * g.nw);
   const int wy = win / g.nw, wx = win % g.nw;
-  const int C = g.C;
-  for (int c = threadIdx.x * 4; c < C; c += 256 * 4) {
-    float4 s = make_float4(0, 0, 0, 0);
-    for (int i = 0; i < WS * WS; ++i) {
-      const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
-      if (y >= 0 && y < g.h && x >= 0 && x < g.w) {
-        const uint2 u = *reinterpret_cast<const uint2*>(yn + ((size_t)(b * g.h + y) * g.w + x) * C + c);
-        const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y);
-        s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
+  const int c = blockIdx.y * 256 + threadIdx.x * 4;
+  if (c >= g.C) return;
+  float4 s = make_float4(0, 0, 0, 0);
+#pragma unroll 7
+  for (int i = 0; i < WS * WS; ++i) {
+    const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
+    if (y >= 0 && y < g.h && x >= 0 && x < g.w) {
+      const uint2 u = *reinterpret_cast<const uint2*>(yn + ((size_t)(b * g.h + y) * g.w + x) * g.C + c);
+      const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y);
+      s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
+    }
+  }
+  const float inv = 1.0f / (WS * WS);                    // zeros of the padding are part of the mean ([V]:347,354)
+  s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+  *reinterpret_cast<float4*>(pooled + (size_t)bw * g.C + c) = s;
+}
+
+// (2) the three 1x1 convs on LeakyReLU(pooled): CTA = one of the 5nH output channels, its weight row kept in registers,
+//     warps stride over the (image, window) rows
+__global__ void __launch_bounds__(256)
+rvsa_heads_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w_off, const float* __restrict__ b_off,
+                      const float* __restrict__ w_sc, const float* __restrict__ b_sc, const float* __restrict__ w_ang,
+                      const float* __restrict__ b_ang, float* __restrict__ params, int n_bw, const RvsaGeom g) {
+  const int o = blockIdx.x, nH = g.nH, C = g.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // output order: [0,2nH) offsets (head-major, x then y), [2nH,4nH) scales, [4nH,5nH) angle
+  const float* wrow;
+  float bias;
+  int n, slot;
+  float div = 1.0f;
+  if (o < 2 * nH) { wrow = w_off + (size_t)o * C; bias = b_off[o]; n = o >> 1; slot = o & 1; div = (float)((slot == 0 ? g.h : g.w) / WS); }   // sic: x by h//7, y by w//7
+  else if (o < 4 * nH) { wrow = w_sc + (size_t)(o - 2 * nH) * C; bias = b_sc[o - 2 * nH]; n = (o - 2 * nH) >> 1; slot = 2 + ((o - 2 * nH) & 1); }
+  else { wrow = w_ang + (size_t)(o - 4 * nH) * C; bias = b_ang[o - 4 * nH]; n = o - 4 * nH; slot = 4; }
+  float4 wv[8];                                           // C <= 1024: 8 float4 per lane
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wv[i] = (i * 128 + lane * 4 < C) ? __ldg(reinterpret_cast<const float4*>(wrow + i * 128 + lane * 4)) : make_float4(0, 0, 0, 0);
+  for (int bw = warp; bw < n_bw; bw += 8) {
+    const float* pr = pooled + (size_t)bw * C;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i * 128 + lane * 4 < C) {
+        float4 a = *reinterpret_cast<const float4*>(pr + i * 128 + lane * 4);
+        a.x = a.x >= 0 ? a.x : 0.01f * a.x; a.y = a.y >= 0 ? a.y : 0.01f * a.y;
+        a.z = a.z >= 0 ? a.z : 0.01f * a.z; a.w = a.w >= 0 ? a.w : 0.01f * a.w;
+        s += wv[i].x * a.x + wv[i].y * a.y + wv[i].z * a.z + wv[i].w * a.w;
       }
     }
-    const float inv = 1.0f / (WS * WS);                  // zeros of the padding are part of the mean ([V]:347,354)
-    s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
-    if (pooled_out) *reinterpret_cast<float4*>(pooled_out + (size_t)bw * C + c) = s;
-    act[c] = s.x >= 0 ? s.x : 0.01f * s.x;
-    act[c + 1] = s.y >= 0 ? s.y : 0.01f * s.y;
-    act[c + 2] = s.z >= 0 ? s.z : 0.01f * s.z;
-    act[c + 3] = s.w >= 0 ? s.w : 0.01f * s.w;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nH = g.nH;
-  for (int o = warp; o < 5 * nH; o += 8) {
-    // output order: [0,2nH) offsets (head-major, x then y), [2nH,4nH) scales, [4nH,5nH) angle
-    const float* wrow;
-    float bias;
-    if (o < 2 * nH) { wrow = w_off + (size_t)o * C; bias = b_off[o]; }
-    else if (o < 4 * nH) { wrow = w_sc + (size_t)(o - 2 * nH) * C; bias = b_sc[o - 2 * nH]; }
-    else { wrow = w_ang + (size_t)(o - 4 * nH) * C; bias = b_ang[o - 4 * nH]; }
-    float s = 0.f;
-    for (int c = lane * 4; c < C; c += 128) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + c));
-      s += wv.x * act[c] + wv.y * act[c + 1] + wv.z * act[c + 2] + wv.w * act[c + 3];
-    }
     s = warp_sum(s) + bias;
-    if (lane == 0) {
-      int n, slot;
-      if (o < 2 * nH) { n = o >> 1; slot = o & 1; s /= (float)((slot == 0 ? g.h : g.w) / WS); }   // sic: x by h//7, y by w//7
-      else if (o < 4 * nH) { n = (o - 2 * nH) >> 1; slot = 2 + ((o - 2 * nH) & 1); }
-      else { n = o - 4 * nH; slot = 4; }
-      params[((size_t)bw * nH + n) * 8 + slot] = s;
-    }
+    if (lane == 0) params[((size_t)bw * nH + n) * 8 + slot] = s / div;
   }
 }
 
@@ -251,14 +256,18 @@ int launch_rvsa_attn_fwd_tc(const void* qkv, const float* params, const float* r
 using namespace mtp;
 
 extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, const float* b_off, const float* w_scale,
-                                     const float* b_scale, const float* w_angle, const float* b_angle, float* pooled,
-                                     float* params, int B, int h, int w, int C, int nH, mtp_stream_t stream) {
-  MTP_REQUIRE(yn_bf16 && w_off && b_off && w_scale && b_scale && w_angle && b_angle && params, "mtp_rvsa_sampling_fwd: null pointer");
-  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD, "mtp_rvsa_sampling_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported (need h,w>=7, C==64*nH)", B, h, w, C, nH);
+                                     const float* b_scale, const float* w_angle, const float* b_angle, float* pooled, float* params,
+                                     int B, int h, int w, int C, int nH, mtp_stream_t stream) {
+  MTP_REQUIRE(yn_bf16 && w_off && b_off && w_scale && b_scale && w_angle && b_angle && pooled && params, "mtp_rvsa_sampling_fwd: null pointer");
+  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && C <= 1024, "mtp_rvsa_sampling_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported (need h,w>=7, C==64*nH<=1024)", B, h, w, C, nH);
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
-  rvsa_sampling_fwd_kernel<<<B * g.nh * g.nw, 256, C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(yn_bf16), w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g);
-  return check_launch("rvsa_sampling_fwd_kernel");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n_bw = B * g.nh * g.nw;
+  rvsa_pool_fwd_kernel<<<dim3(n_bw, ceil_div(C, 256)), 64, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g);
+  int rc = check_launch("rvsa_pool_fwd_kernel");
+  if (rc) return rc;
+  rvsa_heads_fwd_kernel<<<5 * nH, 256, 0, st>>>(pooled, w_off, b_off, w_scale, b_scale, w_angle, b_angle, params, n_bw, g);
+  return check_launch("rvsa_heads_fwd_kernel");
 }
 
 extern "C" int mtp_rvsa_attn_fwd(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,

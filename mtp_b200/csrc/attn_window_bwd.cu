@@ -390,16 +390,19 @@ rvsa_sampling_bwd_kernel(const float* __restrict__ dparams, const float* __restr
     else if (o < 4 * nH) v = dparams[((size_t)bw * nH + ((o - 2 * nH) >> 1)) * 8 + 2 + ((o - 2 * nH) & 1)];
     else v = dparams[((size_t)bw * nH + (o - 4 * nH)) * 8 + 4];
     gs[o] = v;
-    g_out[(size_t)bw * 5 * nH + o] = v;
+    if (blockIdx.y == 0) g_out[(size_t)bw * 5 * nH + o] = v;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float s = 0.f;
-    for (int o = 0; o < 2 * nH; ++o) s += gs[o] * __ldg(w_off + (size_t)o * C + c);
-    for (int o = 0; o < 2 * nH; ++o) s += gs[2 * nH + o] * __ldg(w_sc + (size_t)o * C + c);
-    for (int o = 0; o < nH; ++o) s += gs[4 * nH + o] * __ldg(w_ang + (size_t)o * C + c);
+  const int c = blockIdx.y * 256 + threadIdx.x;          // CTA = (image-window, 256-channel slab)
+  if (c < C) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int o = 0; o < 2 * nH; ++o) {
+      s0 += gs[o] * __ldg(w_off + (size_t)o * C + c);
+      s1 += gs[2 * nH + o] * __ldg(w_sc + (size_t)o * C + c);
+    }
+    for (int o = 0; o < nH; ++o) s0 += gs[4 * nH + o] * __ldg(w_ang + (size_t)o * C + c);
     const float p = pooled[(size_t)bw * C + c];
-    dpooled[(size_t)bw * C + c] = (p >= 0.f ? 1.0f : 0.01f) * s;
+    dpooled[(size_t)bw * C + c] = (p >= 0.f ? 1.0f : 0.01f) * (s0 + s1);
   }
 }
 
@@ -524,7 +527,7 @@ extern "C" int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, 
   const int n_bw = B * g.nh * g.nw;
   float* g_out = reinterpret_cast<float*>(workspace);            // [n_bw][5nH]
   float* dpooled = g_out + (size_t)n_bw * 5 * nH;                // [n_bw][C]
-  rvsa_sampling_bwd_kernel<<<n_bw, 256, 0, st>>>(dparams, pooled, w_off, w_scale, w_angle, g_out, dpooled, g);
+  rvsa_sampling_bwd_kernel<<<dim3(n_bw, ceil_div(C, 256)), 256, 0, st>>>(dparams, pooled, w_off, w_scale, w_angle, g_out, dpooled, g);
   int rc = check_launch("rvsa_sampling_bwd_kernel");
   if (rc) return rc;
   rvsa_sampling_wgrad_kernel<<<dim3(ceil_div(C, 256), 5 * nH), 256, 0, st>>>(g_out, pooled, dw_off, db_off, dw_scale, db_scale, dw_angle,

@@ -83,7 +83,7 @@ def rvsa_sampling_fwd(yn, w_off, b_off, w_sc, b_sc, w_ang, b_ang, B, h, w, nH, s
     C = yn.shape[-1]
     nwin = ((h + 6) // 7) * ((w + 6) // 7)
     params = torch.zeros(B * nwin, nH, 8, device=yn.device, dtype=F32)
-    pooled = torch.empty(B * nwin, C, device=yn.device, dtype=F32) if save_pooled else None
+    pooled = torch.empty(B * nwin, C, device=yn.device, dtype=F32)       # written by the pooling kernel, read by the conv kernel
     L.call("mtp_rvsa_sampling_fwd", yn.data_ptr(), w_off.data_ptr(), b_off.data_ptr(), w_sc.data_ptr(), b_sc.data_ptr(),
            w_ang.data_ptr(), b_ang.data_ptr(), _p(pooled), params.data_ptr(), B, h, w, C, nH, _stream())
     return params, pooled
