@@ -23,10 +23,10 @@ constexpr int GEMM_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epil
 constexpr int EPI_THREADS = 256;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
-template <int BN>
+template <int BN, bool PAIR = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;      // PAIR: each CTA stages half of the pair's B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -177,13 +177,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[3
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-// CL2: clusters of two CTAs working on vertically adjacent m-tiles of the same n-tile; each CTA fetches HALF of the shared B
-// tile and TMA-multicasts it to both, which cuts the per-SM L2->smem traffic per MMA (the measured limiter) by 1/3.
+// CL2 (cta_group::2): the two CTAs of a cluster compute one 256 x BN tile with a single MMA stream issued by the leader
+// (even rank).  Each CTA stages its 128 rows of A and HALF of B (BN/2 columns) and accumulates its 128 rows in its own TMEM;
+// the tensor cores read the other half of B from the peer's shared memory.  This cuts the bytes each SM must pull in per MMA
+// by a third, which is what bounds the 1-CTA kernel (measured: ~70 B/clk/SM of operand ingress regardless of L2 multicast).
 template <int BN, bool A_MN, bool B_MN, bool CL2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep,
                  const int M, const int N, const int K, const int tiles_m, const int tiles_n) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL2>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -209,15 +211,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL2 ? 2 : 1);        // CL2: both CTAs' MMAs must have drained a stage before either refills it
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], EPI_THREADS / 32);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], (CL2 ? 2 : 1) * EPI_THREADS / 32);   // one arrive per epilogue warp (CL2: of both CTAs, on the leader)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (CL2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   if (CL2) cluster_sync_all();       // peer barriers are initialised before any multicast can arrive
@@ -234,14 +239,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = (item / m_groups) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          if (!A_MN) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-          } else {
+          if (!CL2) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+            }
+          } else {
+            // both CTAs' bytes are credited to the LEADER's full barrier (only the leader waits on it and issues the MMAs)
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+            }
           }
           if (!CL2) {
             if (!B_MN) {
@@ -250,15 +266,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
             }
-          } else {                       // my half of B, multicast to both CTAs of the cluster
+          } else {                       // my half of the pair's B tile (columns [n0 + crank*BN/2, +BN/2))
             if (!B_MN) {
-              tma_load_2d_mcast(sb + crank * (BN / 2) * 128, &tmB, &full_bar[stage], kb * BK, n0 + crank * (BN / 2), 0x3);
+              tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, n0 + crank * (BN / 2));
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) {
-                const int jj = crank * (BN / 128) + j;
-                tma_load_2d_mcast(sb + jj * 8192, &tmB, &full_bar[stage], n0 + jj * 64, kb * BK, 0x3);
-              }
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &tmB, &full_bar[stage], n0 + crank * (BN / 2) + j * 64, kb * BK);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -267,8 +280,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && (!CL2 || crank == 0)) {
+      constexpr uint32_t idesc = make_idesc_bf16(CL2 ? 2 * BM : BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -288,13 +301,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // MN-major: 16 k-rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B; 64-wide MN atoms are 8192 B apart (LBO).
             const uint64_t a_desc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t b_desc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            if (CL2) umma_bf16_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
           }
-          if (CL2) umma_commit_mcast(&empty_bar[stage], 0x3);   // releases the stage in BOTH CTAs (my B half lives in both)
-          else umma_commit(&empty_bar[stage]);                  // smem slot reusable once these MMAs retire
+          if (CL2) umma_commit_2sm_mcast(&empty_bar[stage], 0x3);   // releases the stage in BOTH CTAs
+          else umma_commit(&empty_bar[stage]);                      // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);                // accumulator complete
+        if (CL2) umma_commit_2sm_mcast(&tmem_full[acc], 0x3);       // accumulators complete in both CTAs' TMEM
+        else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -337,7 +352,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CL2) mbar_arrive_remote(&tmem_empty[acc], 0);      // the leader's MMA thread waits for both CTAs' epilogues
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -348,7 +366,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CL2) cluster_sync_all();       // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CL2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -387,7 +406,7 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int 
 template <int BN, bool A_MN, bool B_MN, bool CL2>
 static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const EpiParams& ep,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL2>;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major: matrix [M rows, K cols], box rows = BM.  MN-major: matrix [K rows, M cols], box = 64 k-rows x 64 cols.
@@ -425,9 +444,9 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
   return check_launch("gemm_bf16_kernel");
 }
 
-// Tile width and clustering by a wave-quantisation cost model.  Per k-block a CTA needs max(MMA time, smem-fill time):
-// the MMA takes BN/2 cycles x 4; the fill is bounded by the measured ~64 B/clk/SM L2->smem rate, and a 2-CTA cluster halves the
-// B bytes each SM pulls.  Cost = waves x (per-tile mainloop + fixed overhead).
+// Tile width and pairing by a wave-quantisation cost model.  Per k-block a CTA needs max(MMA time, operand-ingress time):
+// the MMAs take 2*BN cycles; ingress is bounded by the measured ~70 B/clk/SM, and a cta_group::2 pair halves the B bytes each
+// SM stages.  Cost = waves x (per-k-block time + amortised fixed overhead).
 static void pick_config(int M, int N, bool b_mn, int& bn_out, bool& cl2_out) {
   const int sms = num_sms();
   const int tiles_m = ceil_div(M, BM);
@@ -444,7 +463,7 @@ static void pick_config(int M, int N, bool b_mn, int& bn_out, bool& cl2_out) {
       const long slots = cl ? sms / 2 : sms;
       const long waves = (items + slots - 1) / slots;
       const double mma = 2.0 * bn;                               // cycles per 64-deep k-block
-      const double fill = (16384.0 + (cl ? 64.0 : 128.0) * bn) / 64.0;
+      const double fill = (16384.0 + (cl ? 64.0 : 128.0) * bn) / 70.0;
       const double cost = (double)waves * (std::max(mma, fill) + 90.0);     // +90: amortised prologue / epilogue tail per k-block scale
       if (cost < best_cost) { best_cost = cost; bn_out = bn; cl2_out = cl == 1; }
     }
