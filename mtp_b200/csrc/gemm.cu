@@ -295,12 +295,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
+          // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups are 1024 B apart (SBO).
+          // MN-major: 16 k-rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B; 64-wide MN atoms are 8192 B apart (LBO).
+          // Descriptors are built once per stage; a k-step only bumps the 14-bit start-address field (units of 16 B).
+          const uint64_t a_desc0 = A_MN ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
+          const uint64_t b_desc0 = B_MN ? make_smem_desc(sb, 8192, 1024) : make_smem_desc(sb, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups are 1024 B apart (SBO).
-            // MN-major: 16 k-rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B; 64-wide MN atoms are 8192 B apart (LBO).
-            const uint64_t a_desc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t b_desc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            const uint64_t a_desc = a_desc0 + (uint64_t)(k * (A_MN ? 2048 : 32) >> 4);
+            const uint64_t b_desc = b_desc0 + (uint64_t)(k * (B_MN ? 2048 : 32) >> 4);
             if (CL2) umma_bf16_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
             else umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
           }

@@ -39,15 +39,20 @@ for name, M, N, K, a_mn, b_mn, mode in shapes:
         out = torch.empty(M, N, device="cuda")
         kw["mode"] = L.EPI_F32
     row = {"name": name, "M": M, "N": N, "K": K}
-    for bn in ((0,) if only else (0, 128, 192, 256, 1128, 1192, 1256)):
+    for bn in (0, 128, 192, 256, 1128, 1192, 1256):
         try:
             for _ in range(3):
                 ops.gemm(A, B, M, N, K, out, a_mn=a_mn, b_mn=b_mn, force_bn=bn, **kw)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
             n = 20
+            gr = torch.cuda.CUDAGraph()          # graph replay removes the ~10 us host cost per launch from the measurement
+            with torch.cuda.graph(gr):
+                for _ in range(n):
+                    ops.gemm(A, B, M, N, K, out, a_mn=a_mn, b_mn=b_mn, force_bn=bn, **kw)
+            gr.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(n):
-                ops.gemm(A, B, M, N, K, out, a_mn=a_mn, b_mn=b_mn, force_bn=bn, **kw)
+            gr.replay()
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / n
@@ -56,12 +61,18 @@ for name, M, N, K, a_mn, b_mn, mode in shapes:
             row[f"bn{bn}"] = str(ex)[:40]
     # cuBLAS reference for context
     if not a_mn and not b_mn:
+        Bt = B.t()
         for _ in range(3):
-            torch.matmul(A, B.t())
+            torch.matmul(A, Bt)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(20):
+                torch.matmul(A, Bt)
+        gr.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(20):
-            torch.matmul(A, B.t())
+        gr.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 20
