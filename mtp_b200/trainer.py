@@ -133,7 +133,8 @@ class PretrainStep:
         with torch.cuda.stream(self.comm_stream):
             dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
 
-    def _step_body(self, x):
+    def _forward_backward(self, x, on_bucket):
+        """forward + heads + backward; ``on_bucket(ranges)`` is called when flat-gradient ranges have become final."""
         m = self.model
         st = m._engine_state
         for k in self._convt_keys:                 # packed ConvTranspose weights are re-derived from the fp32 masters
@@ -146,12 +147,13 @@ class PretrainStep:
         self.G.touched = set()
         buckets = self._bucket_ranges() if self.world > 1 else {}
         engine_bwd.backward_impl(m, x, ctx, douts, grad_store=self.G,
-                                 after_block=(lambda i: self._allreduce_range(*buckets[i]) if i in buckets else None))
+                                 after_block=(lambda i: on_bucket([buckets[i]]) if i in buckets else None))
         if self.world > 1:
             # remaining pieces: the small region and the GEMM weights outside the blocks (patch embed, fpn)
-            for lo, hi in self.layout.tail_ranges(len(m.blocks), self.bucket_blocks):
-                self._allreduce_range(lo, hi)
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            on_bucket(self.layout.tail_ranges(len(m.blocks), self.bucket_blocks))
+        return loss
+
+    def _optimizer(self):
         stream = ops._stream()
         L.call("mtp_optim_step_begin", self.state.data_ptr(), stream)
         if self.max_norm and self.max_norm > 0:
@@ -160,30 +162,77 @@ class PretrainStep:
                self.flat_p16.data_ptr(), self.chunk_group.data_ptr(), self.group_lr.data_ptr(), self.group_wd.data_ptr(),
                self.state.data_ptr(), self.total, float(self.lr), float(self.eta_min), int(self.t_max), float(self.betas[0]),
                float(self.betas[1]), float(self.eps), float(self.max_norm or 0.0), 1.0 / self.world, stream)
+
+    def _reduce(self, ranges):
+        for lo, hi in ranges:
+            self._allreduce_range(lo, hi)
+
+    def _step_body(self, x):
+        loss = self._forward_backward(x, self._reduce)
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._optimizer()
         return loss
+
+    # ---- CUDA-graph execution -------------------------------------------------------------------------------------
+    # world == 1: the whole step is ONE graph.  world > 1: NCCL stays out of the graphs — the step is cut at the bucket
+    # boundaries into a chain of graphs sharing one memory pool; after each piece the bucket's all-reduce is launched
+    # eagerly on the comm stream, so it overlaps with the replay of the following pieces.
+    def _capture(self, x):
+        self._static_x = x.clone()
+        snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.flat_p16, self.state)]
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):                      # warm-up (kernel attributes, allocator, NCCL communicators)
+                self._step_body(self._static_x)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if self.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._static_loss = self._step_body(self._static_x)
+            self.graphs, self.reduce_after = [g], [[]]
+        else:
+            pool = torch.cuda.graph_pool_handle()
+            self.graphs, self.reduce_after = [], []
+            cap = torch.cuda.Stream(device=self.dev)
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                cur = [torch.cuda.CUDAGraph()]
+                cur[0].capture_begin(pool=pool)
+
+                def cut(ranges):                    # close the current piece, remember what to reduce after it, open the next
+                    cur[0].capture_end()
+                    self.graphs.append(cur[0])
+                    self.reduce_after.append(list(ranges))
+                    cur[0] = torch.cuda.CUDAGraph()
+                    cur[0].capture_begin(pool=pool)
+                self._static_loss = self._forward_backward(self._static_x, cut)
+                self._optimizer()                   # last piece: clip + AdamW (replayed after the comm stream has been joined)
+                cur[0].capture_end()
+                self.graphs.append(cur[0])
+                self.reduce_after.append([])
+            torch.cuda.current_stream().wait_stream(cap)
+        for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.flat_p16, self.state), snap):
+            dst.copy_(src)                          # warm-up must not advance the training state
+        del snap
+        torch.cuda.synchronize()
 
     def step(self, x: torch.Tensor) -> torch.Tensor:
         """One training step on a device-resident batch; returns the (device) scalar loss."""
         if not self.use_cuda_graph:
             return self._step_body(x)
         if self.graph is None:
-            self._static_x = x.clone()
-            # warm-up (kernel attributes, allocator) must not advance the training state: snapshot and restore it
-            snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.flat_p16, self.state)]
-            s = torch.cuda.Stream(device=self.dev)
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    self._step_body(self._static_x)
-            torch.cuda.current_stream().wait_stream(s)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._static_loss = self._step_body(self._static_x)
-            for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.flat_p16, self.state), snap):
-                dst.copy_(src)
-            del snap
+            self._capture(x)
+            self.graph = True
         self._static_x.copy_(x, non_blocking=True)
-        self.graph.replay()
+        last = len(self.graphs) - 1
+        for k, g in enumerate(self.graphs):
+            if k == last and self.world > 1:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+            g.replay()
+            self._reduce(self.reduce_after[k])
         return self._static_loss
 
     def step_from_host(self, x_host_pinned: torch.Tensor) -> float:
