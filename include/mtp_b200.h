@@ -75,6 +75,17 @@ typedef struct mtp_epilogue {
 int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N, int K,
                   const mtp_epilogue* ep, int force_bn /* 0 = heuristic */, mtp_stream_t stream);
 
+/* Two INDEPENDENT GEMMs in one persistent launch (e.g. the dgrad dX = dY W and the wgrad dW = dY^T X of one nn.Linear, which
+ * only share an input): the tiles of both are spread over the SMs by one longest-processing-time schedule, so SMs left idle
+ * by one problem's tile count work on the other, and a single launch / prologue / epilogue tail is paid. */
+typedef struct mtp_gemm_desc {
+  const void* A; int lda; int a_mn_major;
+  const void* B; int ldb; int b_mn_major;
+  int M, N, K;
+  const mtp_epilogue* ep;
+} mtp_gemm_desc;
+int mtp_gemm_bf16_dual(const mtp_gemm_desc* g0, const mtp_gemm_desc* g1, int force_bn, mtp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound; one warp per token row; fp32 statistics).
  * mtp_layernorm_fwd replaces nn.LayerNorm(eps=1e-6) norm1/norm2 ([V]:484,496,596) and, with x_is_bf16 + fuse_gelu,

@@ -22,11 +22,18 @@ class Epilogue(ctypes.Structure):
                 ("accumulate", c_int), ("ps_h", c_int), ("ps_w", c_int), ("ps_cout", c_int)]
 
 
+class GemmDesc(ctypes.Structure):
+    """struct mtp_gemm_desc (include/mtp_b200.h)."""
+    _fields_ = [("A", c_void_p), ("lda", c_int), ("a_mn_major", c_int), ("B", c_void_p), ("ldb", c_int), ("b_mn_major", c_int),
+                ("M", c_int), ("N", c_int), ("K", c_int), ("ep", ctypes.POINTER(Epilogue))]
+
+
 EPI_BF16, EPI_BF16_GELU, EPI_F32_RESID, EPI_F32_POS, EPI_F32, EPI_BF16_DGELU, EPI_BF16_PIXSHUF = range(7)
 
 # name -> argtypes (restype is always int unless listed in _SPECIAL)
 _SIGNATURES = {
     "mtp_gemm_bf16": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_int, c_void_p],
+    "mtp_gemm_bf16_dual": [ctypes.POINTER(GemmDesc), ctypes.POINTER(GemmDesc), c_int, c_void_p],
     "mtp_layernorm_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],
     "mtp_layernorm_bwd": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

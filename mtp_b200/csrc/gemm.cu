@@ -11,6 +11,11 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <queue>
+#include <vector>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -177,14 +182,32 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[3
 }
 
 // -------------------------------------------------------------------------------------------------------------------
+// Grouped persistent kernel: up to two independent GEMM problems (e.g. the dgrad and the wgrad of one Linear) share one
+// launch.  Work items (tiles, or 256-row tile pairs in CL2 mode) of both problems are assigned to the CTAs by a
+// longest-processing-time schedule computed on the host and passed BY VALUE, so all three warp roles walk the same list
+// without any device-side scheduler traffic, idle SMs of one problem are filled by the other, and one prologue/epilogue
+// tail is paid instead of two.
+//
 // CL2 (cta_group::2): the two CTAs of a cluster compute one 256 x BN tile with a single MMA stream issued by the leader
 // (even rank).  Each CTA stages its 128 rows of A and HALF of B (BN/2 columns) and accumulates its 128 rows in its own TMEM;
-// the tensor cores read the other half of B from the peer's shared memory.  This cuts the bytes each SM must pull in per MMA
-// by a third, which is what bounds the 1-CTA kernel (measured: ~70 B/clk/SM of operand ingress regardless of L2 multicast).
-template <int BN, bool A_MN, bool B_MN, bool CL2>
+// the tensor cores read the other half of B from the peer's shared memory.
+constexpr int MAX_SLOTS = 148;
+constexpr int MAX_ITEMS = 8;
+
+struct GemmProblem {
+  CUtensorMap tmA, tmB;
+  EpiParams ep;
+  int M, N, K, tiles_m, tiles_n, a_mn, b_mn;
+};
+
+struct Sched {
+  uint16_t count[MAX_SLOTS];
+  uint16_t item[MAX_SLOTS][MAX_ITEMS];
+};
+
+template <int BN, bool CL2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep,
-                 const int M, const int N, const int K, const int tiles_m, const int tiles_n) {
+gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__ GemmProblem p1, const __grid_constant__ Sched sched) {
   using Cfg = GemmCfg<BN, CL2>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -198,17 +221,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int k_blocks = (K + BK - 1) / BK;
-  // work items: single tiles, or (CL2) pairs of m-tiles handled by the two CTAs of a cluster in lockstep
   const int crank = CL2 ? (int)cluster_ctarank() : 0;
-  const int m_groups = CL2 ? (tiles_m + 1) / 2 : tiles_m;
-  const int num_items = m_groups * tiles_n;
-  const int item0 = CL2 ? blockIdx.x / 2 : blockIdx.x;
-  const int item_stride = CL2 ? gridDim.x / 2 : gridDim.x;
+  const int slot = CL2 ? blockIdx.x / 2 : blockIdx.x;
+  const int n_items = sched.count[slot];
+  const int groups0 = CL2 ? (p0.tiles_m + 1) / 2 : p0.tiles_m;
+  const int items0 = groups0 * p0.tiles_n;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&p0.tmA);
+    tma_prefetch_desc(&p0.tmB);
+    if (p1.tiles_m > 0) {
+      tma_prefetch_desc(&p1.tmA);
+      tma_prefetch_desc(&p1.tmB);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -225,53 +250,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();       // peer barriers are initialised before any multicast can arrive
+  if (CL2) cluster_sync_all();       // peer barriers are initialised before any remote signal can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+#define MTP_DECODE_ITEM(IT)                                                                      \
+  const int item_ = sched.item[slot][IT];                                                        \
+  const GemmProblem& P = item_ < items0 ? p0 : p1;                                               \
+  const int local_ = item_ < items0 ? item_ : item_ - items0;                                    \
+  const int mg_ = CL2 ? (P.tiles_m + 1) / 2 : P.tiles_m;                                         \
+  const int m0 = ((local_ % mg_) * (CL2 ? 2 : 1) + crank) * BM;                                  \
+  const int n0 = (local_ / mg_) * BN;                                                            \
+  const int k_blocks = (P.K + BK - 1) / BK;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = item0; item < num_items; item += item_stride) {
-        const int m0 = ((item % m_groups) * (CL2 ? 2 : 1) + crank) * BM;
-        const int n0 = (item / m_groups) * BN;
+      for (int it = 0; it < n_items; ++it) {
+        MTP_DECODE_ITEM(it)
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (!CL2) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            if (!A_MN) {
-              tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            if (!P.a_mn) {
+              tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+            }
+            if (!P.b_mn) {
+              tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[stage], n0 + j * 64, kb * BK);
             }
           } else {
             // both CTAs' bytes are credited to the LEADER's full barrier (only the leader waits on it and issues the MMAs)
             if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            if (!A_MN) {
-              tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            if (!P.a_mn) {
+              tma_load_2d_2sm(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
             }
-          }
-          if (!CL2) {
-            if (!B_MN) {
-              tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+            if (!P.b_mn) {       // my half of the pair's B tile: columns [n0 + crank*BN/2, +BN/2)
+              tma_load_2d_2sm(sb, &P.tmB, &full_bar[stage], kb * BK, n0 + crank * (BN / 2));
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
-            }
-          } else {                       // my half of the pair's B tile (columns [n0 + crank*BN/2, +BN/2))
-            if (!B_MN) {
-              tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * BK, n0 + crank * (BN / 2));
-            } else {
-#pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &tmB, &full_bar[stage], n0 + crank * (BN / 2) + j * 64, kb * BK);
+              for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &P.tmB, &full_bar[stage], n0 + crank * (BN / 2) + j * 64, kb * BK);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -281,12 +311,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && (!CL2 || crank == 0)) {
-      constexpr uint32_t idesc = make_idesc_bf16(CL2 ? 2 * BM : BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = item0; item < num_items; item += item_stride) {
+      for (int it = 0; it < n_items; ++it) {
+        MTP_DECODE_ITEM(it)
+        (void)m0; (void)n0;
+        const uint32_t idesc = make_idesc_bf16(CL2 ? 2 * BM : BM, BN, P.a_mn != 0, P.b_mn != 0);
+        // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups are 1024 B apart (SBO).
+        // MN-major: 16 k-rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B; 64-wide MN atoms are 8192 B apart (LBO).
+        const uint32_t a_lbo = P.a_mn ? 8192 : 16, b_lbo = P.b_mn ? 8192 : 16;
+        const uint64_t a_step = P.a_mn ? 128 : 2, b_step = P.b_mn ? 128 : 2;      // start-address units of 16 B per k-step
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -295,17 +331,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
-          // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; 8-row groups are 1024 B apart (SBO).
-          // MN-major: 16 k-rows = 2 swizzle atoms of 8 rows x 128 B = 2048 B; 64-wide MN atoms are 8192 B apart (LBO).
-          // Descriptors are built once per stage; a k-step only bumps the 14-bit start-address field (units of 16 B).
-          const uint64_t a_desc0 = A_MN ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
-          const uint64_t b_desc0 = B_MN ? make_smem_desc(sb, 8192, 1024) : make_smem_desc(sb, 16, 1024);
+          const uint64_t a_desc0 = make_smem_desc(sa, a_lbo, 1024);
+          const uint64_t b_desc0 = make_smem_desc(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t a_desc = a_desc0 + (uint64_t)(k * (A_MN ? 2048 : 32) >> 4);
-            const uint64_t b_desc = b_desc0 + (uint64_t)(k * (B_MN ? 2048 : 32) >> 4);
-            if (CL2) umma_bf16_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
-            else umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            if (CL2) umma_bf16_2sm(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
           }
           if (CL2) umma_commit_2sm_mcast(&empty_bar[stage], 0x3);   // releases the stage in BOTH CTAs
           else umma_commit(&empty_bar[stage]);                      // smem slot reusable once these MMAs retire
@@ -323,17 +354,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 64;        // 0..255 within the epilogue group
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = item0; item < num_items; item += item_stride) {
-      const int m0 = ((item % m_groups) * (CL2 ? 2 : 1) + crank) * BM;
-      const int n0 = (item / m_groups) * BN;
+    for (int it = 0; it < n_items; ++it) {
+      MTP_DECODE_ITEM(it)
+      (void)k_blocks;
+      const EpiParams& ep = P.ep;
+      const int M = P.M, N = P.N;
       float* bsm = bias_s + acc * BN;
       if (ep.bias != nullptr) {             // stage this tile's bias slice once (zeros beyond N)
         for (int i = et; i < BN; i += EPI_THREADS) {
           const int n = n0 + i;
           bsm[i] = n < N ? __ldg(ep.bias + (ep.mode == MTP_EPI_BF16_PIXSHUF ? n % ep.ps_cout : n)) : 0.f;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      // bias visible; also keeps the 8 warps on the same item
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
@@ -362,6 +395,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
+#undef MTP_DECODE_ITEM
 
   __syncwarp();
   tc_fence_before();
@@ -406,30 +440,113 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int 
   return MTP_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool CL2>
-static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const EpiParams& ep,
-                       cudaStream_t stream) {
+struct HostProblem {
+  const void* A; int lda, a_mn;
+  const void* B; int ldb, b_mn;
+  int M, N, K;
+  EpiParams ep;
+};
+
+// cycles of one 64-deep k-block of a BN-wide tile: the MMAs (2*BN) or operand ingress at the measured ~59 B/clk/SM
+static double kblock_cycles(int bn, bool cl2) { return std::max(2.0 * bn, (16384.0 + (cl2 ? 64.0 : 128.0) * bn) / 59.0); }
+static const double kTileFixedCycles = 1800.0;      // epilogue / pipeline fill per tile
+
+// Longest-processing-time schedule of the work items of up to two problems over the slots; returns the makespan (cycles).
+static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sched* out) {
+  const int slots = cl2 ? num_sms() / 2 : num_sms();
+  struct Item { int id; double cost; };
+  std::vector<Item> items;
+  int base = 0;
+  for (int p = 0; p < np; ++p) {
+    const int tiles_m = ceil_div(pr[p].M, BM), tiles_n = ceil_div(pr[p].N, bn);
+    const int n = (cl2 ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
+    const double c = ceil_div(pr[p].K, BK) * kblock_cycles(bn, cl2) + kTileFixedCycles;
+    for (int i = 0; i < n; ++i) items.push_back({base + i, c});
+    base += n;
+  }
+  if (base > 65535) return -1.0;
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+  std::vector<double> load(slots, 0.0);
+  std::vector<int> cnt(slots, 0);
+  // min-heap over (load, slot)
+  std::priority_queue<std::pair<double, int>, std::vector<std::pair<double, int>>, std::greater<std::pair<double, int>>> pq;
+  for (int s = 0; s < slots; ++s) pq.push({0.0, s});
+  for (const Item& it : items) {
+    auto top = pq.top();
+    pq.pop();
+    const int s = top.second;
+    if (cnt[s] >= MAX_ITEMS) return -1.0;       // does not fit the by-value schedule: caller falls back to another config
+    if (out) out->item[s][cnt[s]] = (uint16_t)it.id;
+    ++cnt[s];
+    load[s] = top.first + it.cost;
+    pq.push({load[s], s});
+  }
+  if (out) {
+    for (int s = 0; s < MAX_SLOTS; ++s) out->count[s] = s < slots ? (uint16_t)cnt[s] : 0;
+  }
+  return *std::max_element(load.begin(), load.end());
+}
+
+// config choice (cached per shape signature): minimise the LPT makespan over tile widths and single / paired CTAs
+struct Config { int bn; bool cl2; Sched sched; };
+
+static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
+  static std::map<std::vector<int>, Config> cache;
+  std::vector<int> key = {force_bn, np};
+  for (int p = 0; p < np; ++p) { key.push_back(pr[p].M); key.push_back(pr[p].N); key.push_back(pr[p].K); key.push_back(pr[p].b_mn); }
+  auto it = cache.find(key);
+  if (it != cache.end()) return &it->second;
+  bool any_bmn = false, all_pairable = true;
+  for (int p = 0; p < np; ++p) { any_bmn |= pr[p].b_mn != 0; all_pairable &= ceil_div(pr[p].M, BM) >= 2; }
+  Config best;
+  best.bn = 0;
+  double best_cost = 1e300;
+  const int cand[4] = {256, 192, 128, 64};
+  for (int cl = 0; cl < 2; ++cl) {
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cand[i];
+      if (force_bn) { if (cl != (force_bn >= 1000) || bn != force_bn % 1000) continue; }
+      else if (cl == 1 && !all_pairable) continue;
+      if (cl == 1 && any_bmn && bn % 128 != 0) continue;     // MN-major B is fetched in 64-column boxes: a pair needs an even count
+      const double c = build_schedule(pr, np, bn, cl == 1, nullptr);
+      if (c >= 0 && c < best_cost) { best_cost = c; best.bn = bn; best.cl2 = cl == 1; }
+    }
+  }
+  if (best.bn == 0) return nullptr;
+  build_schedule(pr, np, best.bn, best.cl2, &best.sched);
+  return &cache.emplace(key, best).first->second;
+}
+
+template <int BN, bool CL2>
+static int launch_grouped(const HostProblem* pr, int np, const Sched& sched, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CL2>;
-  CUtensorMap tmA, tmB;
-  int rc;
-  // K-major: matrix [M rows, K cols], box rows = BM.  MN-major: matrix [K rows, M cols], box = 64 k-rows x 64 cols.
-  rc = A_MN ? make_tmap(&tmA, A, K, M, lda, BK) : make_tmap(&tmA, A, M, K, lda, BM);
-  if (rc) return rc;
-  rc = B_MN ? make_tmap(&tmB, B, K, N, ldb, BK) : make_tmap(&tmB, B, N, K, ldb, CL2 ? BN / 2 : BN);
-  if (rc) return rc;
+  GemmProblem gp[2];
+  memset(gp, 0, sizeof(gp));
+  for (int p = 0; p < np; ++p) {
+    const HostProblem& h = pr[p];
+    int rc = h.a_mn ? make_tmap(&gp[p].tmA, h.A, h.K, h.M, h.lda, BK) : make_tmap(&gp[p].tmA, h.A, h.M, h.K, h.lda, BM);
+    if (rc) return rc;
+    rc = h.b_mn ? make_tmap(&gp[p].tmB, h.B, h.K, h.N, h.ldb, BK) : make_tmap(&gp[p].tmB, h.B, h.N, h.K, h.ldb, CL2 ? BN / 2 : BN);
+    if (rc) return rc;
+    gp[p].ep = h.ep;
+    gp[p].M = h.M; gp[p].N = h.N; gp[p].K = h.K;
+    gp[p].tiles_m = ceil_div(h.M, BM); gp[p].tiles_n = ceil_div(h.N, BN);
+    gp[p].a_mn = h.a_mn; gp[p].b_mn = h.b_mn;
+  }
   static bool attr_set = false;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CL2>;
+  auto kern = gemm_bf16_kernel<BN, CL2>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
+  const int slots = CL2 ? num_sms() / 2 : num_sms();
+  int used = 0;
+  for (int s = 0; s < slots; ++s) if (sched.count[s] > 0) used = s + 1;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   if (CL2) {
-    const int items = ((tiles_m + 1) / 2) * tiles_n;
-    cfg.gridDim = dim3(2 * std::min(items, num_sms() / 2));
+    cfg.gridDim = dim3(2 * used);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
@@ -437,102 +554,83 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    cfg.gridDim = dim3(std::min(tiles_m * tiles_n, num_sms()));
+    cfg.gridDim = dim3(used);
   }
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ep, M, N, K, tiles_m, tiles_n);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gp[0], gp[1], sched);
   if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "gemm_bf16_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_bf16_kernel");
 }
 
-// Tile width and pairing by a wave-quantisation cost model.  Per k-block a CTA needs max(MMA time, operand-ingress time):
-// the MMAs take 2*BN cycles; ingress is bounded by the measured ~70 B/clk/SM, and a cta_group::2 pair halves the B bytes each
-// SM stages.  Cost = waves x (per-k-block time + amortised fixed overhead).
-static void pick_config(int M, int N, bool b_mn, int& bn_out, bool& cl2_out) {
-  const int sms = num_sms();
-  const int tiles_m = ceil_div(M, BM);
-  const int cand[4] = {256, 192, 128, 64};
-  double best_cost = 1e30;
-  bn_out = 128;
-  cl2_out = false;
-  for (int cl = 0; cl < 2; ++cl) {
-    if (cl == 1 && tiles_m < 2) continue;
-    for (int i = 0; i < 4; ++i) {
-      const int bn = cand[i];
-      if (cl == 1 && b_mn && bn % 128 != 0) continue;          // MN-major B is fetched in 64-column boxes: need an even count
-      const long items = (long)(cl ? (tiles_m + 1) / 2 : tiles_m) * ceil_div(N, bn);
-      const long slots = cl ? sms / 2 : sms;
-      const long waves = (items + slots - 1) / slots;
-      const double mma = 2.0 * bn;                               // cycles per 64-deep k-block
-      const double fill = (16384.0 + (cl ? 64.0 : 128.0) * bn) / 70.0;
-      const double cost = (double)waves * (std::max(mma, fill) + 90.0);     // +90: amortised prologue / epilogue tail per k-block scale
-      if (cost < best_cost) { best_cost = cost; bn_out = bn; cl2_out = cl == 1; }
-    }
+static int validate_problem(const HostProblem& h) {
+  MTP_REQUIRE(h.A && h.B && h.ep.out, "mtp_gemm_bf16: null pointer");
+  MTP_REQUIRE(h.M > 0 && h.N > 0 && h.K > 0, "mtp_gemm_bf16: empty problem M=%d N=%d K=%d", h.M, h.N, h.K);
+  MTP_REQUIRE(h.N % 8 == 0, "mtp_gemm_bf16: N=%d must be a multiple of 8", h.N);
+  MTP_REQUIRE(h.lda % 8 == 0 && h.ldb % 8 == 0, "mtp_gemm_bf16: lda/ldb must be multiples of 8 (got %d, %d)", h.lda, h.ldb);
+  MTP_REQUIRE(((uintptr_t)h.A & 15) == 0 && ((uintptr_t)h.B & 15) == 0 && ((uintptr_t)h.ep.out & 15) == 0,
+              "mtp_gemm_bf16: pointers must be 16-byte aligned");
+  const EpiParams& ep = h.ep;
+  MTP_REQUIRE(ep.mode >= MTP_EPI_BF16 && ep.mode <= MTP_EPI_BF16_PIXSHUF, "mtp_gemm_bf16: bad epilogue mode %d", ep.mode);
+  MTP_REQUIRE(ep.ldo % 8 == 0 && ep.ldo > 0, "mtp_gemm_bf16: ldo=%d must be a positive multiple of 8", ep.ldo);
+  if (ep.mode == MTP_EPI_F32_RESID || ep.mode == MTP_EPI_F32_POS || ep.mode == MTP_EPI_BF16_DGELU)
+    MTP_REQUIRE(ep.aux != nullptr, "mtp_gemm_bf16: epilogue mode %d needs aux", ep.mode);
+  if (ep.mode == MTP_EPI_F32_RESID && ep.row_scale) MTP_REQUIRE(ep.rows_per_group > 0, "mtp_gemm_bf16: rows_per_group");
+  if (ep.mode == MTP_EPI_F32_POS) MTP_REQUIRE(ep.pos_rows > 0, "mtp_gemm_bf16: pos_rows");
+  if (ep.mode == MTP_EPI_BF16_PIXSHUF)
+    MTP_REQUIRE(ep.ps_h > 0 && ep.ps_w > 0 && ep.ps_cout > 0 && ep.ps_cout % 32 == 0 && h.N == 4 * ep.ps_cout,
+                "mtp_gemm_bf16: bad pixel-shuffle geometry");
+  return MTP_OK;
+}
+
+static EpiParams to_epi(const mtp_epilogue* ep) {
+  EpiParams p;
+  p.mode = ep->mode; p.ldo = ep->ldo; p.bias = ep->bias; p.out = ep->out; p.out2 = ep->out2; p.aux = ep->aux;
+  p.row_scale = ep->row_scale; p.rows_per_group = ep->rows_per_group; p.pos_rows = ep->pos_rows;
+  p.accumulate = ep->accumulate; p.ps_h = ep->ps_h; p.ps_w = ep->ps_w; p.ps_cout = ep->ps_cout;
+  return p;
+}
+
+static int run_grouped(const HostProblem* pr, int np, int force_bn, cudaStream_t stream) {
+  for (int p = 0; p < np; ++p) {
+    int rc = validate_problem(pr[p]);
+    if (rc) return rc;
   }
+  if (force_bn >= 1000) {
+    for (int p = 0; p < np; ++p)
+      MTP_REQUIRE(!pr[p].b_mn || (force_bn % 1000) % 128 == 0, "mtp_gemm_bf16: paired CTAs with MN-major B need a tile width of 128 or 256");
+  }
+  const Config* cfg = get_config(pr, np, force_bn);
+  if (cfg == nullptr) return set_error(MTP_ERR_INVALID, "mtp_gemm_bf16: no valid tile configuration (force_bn=%d)", force_bn);
+#define MTP_LAUNCH(BN_)                                                             \
+  case BN_:                                                                         \
+    return cfg->cl2 ? launch_grouped<BN_, true>(pr, np, cfg->sched, stream) : launch_grouped<BN_, false>(pr, np, cfg->sched, stream);
+  switch (cfg->bn) {
+    MTP_LAUNCH(64)
+    MTP_LAUNCH(128)
+    MTP_LAUNCH(192)
+    MTP_LAUNCH(256)
+    default: break;
+  }
+#undef MTP_LAUNCH
+  return set_error(MTP_ERR_INVALID, "mtp_gemm_bf16: unsupported tile width %d", cfg->bn);
 }
 
 }  // namespace mtp
 
 using namespace mtp;
 
-#define DISPATCH_LAYOUT(BN_, CL_)                                                                                   \
-  do {                                                                                                              \
-    if (!a_mn_major && !b_mn_major) return launch_gemm<BN_, false, false, CL_>(A, lda, B, ldb, M, N, K, p, stream); \
-    if (!a_mn_major && b_mn_major) return launch_gemm<BN_, false, true, CL_>(A, lda, B, ldb, M, N, K, p, stream);   \
-    if (a_mn_major && b_mn_major) return launch_gemm<BN_, true, true, CL_>(A, lda, B, ldb, M, N, K, p, stream);     \
-    return launch_gemm<BN_, true, false, CL_>(A, lda, B, ldb, M, N, K, p, stream);                                  \
-  } while (0)
-
 extern "C" int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N,
                              int K, const mtp_epilogue* ep, int force_bn, mtp_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  MTP_REQUIRE(A && B && ep && ep->out, "mtp_gemm_bf16: null pointer");
-  MTP_REQUIRE(M > 0 && N > 0 && K > 0, "mtp_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
-  MTP_REQUIRE(N % 8 == 0, "mtp_gemm_bf16: N=%d must be a multiple of 8", N);
-  MTP_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "mtp_gemm_bf16: lda/ldb must be multiples of 8 (got %d, %d)", lda, ldb);
-  MTP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)ep->out & 15) == 0,
-              "mtp_gemm_bf16: pointers must be 16-byte aligned");
-  MTP_REQUIRE(ep->mode >= MTP_EPI_BF16 && ep->mode <= MTP_EPI_BF16_PIXSHUF, "mtp_gemm_bf16: bad epilogue mode %d", ep->mode);
-  MTP_REQUIRE(ep->ldo % 8 == 0 && ep->ldo > 0, "mtp_gemm_bf16: ldo=%d must be a positive multiple of 8", ep->ldo);
-  if (ep->mode == MTP_EPI_F32_RESID || ep->mode == MTP_EPI_F32_POS || ep->mode == MTP_EPI_BF16_DGELU)
-    MTP_REQUIRE(ep->aux != nullptr, "mtp_gemm_bf16: epilogue mode %d needs aux", ep->mode);
-  if (ep->mode == MTP_EPI_F32_RESID && ep->row_scale) MTP_REQUIRE(ep->rows_per_group > 0, "mtp_gemm_bf16: rows_per_group");
-  if (ep->mode == MTP_EPI_F32_POS) MTP_REQUIRE(ep->pos_rows > 0, "mtp_gemm_bf16: pos_rows");
-  if (ep->mode == MTP_EPI_BF16_PIXSHUF)
-    MTP_REQUIRE(ep->ps_h > 0 && ep->ps_w > 0 && ep->ps_cout > 0 && ep->ps_cout % 32 == 0 && N == 4 * ep->ps_cout,
-                "mtp_gemm_bf16: bad pixel-shuffle geometry");
-  EpiParams p;
-  p.mode = ep->mode; p.ldo = ep->ldo; p.bias = ep->bias; p.out = ep->out; p.out2 = ep->out2; p.aux = ep->aux;
-  p.row_scale = ep->row_scale; p.rows_per_group = ep->rows_per_group; p.pos_rows = ep->pos_rows;
-  p.accumulate = ep->accumulate; p.ps_h = ep->ps_h; p.ps_w = ep->ps_w; p.ps_cout = ep->ps_cout;
-  // force_bn: 0 = heuristic; otherwise tile width, +1000 to force the 2-CTA multicast cluster variant (tests / tuning)
-  int bn;
-  bool cl2;
-  if (force_bn == 0) {
-    pick_config(M, N, b_mn_major != 0, bn, cl2);
-  } else {
-    cl2 = force_bn >= 1000;
-    bn = force_bn % 1000;
-    MTP_REQUIRE(!cl2 || !b_mn_major || bn % 128 == 0, "mtp_gemm_bf16: clustered MN-major B needs a tile width of 128 or 256");
-  }
-  if (cl2) {
-    switch (bn) {
-      case 64: DISPATCH_LAYOUT(64, true);
-      case 128: DISPATCH_LAYOUT(128, true);
-      case 192: DISPATCH_LAYOUT(192, true);
-      case 256: DISPATCH_LAYOUT(256, true);
-      default: break;
-    }
-  } else {
-    switch (bn) {
-      case 64: DISPATCH_LAYOUT(64, false);
-      case 128: DISPATCH_LAYOUT(128, false);
-      case 192: DISPATCH_LAYOUT(192, false);
-      case 256: DISPATCH_LAYOUT(256, false);
-      default: break;
-    }
-  }
-  return set_error(MTP_ERR_INVALID, "mtp_gemm_bf16: unsupported tile width %d", bn);
+  MTP_REQUIRE(ep != nullptr, "mtp_gemm_bf16: null epilogue");
+  HostProblem h = {A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, to_epi(ep)};
+  return run_grouped(&h, 1, force_bn, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mtp_gemm_bf16_dual(const mtp_gemm_desc* g0, const mtp_gemm_desc* g1, int force_bn, mtp_stream_t stream_) {
+  MTP_REQUIRE(g0 && g1 && g0->ep && g1->ep, "mtp_gemm_bf16_dual: null descriptor");
+  HostProblem h[2] = {{g0->A, g0->lda, g0->a_mn_major, g0->B, g0->ldb, g0->b_mn_major, g0->M, g0->N, g0->K, to_epi(g0->ep)},
+                      {g1->A, g1->lda, g1->a_mn_major, g1->B, g1->ldb, g1->b_mn_major, g1->M, g1->N, g1->K, to_epi(g1->ep)}};
+  return run_grouped(h, 2, force_bn, reinterpret_cast<cudaStream_t>(stream_));
 }

@@ -40,14 +40,13 @@ class GradStore:
         return self.views[name]
 
 
-def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_BF16, aux=None, want_dx=True):
+def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_BF16, aux=None):
     """y = x W^T + b with x [T, n_in], W [n_out, n_in], cotangent g [T, n_out].
-    dW = g^T x (both operands MN-major, K = T); dx = g W (B operand MN-major)."""
-    ops.gemm(g_bf16, x_bf16, n_out, n_in, T, dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=n_out, ldb=n_in, ldo=n_in)
-    if not want_dx:
-        return None
+    dW = g^T x (both operands MN-major, K = T) and dx = g W (B operand MN-major) only share the input g: they run as ONE
+    grouped launch whose tiles are spread over the SMs by a common schedule."""
     dx = torch.empty(T, n_in, device=g_bf16.device, dtype=BF16)
-    ops.gemm(g_bf16, w_bf16, T, n_in, n_out, dx, b_mn=True, mode=dgrad_mode, aux=aux, lda=n_out, ldb=n_in)
+    ops.gemm_dual(dict(A=g_bf16, B=w_bf16, M=T, N=n_in, K=n_out, out=dx, b_mn=True, mode=dgrad_mode, aux=aux, lda=n_out, ldb=n_in),
+                  dict(A=g_bf16, B=x_bf16, M=n_out, N=n_in, K=T, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=n_out, ldb=n_in, ldo=n_in))
     return dx
 
 

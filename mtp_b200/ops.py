@@ -1,4 +1,6 @@
 """Thin torch-tensor wrappers over the C ABI (pointers + sizes + the current CUDA stream).  No autograd here."""
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -33,6 +35,28 @@ def gemm(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=No
     L.call("mtp_gemm_bf16", A.data_ptr(), lda, int(a_mn), B.data_ptr(), ldb, int(b_mn), int(M), int(N), int(K),
            ep, int(force_bn), _stream())
     return out
+
+
+def _desc(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=None, out2=None, aux=None, row_scale=None,
+          rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None):
+    ep = L.Epilogue()
+    ep.mode = mode
+    ep.ldo = int(ldo if ldo is not None else out.shape[-1])
+    ep.bias, ep.out, ep.out2, ep.aux, ep.row_scale = _p(bias), _p(out), _p(out2), _p(aux), _p(row_scale)
+    ep.rows_per_group, ep.pos_rows, ep.accumulate = int(rows_per_group), int(pos_rows), int(bool(accumulate))
+    d = L.GemmDesc()
+    d.A, d.lda, d.a_mn_major = A.data_ptr(), int(lda if lda is not None else A.shape[-1]), int(a_mn)
+    d.B, d.ldb, d.b_mn_major = B.data_ptr(), int(ldb if ldb is not None else B.shape[-1]), int(b_mn)
+    d.M, d.N, d.K = int(M), int(N), int(K)
+    d.ep = ctypes.pointer(ep)
+    d._keep = ep
+    return d
+
+
+def gemm_dual(g0, g1, force_bn=0):
+    """Two independent GEMMs (dicts of gemm() arguments) in one grouped persistent launch."""
+    d0, d1 = _desc(**g0), _desc(**g1)
+    L.call("mtp_gemm_bf16_dual", ctypes.byref(d0), ctypes.byref(d1), int(force_bn), _stream())
 
 
 def layernorm_fwd(x, gamma, beta, eps=1e-6, gelu=False, save_stats=True):

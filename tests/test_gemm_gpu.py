@@ -139,3 +139,22 @@ def test_gemm_rejects_bad_args():
     out = torch.empty(16, 16, device="cuda")
     with pytest.raises(L.MtpError):
         ops.gemm(A, B, 16, 16, 20, out, mode=L.EPI_F32)       # lda not a multiple of 8
+
+
+def test_grouped_dual_launch_matches_separate():
+    """dgrad + wgrad of one Linear in a single grouped launch (host LPT schedule over both problems)."""
+    from mtp_b200 import ops, _lib as L
+    T, Cin, Cout = 1568, 1024, 256
+    x, W = _mk((T, Cin), seed=31), _mk((Cout, Cin), 0.1, seed=32)
+    dy = _mk((T, Cout), seed=33)
+    dx = torch.empty(T, Cin, device="cuda", dtype=torch.bfloat16)
+    dW = torch.empty(Cout, Cin, device="cuda")
+    for force in (0, 128, 1128, 256):
+        dx.zero_(); dW.zero_()
+        ops.gemm_dual(dict(A=dy, B=W, M=T, N=Cin, K=Cout, out=dx, b_mn=True, lda=Cout, ldb=Cin),
+                      dict(A=dy, B=x, M=Cout, N=Cin, K=T, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=Cout, ldb=Cin), force_bn=force)
+        torch.cuda.synchronize()
+        ref_dx = dy.float() @ W.float()
+        ref_dW = dy.float().t() @ x.float()
+        assert ((dx.float() - ref_dx).abs() <= 8e-3 * ref_dx.abs() + 1e-2).all(), force
+        assert (dW - ref_dW).norm().item() / ref_dW.norm().item() < 1e-5, force
