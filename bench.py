@@ -199,12 +199,23 @@ def gemm_profile(trainer, x):
         e1.record()
         recs.append((e0, e1, 2.0 * M * N * K))
         return r
+    orig_dual = ops.gemm_dual
+
+    def timed_dual(g0, g1, force_bn=0):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_dual(g0, g1, force_bn)
+        e1.record()
+        recs.append((e0, e1, 2.0 * (g0["M"] * g0["N"] * g0["K"] + g1["M"] * g1["N"] * g1["K"])))
+        return r
     ops.gemm = timed
+    ops.gemm_dual = timed_dual
     try:
         trainer._step_body(x)
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
+        ops.gemm_dual = orig_dual
     ms = sum(a.elapsed_time(b) for a, b, _ in recs)
     flops = sum(f for _, _, f in recs)
     return len(recs), ms, flops
