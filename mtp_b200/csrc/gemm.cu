@@ -203,7 +203,15 @@ struct GemmProblem {
 struct Sched {
   uint16_t count[MAX_SLOTS];
   uint16_t item[MAX_SLOTS][MAX_ITEMS];
+  long long* dbg;      // optional: [gridDim.x][8] globaltimer stamps of the pipeline phases (tuning aid, mtp_gemm_set_debug)
 };
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define MTP_STAMP(i) do { if (sched.dbg) sched.dbg[blockIdx.x * 8 + (i)] = gtime(); } while (0)
 
 template <int BN, bool CL2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -221,6 +229,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) MTP_STAMP(0);
   const int crank = CL2 ? (int)cluster_ctarank() : 0;
   const int slot = CL2 ? blockIdx.x / 2 : blockIdx.x;
   const int n_items = sched.count[slot];
@@ -253,6 +262,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   if (CL2) cluster_sync_all();       // peer barriers are initialised before any remote signal can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) MTP_STAMP(1);
 
 #define MTP_DECODE_ITEM(IT)                                                                      \
   const int item_ = sched.item[slot][IT];                                                        \
@@ -328,6 +338,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (it == 0 && kb == 0) MTP_STAMP(2);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -344,6 +355,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         }
         if (CL2) umma_commit_2sm_mcast(&tmem_full[acc], 0x3);       // accumulators complete in both CTAs' TMEM
         else umma_commit(&tmem_full[acc]);
+        if (it == 0) MTP_STAMP(3);
+        if (it == n_items - 1) MTP_STAMP(4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -368,6 +381,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      // bias visible; also keeps the 8 warps on the same item
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (it == n_items - 1 && threadIdx.x == 64) MTP_STAMP(5);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < M;
@@ -400,6 +414,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) MTP_STAMP(6);
   if (CL2) cluster_sync_all();       // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
@@ -517,8 +532,12 @@ static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
   return &cache.emplace(key, best).first->second;
 }
 
+static long long* g_gemm_dbg = nullptr;
+
 template <int BN, bool CL2>
-static int launch_grouped(const HostProblem* pr, int np, const Sched& sched, cudaStream_t stream) {
+static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, cudaStream_t stream) {
+  Sched sched = sched_in;
+  sched.dbg = g_gemm_dbg;
   using Cfg = GemmCfg<BN, CL2>;
   GemmProblem gp[2];
   memset(gp, 0, sizeof(gp));
@@ -626,6 +645,13 @@ extern "C" int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
   MTP_REQUIRE(ep != nullptr, "mtp_gemm_bf16: null epilogue");
   HostProblem h = {A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, to_epi(ep)};
   return run_grouped(&h, 1, force_bn, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+/* tuning aid: when set, every GEMM launch writes per-CTA globaltimer stamps [grid][8]: 0 start, 1 prologue done, 2 first operands
+ * landed, 3 first item's MMAs issued, 4 last item's MMAs issued, 5 last accumulator complete (epilogue starts), 6 CTA done */
+extern "C" int mtp_gemm_set_debug(void* device_buffer) {
+  g_gemm_dbg = reinterpret_cast<long long*>(device_buffer);
+  return MTP_OK;
 }
 
 extern "C" int mtp_gemm_bf16_dual(const mtp_gemm_desc* g0, const mtp_gemm_desc* g1, int force_bn, mtp_stream_t stream_) {
