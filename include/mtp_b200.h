@@ -87,6 +87,8 @@ typedef struct mtp_gemm_desc {
 int mtp_gemm_bf16_dual(const mtp_gemm_desc* g0, const mtp_gemm_desc* g1, int force_bn, mtp_stream_t stream);
 /* Tuning aid: device buffer [grid][8] of int64 that receives per-CTA globaltimer stamps of the pipeline phases (NULL = off). */
 int mtp_gemm_set_debug(void* device_buffer);
+/* Tuning aid: 0 normal; 1 = skip the TMA loads (isolates the MMA pipeline; results are garbage); 2 = skip the MMAs. */
+int mtp_gemm_set_debug_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound; one warp per token row; fp32 statistics).

@@ -103,10 +103,13 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     ft_load_rows(Qs, base, C3, q0, 128, N);
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
       tc_fence_after();
-      tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, N16, 64, false);
-      umma_commit(mbar);
+      if (elect_one()) {
+        tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, N16, 64, false);
+        umma_commit(mbar);
+      }
+      __syncwarp();
     }
     const int q = q0 + tid;
     const bool qvalid = q < N;
@@ -174,10 +177,13 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
       tc_fence_after();
-      tc_mma_tiles<false, true>(T_O, smem_u32(Pt), FT_TILE, smem_u32(Vs), 0, 128, 64, N16, false);
-      umma_commit(mbar);
+      if (elect_one()) {
+        tc_mma_tiles<false, true>(T_O, smem_u32(Pt), FT_TILE, smem_u32(Vs), 0, 128, 64, N16, false);
+        umma_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(mbar, phase);
     phase ^= 1;
@@ -323,11 +329,14 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     for (int h = 0; h < n_halves; ++h) {
       const int k0 = h * 128;
       const int nk16 = min(128, N16 - k0);                 // keys of this half, multiple of 16
-      if (tid == 0) {
+      if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
         tc_fence_after();
-        tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks) + h * FT_TILE, 0, 128, nk16, 64, false);
-        tc_mma_tiles<false, false>(T_DP, smem_u32(Gs), 0, smem_u32(Vs) + h * FT_TILE, 0, 128, nk16, 64, false);
-        umma_commit(mbar);
+        if (elect_one()) {
+          tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks) + h * FT_TILE, 0, 128, nk16, 64, false);
+          tc_mma_tiles<false, false>(T_DP, smem_u32(Gs), 0, smem_u32(Vs) + h * FT_TILE, 0, 128, nk16, 64, false);
+          umma_commit(mbar);
+        }
+        __syncwarp();
       }
       mbar_wait(mbar, phase);
       phase ^= 1;
@@ -379,13 +388,16 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       tc_fence_before();
       fence_proxy_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
         tc_fence_after();
-        // dQ_half = dS K_h (temp in T_S) ; dK_h += dS^T Q ; dV_h += P^T dO     (M = 128 keys/queries, N = 64, K = 128)
-        tc_mma_tiles<false, true>(T_S, smem_u32(St), FT_TILE, smem_u32(Ks) + h * FT_TILE, 0, 128, 64, 128, false);
-        tc_mma_tiles<true, true>(T_DK + 64 * h, smem_u32(St), FT_TILE, smem_u32(Qs), 0, 128, 64, 128, qt > 0);
-        tc_mma_tiles<true, true>(T_DV + 64 * h, smem_u32(Pt), FT_TILE, smem_u32(Gs), 0, 128, 64, 128, qt > 0);
-        umma_commit(mbar);
+        if (elect_one()) {
+          // dQ_half = dS K_h (temp in T_S) ; dK_h += dS^T Q ; dV_h += P^T dO     (M = 128 keys/queries, N = 64, K = 128)
+          tc_mma_tiles<false, true>(T_S, smem_u32(St), FT_TILE, smem_u32(Ks) + h * FT_TILE, 0, 128, 64, 128, false);
+          tc_mma_tiles<true, true>(T_DK + 64 * h, smem_u32(St), FT_TILE, smem_u32(Qs), 0, 128, 64, 128, qt > 0);
+          tc_mma_tiles<true, true>(T_DV + 64 * h, smem_u32(Pt), FT_TILE, smem_u32(Gs), 0, 128, 64, 128, qt > 0);
+          umma_commit(mbar);
+        }
+        __syncwarp();
       }
       mbar_wait(mbar, phase);
       phase ^= 1;
@@ -452,10 +464,13 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       tc_fence_before();
       fence_proxy_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
         tc_fence_after();
-        tc_mma_tiles<true, true>(T_S + 64, smem_u32(Pt), FT_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
-        umma_commit(mbar);
+        if (elect_one()) {
+          tc_mma_tiles<true, true>(T_S + 64, smem_u32(Pt), FT_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
+          umma_commit(mbar);
+        }
+        __syncwarp();
       }
       mbar_wait(mbar, phase);
       phase ^= 1;

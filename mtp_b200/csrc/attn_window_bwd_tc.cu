@@ -136,11 +136,14 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   __syncthreads();
 
   // ---- S = Q K~^T, dP = dO V~^T
-  if (tid == 0) {
+  if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
     tc_fence_after();
-    tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, 128, 64, false);
-    tc_mma_tiles<false, false>(T_DP, smem_u32(Gs), 0, smem_u32(Vs), 0, 128, 128, 64, false);
-    umma_commit(mbar);
+    if (elect_one()) {
+      tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, 128, 64, false);
+      tc_mma_tiles<false, false>(T_DP, smem_u32(Gs), 0, smem_u32(Vs), 0, 128, 128, 64, false);
+      umma_commit(mbar);
+    }
+    __syncwarp();
   }
   const int p = tid >> 6, q = tid & 63;
   const bool qvalid = q < NTOK;
@@ -251,13 +254,16 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   __syncthreads();
 
   // ---- dQ = dS K~ ; dK~ = dS^T Q ; dV~ = P^T dO
-  if (tid == 0) {
+  if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
     tc_fence_after();
-    tc_mma_tiles<false, true>(T_DQ, smem_u32(St), WB_TILE, smem_u32(Ks), 0, 128, 64, 128, false);
-    tc_mma_tiles<true, true>(T_DK, smem_u32(St), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
-    tc_mma_tiles<true, true>(T_DV, smem_u32(Pt), WB_TILE, smem_u32(Gs), 0, 128, 64, 128, false);
-    tc_mma_tiles<true, true>(T_DR, smem_u32(Wt), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);     // d rel tables = W^T Q (both heads)
-    umma_commit(mbar);
+    if (elect_one()) {
+      tc_mma_tiles<false, true>(T_DQ, smem_u32(St), WB_TILE, smem_u32(Ks), 0, 128, 64, 128, false);
+      tc_mma_tiles<true, true>(T_DK, smem_u32(St), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
+      tc_mma_tiles<true, true>(T_DV, smem_u32(Pt), WB_TILE, smem_u32(Gs), 0, 128, 64, 128, false);
+      tc_mma_tiles<true, true>(T_DR, smem_u32(Wt), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);     // d rel tables = W^T Q (both heads)
+      umma_commit(mbar);
+    }
+    __syncwarp();
   }
   // meanwhile: bias-table partials, one output per (head, displacement): sum of dS over the pairs with that displacement
   for (int i = tid; i < 2 * 169; i += WB_THREADS) {

@@ -114,10 +114,13 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   __syncthreads();
 
   // ---- S = Q K~^T  (M = 128, N = 128, K = 64) -> TMEM columns [0, 128)
-  if (tid == 0) {
+  if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
     tc_fence_after();
-    tc_mma_tiles<false, false>(tmem, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, 128, 64, false);
-    umma_commit(mbar);
+    if (elect_one()) {
+      tc_mma_tiles<false, false>(tmem, smem_u32(Qs), 0, smem_u32(Ks), 0, 128, 128, 64, false);
+      umma_commit(mbar);
+    }
+    __syncwarp();
   }
   // meanwhile: decomposed rel-pos terms of this thread's row (fp32, UNscaled q)
   const int p = tid >> 6, q = tid & 63;
@@ -187,10 +190,13 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   __syncthreads();
 
   // ---- O = P V~  (M = 128, N = 64, K = 128; V~ read MN-major: rows = key index) -> TMEM columns [128, 192)
-  if (tid == 0) {
+  if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
     tc_fence_after();
-    tc_mma_tiles<false, true>(tmem + 128, smem_u32(Ps), WTC_TILE, smem_u32(Vs), 0, 128, 64, 128, false);
-    umma_commit(mbar);
+    if (elect_one()) {
+      tc_mma_tiles<false, true>(tmem + 128, smem_u32(Ps), WTC_TILE, smem_u32(Vs), 0, 128, 64, 128, false);
+      umma_commit(mbar);
+    }
+    __syncwarp();
   }
   mbar_wait(mbar, 1);
   tc_fence_after();

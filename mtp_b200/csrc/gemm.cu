@@ -203,6 +203,7 @@ struct GemmProblem {
 struct Sched {
   uint16_t count[MAX_SLOTS];
   uint16_t item[MAX_SLOTS][MAX_ITEMS];
+  int dbg_mode;        // tuning aid: 0 normal, 1 = skip the TMA loads (MMA pipeline only), 2 = skip the MMAs (TMA pipeline only)
   long long* dbg;      // optional: [gridDim.x][8] globaltimer stamps of the pipeline phases (tuning aid, mtp_gemm_set_debug)
 };
 
@@ -275,7 +276,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow keeps descriptors / coordinates in uniform registers);
+    // one elected lane issues.  Issuing from inside a divergent `if (lane == 0)` makes the compiler wrap every UTMALDG /
+    // UTCHMMA in an ELECT + R2UR.BROADCAST waterfall loop (measured: ~175 cycles per MMA instead of its N/2).
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_items; ++it) {
@@ -284,43 +288,48 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          if (!CL2) {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            if (!P.a_mn) {
-              tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
-            } else {
+          if (elect_one()) {
+            if (sched.dbg_mode == 1) {
+              if (!CL2 || crank == 0) mbar_arrive(&full_bar[stage]);
+            } else if (!CL2) {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              if (!P.a_mn) {
+                tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
-            }
-            if (!P.b_mn) {
-              tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * BK, n0);
-            } else {
+                for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+              }
+              if (!P.b_mn) {
+                tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * BK, n0);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[stage], n0 + j * 64, kb * BK);
-            }
-          } else {
-            // both CTAs' bytes are credited to the LEADER's full barrier (only the leader waits on it and issues the MMAs)
-            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            if (!P.a_mn) {
-              tma_load_2d_2sm(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
+                for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+              }
             } else {
+              // both CTAs' bytes are credited to the LEADER's full barrier (only the leader waits on it and issues the MMAs)
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              if (!P.a_mn) {
+                tma_load_2d_2sm(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
-            }
-            if (!P.b_mn) {       // my half of the pair's B tile: columns [n0 + crank*BN/2, +BN/2)
-              tma_load_2d_2sm(sb, &P.tmB, &full_bar[stage], kb * BK, n0 + crank * (BN / 2));
-            } else {
+                for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+              }
+              if (!P.b_mn) {       // my half of the pair's B tile: columns [n0 + crank*BN/2, +BN/2)
+                tma_load_2d_2sm(sb, &P.tmB, &full_bar[stage], kb * BK, n0 + crank * (BN / 2));
+              } else {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &P.tmB, &full_bar[stage], n0 + crank * (BN / 2) + j * 64, kb * BK);
+                for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &P.tmB, &full_bar[stage], n0 + crank * (BN / 2) + j * 64, kb * BK);
+              }
             }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && (!CL2 || crank == 0)) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
+    if (!CL2 || crank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -338,25 +347,37 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (it == 0 && kb == 0) MTP_STAMP(2);
+          if (it == 0 && kb == 0 && lane == 0) MTP_STAMP(2);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint64_t a_desc0 = make_smem_desc(sa, a_lbo, 1024);
           const uint64_t b_desc0 = make_smem_desc(sb, b_lbo, 1024);
+          if (elect_one()) {
+            if (sched.dbg_mode == 2 && !CL2) {
+              mbar_arrive(&empty_bar[stage]);
+            } else {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if (CL2) umma_bf16_2sm(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
-            else umma_bf16(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
+              for (int k = 0; k < BK / 16; ++k) {
+                if (CL2) umma_bf16_2sm(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
+                else umma_bf16(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
+              }
+              if (CL2) umma_commit_2sm_mcast(&empty_bar[stage], 0x3);   // releases the stage in BOTH CTAs
+              else umma_commit(&empty_bar[stage]);                      // smem slot reusable once these MMAs retire
+            }
           }
-          if (CL2) umma_commit_2sm_mcast(&empty_bar[stage], 0x3);   // releases the stage in BOTH CTAs
-          else umma_commit(&empty_bar[stage]);                      // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CL2) umma_commit_2sm_mcast(&tmem_full[acc], 0x3);       // accumulators complete in both CTAs' TMEM
-        else umma_commit(&tmem_full[acc]);
-        if (it == 0) MTP_STAMP(3);
-        if (it == n_items - 1) MTP_STAMP(4);
+        if (elect_one()) {
+          if (CL2) umma_commit_2sm_mcast(&tmem_full[acc], 0x3);       // accumulators complete in both CTAs' TMEM
+          else umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (it == 0) MTP_STAMP(3);
+          if (it == n_items - 1) MTP_STAMP(4);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -533,11 +554,13 @@ static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
 }
 
 static long long* g_gemm_dbg = nullptr;
+static int g_gemm_dbg_mode = 0;
 
 template <int BN, bool CL2>
 static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, cudaStream_t stream) {
   Sched sched = sched_in;
   sched.dbg = g_gemm_dbg;
+  sched.dbg_mode = g_gemm_dbg_mode;
   using Cfg = GemmCfg<BN, CL2>;
   GemmProblem gp[2];
   memset(gp, 0, sizeof(gp));
@@ -651,6 +674,10 @@ extern "C" int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void*
  * landed, 3 first item's MMAs issued, 4 last item's MMAs issued, 5 last accumulator complete (epilogue starts), 6 CTA done */
 extern "C" int mtp_gemm_set_debug(void* device_buffer) {
   g_gemm_dbg = reinterpret_cast<long long*>(device_buffer);
+  return MTP_OK;
+}
+extern "C" int mtp_gemm_set_debug_mode(int mode) {
+  g_gemm_dbg_mode = mode;
   return MTP_OK;
 }
 
