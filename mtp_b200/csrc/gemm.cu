@@ -483,9 +483,11 @@ struct HostProblem {
   EpiParams ep;
 };
 
-// cycles of one 64-deep k-block of a BN-wide tile: the MMAs (2*BN) or operand ingress at the measured ~59 B/clk/SM
-static double kblock_cycles(int bn, bool cl2) { return std::max(2.0 * bn, (16384.0 + (cl2 ? 64.0 : 128.0) * bn) / 59.0); }
-static const double kTileFixedCycles = 1800.0;      // epilogue / pipeline fill per tile
+// Cycles of one 64-deep k-block of a BN-wide tile (measured with the in-kernel phase stamps, tools/gemm_phases.py): the MMAs
+// take 2*BN cycles; the TMA unit of an SM delivers one 128-byte row of a box per ~1.8 cycles, and a cta_group::2 pair halves
+// the B rows each SM stages.
+static double kblock_cycles(int bn, bool cl2) { return std::max(2.0 * bn, 1.8 * (128.0 + (cl2 ? bn / 2 : bn))); }
+static const double kTileFixedCycles = 2500.0;      // epilogue / pipeline fill per tile
 
 // Longest-processing-time schedule of the work items of up to two problems over the slots; returns the makespan (cycles).
 static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sched* out) {
