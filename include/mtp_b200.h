@@ -35,6 +35,9 @@ const char* mtp_last_error(void);
 int mtp_version(void);
 /* SM count of the current device (cached). */
 int mtp_num_sms(void);
+/* Programmatic dependent launch for every kernel of the library (default on): each kernel may be scheduled while its stream
+ * predecessor drains and holds at griddepcontrol.wait until the predecessor's results are visible.  Off = plain stream order. */
+int mtp_set_pdl(int enabled);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GEMM on tcgen05 tensor cores:  acc[m,n] = sum_k A[m,k] * B[n,k]   (bf16 in, fp32 accumulate in TMEM)

@@ -34,6 +34,7 @@ EPI_BF16, EPI_BF16_GELU, EPI_F32_RESID, EPI_F32_POS, EPI_F32, EPI_BF16_DGELU, EP
 _SIGNATURES = {
     "mtp_gemm_bf16": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_int, c_void_p],
     "mtp_gemm_bf16_dual": [ctypes.POINTER(GemmDesc), ctypes.POINTER(GemmDesc), c_int, c_void_p],
+    "mtp_set_pdl": [c_int],
     "mtp_gemm_set_debug": [c_void_p],
     "mtp_gemm_set_debug_mode": [c_int],
     "mtp_layernorm_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],

@@ -14,6 +14,10 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl(bool on) { g_pdl = on; }
+
 int num_sms() {
   static int cached = 0;
   if (cached == 0) {
@@ -31,4 +35,8 @@ int num_sms() {
 
 extern "C" const char* mtp_last_error(void) { return mtp::g_err; }
 extern "C" int mtp_version(void) { return 100; }
+extern "C" int mtp_set_pdl(int enabled) {
+  mtp::set_pdl(enabled != 0);
+  return MTP_OK;
+}
 extern "C" int mtp_num_sms(void) { return mtp::num_sms(); }

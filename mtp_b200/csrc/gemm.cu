@@ -49,7 +49,14 @@ struct EpiParams {
   int rows_per_group, pos_rows, accumulate, ps_h, ps_w, ps_cout;
 };
 
-// ---- epilogue for one thread: 32 consecutive columns [n, n+32) of row m -------------------------------------------
+// ---- epilogue ---------------------------------------------------------------------------------------------------------
+// tcgen05.ld (32x32b) hands every lane 32 consecutive columns of ONE accumulator row, so storing straight from that layout makes
+// each warp-wide store touch 32 different rows with 16 bytes apiece: partial-sector requests that throttle L2 (measured: the
+// 9.6 MB output of the qkv GEMM cost 5.3 us of a 19 us launch).  Each group of four lanes therefore first transposes its 4 rows x
+// 4 column blocks through warp shuffles: afterwards a lane owns four PIECES, piece p = 8 columns of row (lane & ~3) | ((lane & 3)
+// ^ {0,2,1,3}[p]), and the four lanes of a group cover 64 contiguous bytes of a row per 16-byte access (bf16 outputs: columns
+// i*8 + k; fp32 outputs: two runs i*4 + {0,16} + k so that every access still fills whole 32-byte sectors).  All epilogue
+// arithmetic, the aux loads and the stores run in that layout.
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]);
@@ -59,125 +66,140 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// aux operand of one 32-column chunk, fetched BEFORE waiting on the TMEM load so the two latencies overlap
+__device__ __forceinline__ bool mode_is_f32(int mode) { return mode == MTP_EPI_F32_RESID || mode == MTP_EPI_F32_POS || mode == MTP_EPI_F32; }
+
+// column (within the 32-column chunk) of element k of this lane's pieces
+template <bool F32>
+__device__ __forceinline__ int piece_col(int lane, int k) {
+  const int i = lane & 3;
+  return F32 ? ((k >> 2) * 16 + i * 4 + (k & 3)) : (i * 8 + k);
+}
+// row (within the warp's 32 rows) of piece p
+__device__ __forceinline__ int piece_row(int lane, int p) {
+  const int perm = (p == 0) ? 0 : (p == 1) ? 2 : (p == 2) ? 1 : 3;
+  return (lane & ~3) | ((lane & 3) ^ perm);
+}
+
+template <bool F32>
+__device__ __forceinline__ void lane_transpose(const float (&v)[32], float (&t)[4][8], int lane) {
+  const bool b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+#define MTP_BLK(c, k) v[F32 ? (((k) >> 2) * 16 + (c) * 4 + ((k) & 3)) : ((c) * 8 + (k))]
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float x0 = MTP_BLK(0, k), x1 = MTP_BLK(1, k), x2 = MTP_BLK(2, k), x3 = MTP_BLK(3, k);
+    // stage 1 (partner lane ^ 2): keep the block pair {2*b1, 2*b1+1} of my row, fetch the same pair of the partner's row
+    const float keep_lo = b1 ? x2 : x0, keep_hi = b1 ? x3 : x1;
+    const float recv_lo = __shfl_xor_sync(0xffffffffu, b1 ? x0 : x2, 2);
+    const float recv_hi = __shfl_xor_sync(0xffffffffu, b1 ? x1 : x3, 2);
+    // stage 2 (partner lane ^ 1): keep block (lane & 3) of both rows, fetch it from the partner's two rows
+    t[0][k] = b0 ? keep_hi : keep_lo;
+    t[1][k] = b0 ? recv_hi : recv_lo;
+    t[2][k] = __shfl_xor_sync(0xffffffffu, b0 ? keep_lo : keep_hi, 1);
+    t[3][k] = __shfl_xor_sync(0xffffffffu, b0 ? recv_lo : recv_hi, 1);
+  }
+#undef MTP_BLK
+}
+
+// aux operand of this lane's four pieces, fetched BEFORE waiting on the TMEM load so the two latencies overlap
 struct AuxRegs { float4 f[8]; };
 
-__device__ __forceinline__ void load_aux(const EpiParams& ep, AuxRegs& a, int m, int n, int N) {
-  if (ep.mode == MTP_EPI_F32_RESID) {
-    const float* r = reinterpret_cast<const float*>(ep.aux) + (size_t)m * ep.ldo + n;
+// m[p] = global row of piece p (callers pass ok[p] = row is in range); n = first column of the 32-column chunk
+__device__ __forceinline__ void load_aux(const EpiParams& ep, AuxRegs& a, const int (&m)[4], const bool (&ok)[4], int n, int N, int lane) {
+  const int i = lane & 3;
+  if (ep.mode == MTP_EPI_F32_RESID || ep.mode == MTP_EPI_F32_POS || (ep.mode == MTP_EPI_F32 && ep.accumulate)) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (n + 4 * j < N) a.f[j] = *reinterpret_cast<const float4*>(r + 4 * j);
-  } else if (ep.mode == MTP_EPI_F32_POS) {
-    const float* r = reinterpret_cast<const float*>(ep.aux) + (size_t)(m % ep.pos_rows) * N + n;
+    for (int p = 0; p < 4; ++p) {
+      if (!ok[p]) continue;
+      const float* r = ep.mode == MTP_EPI_F32_RESID ? reinterpret_cast<const float*>(ep.aux) + (size_t)m[p] * ep.ldo
+                       : ep.mode == MTP_EPI_F32_POS ? reinterpret_cast<const float*>(ep.aux) + (size_t)(m[p] % ep.pos_rows) * N
+                                                    : reinterpret_cast<const float*>(ep.out) + (size_t)m[p] * ep.ldo;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (n + 4 * j < N) a.f[j] = __ldg(reinterpret_cast<const float4*>(r + 4 * j));
+      for (int h = 0; h < 2; ++h) {
+        const int col = n + h * 16 + i * 4;
+        if (col < N) a.f[p * 2 + h] = *reinterpret_cast<const float4*>(r + col);
+      }
+    }
   } else if (ep.mode == MTP_EPI_BF16_DGELU) {
-    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)m * ep.ldo + n;
+    const int col = n + i * 8;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) if (n + 8 * j < N) a.f[j] = *reinterpret_cast<const float4*>(h + 8 * j);
-  } else if (ep.mode == MTP_EPI_F32 && ep.accumulate) {
-    const float* o = reinterpret_cast<const float*>(ep.out) + (size_t)m * ep.ldo + n;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) if (n + 4 * j < N) a.f[j] = *reinterpret_cast<const float4*>(o + 4 * j);
+    for (int p = 0; p < 4; ++p)
+      if (ok[p] && col < N)
+        a.f[p] = *reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)m[p] * ep.ldo + col);
   }
 }
 
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[32], const AuxRegs& a, const float* bias_s, int m, int n, int N) {
-  if (bias_s != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(bias_s + j);      // smem broadcast; columns >= N hold zeros
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+__device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[4][8], const AuxRegs& a, const float* bias_s,
+                                                const int (&m)[4], const bool (&ok)[4], int n, int N, int lane) {
+  const int i = lane & 3;
+  const bool f32 = mode_is_f32(ep.mode);
+  if (bias_s != nullptr) {             // smem; columns >= N hold zeros
+    float b[8];
+    if (f32) {
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(bias_s + i * 4);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(bias_s + 16 + i * 4);
+    } else {
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(bias_s + i * 8);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(bias_s + i * 8 + 4);
     }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[p][k] += b[k];
   }
-  switch (ep.mode) {
-    case MTP_EPI_BF16: {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)m * ep.ldo + n;
+  if (f32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        if (n + j < N) store_bf16x8(o + j, v + j);
-    } break;
-    case MTP_EPI_BF16_GELU: {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)m * ep.ldo + n;
-      if (ep.out2 != nullptr) {
-        __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(ep.out2) + (size_t)m * ep.ldo + n;
+    for (int p = 0; p < 4; ++p) {
+      if (!ok[p]) continue;
+      float* o = reinterpret_cast<float*>(ep.out) + (size_t)m[p] * ep.ldo;
+      const float s = (ep.mode == MTP_EPI_F32_RESID && ep.row_scale) ? __ldg(ep.row_scale + m[p] / ep.rows_per_group) : 1.0f;
+      const bool add = ep.mode != MTP_EPI_F32 || ep.accumulate;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          if (n + j < N) store_bf16x8(o2 + j, v + j);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        if (n + j < N) store_bf16x8(o + j, v + j);
-    } break;
-    case MTP_EPI_F32_RESID: {
-      const float s = ep.row_scale ? __ldg(ep.row_scale + m / ep.rows_per_group) : 1.0f;
-      float* o = reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldo + n;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (n + j < N) {
-          float4 x = a.f[j >> 2];
-          x.x += s * v[j]; x.y += s * v[j + 1]; x.z += s * v[j + 2]; x.w += s * v[j + 3];
-          *reinterpret_cast<float4*>(o + j) = x;
-        }
-      }
-    } break;
-    case MTP_EPI_F32_POS: {
-      float* o = reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldo + n;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (n + j < N) {
-          float4 x = a.f[j >> 2];
-          x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
-          *reinterpret_cast<float4*>(o + j) = x;
-        }
-      }
-    } break;
-    case MTP_EPI_F32: {
-      float* o = reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ldo + n;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (n + j < N) {
-          float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (ep.accumulate) {
-            const float4 y = a.f[j >> 2];
+      for (int h = 0; h < 2; ++h) {
+        const int col = n + h * 16 + i * 4;
+        if (col < N) {
+          float4 x = make_float4(s * t[p][h * 4], s * t[p][h * 4 + 1], s * t[p][h * 4 + 2], s * t[p][h * 4 + 3]);
+          if (add) {
+            const float4 y = a.f[p * 2 + h];
             x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
           }
-          *reinterpret_cast<float4*>(o + j) = x;
+          *reinterpret_cast<float4*>(o + col) = x;
         }
       }
-    } break;
-    case MTP_EPI_BF16_DGELU: {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)m * ep.ldo + n;
+    }
+    return;
+  }
+  const int col = n + i * 8;
+  if (col >= N) return;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        if (n + j < N) {
-          const float4 hv = a.f[j >> 3];
-          const uint32_t w[4] = {__float_as_uint(hv.x), __float_as_uint(hv.y), __float_as_uint(hv.z), __float_as_uint(hv.w)};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_bf16x2(w[t]);
-            v[j + 2 * t] *= gelu_erf_grad(f.x);
-            v[j + 2 * t + 1] *= gelu_erf_grad(f.y);
-          }
-          store_bf16x8(o + j, v + j);
-        }
-      }
-    } break;
-    case MTP_EPI_BF16_PIXSHUF: {
-      const int g = n / ep.ps_cout, co = n % ep.ps_cout;
+  for (int p = 0; p < 4; ++p) {
+    if (!ok[p]) continue;
+    size_t row = (size_t)m[p];
+    int ocol = col;
+    if (ep.mode == MTP_EPI_BF16_PIXSHUF) {
+      const int g = col / ep.ps_cout;
+      ocol = col % ep.ps_cout;
       const int dy = g >> 1, dx = g & 1;
       const int hw = ep.ps_h * ep.ps_w;
-      const int b = m / hw, rem = m % hw;
+      const int b = m[p] / hw, rem = m[p] % hw;
       const int y = rem / ep.ps_w, x = rem % ep.ps_w;
-      const size_t row = ((size_t)b * 2 * ep.ps_h + 2 * y + dy) * (2 * ep.ps_w) + 2 * x + dx;
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + row * ep.ldo + co;
+      row = ((size_t)b * 2 * ep.ps_h + 2 * y + dy) * (2 * ep.ps_w) + 2 * x + dx;
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + row * ep.ldo + ocol;
+    if (ep.mode == MTP_EPI_BF16_GELU) {
+      if (ep.out2 != nullptr) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(ep.out2) + row * ep.ldo + ocol, t[p]);
 #pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        if (n + j < N) store_bf16x8(o + j, v + j);
-    } break;
-    default: break;
+      for (int k = 0; k < 8; ++k) t[p][k] = gelu_erf(t[p][k]);
+    } else if (ep.mode == MTP_EPI_BF16_DGELU) {
+      const float4 hv = a.f[p];
+      const uint32_t w[4] = {__float_as_uint(hv.x), __float_as_uint(hv.y), __float_as_uint(hv.z), __float_as_uint(hv.w)};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16x2(w[q]);
+        t[p][2 * q] *= gelu_erf_grad(f.x);
+        t[p][2 * q + 1] *= gelu_erf_grad(f.y);
+      }
+    }
+    store_bf16x8(o, t[p]);
   }
 }
 
@@ -203,6 +225,7 @@ struct GemmProblem {
 struct Sched {
   uint16_t count[MAX_SLOTS];
   uint16_t item[MAX_SLOTS][MAX_ITEMS];
+  int strided_total;   // > 0: the lists above are unused; slot s walks items s, s + slots, s + 2*slots, ... < strided_total
   int dbg_mode;        // tuning aid: 0 normal, 1 = skip the TMA loads (MMA pipeline only), 2 = skip the MMAs (TMA pipeline only)
   long long* dbg;      // optional: [gridDim.x][8] globaltimer stamps of the pipeline phases (tuning aid, mtp_gemm_set_debug)
 };
@@ -233,7 +256,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   if (threadIdx.x == 0) MTP_STAMP(0);
   const int crank = CL2 ? (int)cluster_ctarank() : 0;
   const int slot = CL2 ? blockIdx.x / 2 : blockIdx.x;
-  const int n_items = sched.count[slot];
+  const int n_slots = CL2 ? gridDim.x / 2 : gridDim.x;
+  const int n_items = sched.strided_total > 0 ? (sched.strided_total - slot + n_slots - 1) / n_slots : sched.count[slot];
   const int groups0 = CL2 ? (p0.tiles_m + 1) / 2 : p0.tiles_m;
   const int items0 = groups0 * p0.tiles_n;
 
@@ -263,10 +287,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   if (CL2) cluster_sync_all();       // peer barriers are initialised before any remote signal can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  MTP_PDL_ENTRY();                   // everything above overlapped the previous kernel's tail; operands are read below
   if (threadIdx.x == 0) MTP_STAMP(1);
 
 #define MTP_DECODE_ITEM(IT)                                                                      \
-  const int item_ = sched.item[slot][IT];                                                        \
+  const int item_ = sched.strided_total > 0 ? slot + (IT) * n_slots : sched.item[slot][IT];      \
   const GemmProblem& P = item_ < items0 ? p0 : p1;                                               \
   const int local_ = item_ < items0 ? item_ : item_ - items0;                                    \
   const int mg_ = CL2 ? (P.tiles_m + 1) / 2 : P.tiles_m;                                         \
@@ -404,8 +429,14 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       mbar_wait(&tmem_full[acc], acc_phase);
       if (it == n_items - 1 && threadIdx.x == 64) MTP_STAMP(5);
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < M;
+      int pm[4];
+      bool pok[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        pm[p] = m0 + q * 32 + piece_row(lane, p);
+        pok[p] = pm[p] < M && sched.dbg_mode != 3;      // dbg 3: no epilogue stores (isolates the store drain at kernel end)
+      }
+      const bool f32 = mode_is_f32(ep.mode);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const int n_chunks = (min(BN, N - n0) + 31) / 32;
       uint32_t r[32];
@@ -413,13 +444,16 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       if (c < n_chunks) tmem_ld_32x32(taddr + c * 32, r);
       for (; c < n_chunks; c += 2) {
         AuxRegs aux;
-        if (row_ok) load_aux(ep, aux, m, n0 + c * 32, N);
+        load_aux(ep, aux, pm, pok, n0 + c * 32, N, lane);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (c + 2 < n_chunks) tmem_ld_32x32(taddr + (c + 2) * 32, r);      // next chunk streams in while this one is processed
-        if (row_ok) epilogue_chunk(ep, v, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, m, n0 + c * 32, N);
+        float t[4][8];
+        if (f32) lane_transpose<true>(v, t, lane);
+        else lane_transpose<false>(v, t, lane);
+        epilogue_pieces(ep, t, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -488,6 +522,7 @@ struct HostProblem {
 // the B rows each SM stages.
 static double kblock_cycles(int bn, bool cl2) { return std::max(2.0 * bn, 1.8 * (128.0 + (cl2 ? bn / 2 : bn))); }
 static const double kTileFixedCycles = 2500.0;      // epilogue / pipeline fill per tile
+static const double kClusterLaunchCycles = 5000.0;  // a cluster launch starts / retires ~2.5 us later than a plain one (tools/gemm_gaps.py)
 
 // Longest-processing-time schedule of the work items of up to two problems over the slots; returns the makespan (cycles).
 static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sched* out) {
@@ -502,7 +537,19 @@ static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sc
     for (int i = 0; i < n; ++i) items.push_back({base + i, c});
     base += n;
   }
-  if (base > 65535) return -1.0;
+  auto strided = [&]() {
+    // too many items for the by-value lists: every slot strides through the item range (items of one problem cost the same,
+    // so this is the same balance as LPT up to one item at the boundary between the problems)
+    std::vector<double> load(slots, 0.0);
+    for (size_t i = 0; i < items.size(); ++i) load[i % slots] += items[i].cost;
+    if (out) {
+      out->strided_total = base;
+      for (int s = 0; s < MAX_SLOTS; ++s) out->count[s] = s < slots ? 1 : 0;     // all slots are launched
+    }
+    return *std::max_element(load.begin(), load.end());
+  };
+  if (out) out->strided_total = 0;
+  if (base > MAX_ITEMS * slots) return strided();
   std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
   std::vector<double> load(slots, 0.0);
   std::vector<int> cnt(slots, 0);
@@ -513,7 +560,10 @@ static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sc
     auto top = pq.top();
     pq.pop();
     const int s = top.second;
-    if (cnt[s] >= MAX_ITEMS) return -1.0;       // does not fit the by-value schedule: caller falls back to another config
+    if (cnt[s] >= MAX_ITEMS) {
+      std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.id < b.id; });
+      return strided();
+    }
     if (out) out->item[s][cnt[s]] = (uint16_t)it.id;
     ++cnt[s];
     load[s] = top.first + it.cost;
@@ -546,7 +596,8 @@ static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
       if (force_bn) { if (cl != (force_bn >= 1000) || bn != force_bn % 1000) continue; }
       else if (cl == 1 && !all_pairable) continue;
       if (cl == 1 && any_bmn && bn % 128 != 0) continue;     // MN-major B is fetched in 64-column boxes: a pair needs an even count
-      const double c = build_schedule(pr, np, bn, cl == 1, nullptr);
+      double c = build_schedule(pr, np, bn, cl == 1, nullptr);
+      if (c >= 0 && cl == 1) c += kClusterLaunchCycles;
       if (c >= 0 && c < best_cost) { best_cost = c; best.bn = bn; best.cl2 = cl == 1; }
     }
   }
@@ -588,17 +639,22 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
   int used = 0;
   for (int s = 0; s < slots; ++s) if (sched.count[s] > 0) used = s + 1;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr;
   if (CL2) {
     cfg.gridDim = dim3(2 * used);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
     cfg.gridDim = dim3(used);
+  }
+  if (pdl_enabled()) {
+    attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+    ++cfg.numAttrs;
   }
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
