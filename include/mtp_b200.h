@@ -73,6 +73,8 @@ typedef struct mtp_epilogue {
   int pos_rows;           /* POS: rows of the positional table */
   int accumulate;         /* F32: add into out */
   int ps_h, ps_w, ps_cout;
+  float* colsum;          /* BF16 / BF16_DGELU: optional [N] fp32, += column sums of the stored values (the bias gradient of the
+                             Linear whose cotangent this GEMM produces); 16-byte aligned */
 } mtp_epilogue;
 
 int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N, int K,
@@ -105,7 +107,11 @@ int mtp_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const fl
                       float* rstd, int rows, int C, float eps, int fuse_gelu, mtp_stream_t stream);
 int mtp_layernorm_bwd(const void* dy_bf16, const void* x, int x_is_bf16, const float* mean, const float* rstd,
                       const float* gamma, const float* beta, const float* dres_f32, void* dx, int dx_is_bf16,
-                      float* dgamma, float* dbeta, int rows, int C, int fused_gelu, mtp_stream_t stream);
+                      float* dgamma, float* dbeta,
+                      /* optional fused mtp_scale_cast_bf16 of dx (f32 variant only; all NULL/0 = off): cast_out_bf16[r,c] =
+                       * bf16(dx[r,c] * cast_row_scale[r / cast_rows_per_group]), cast_colsum += its column sums */
+                      const float* cast_row_scale, int cast_rows_per_group, void* cast_out_bf16, float* cast_colsum,
+                      int rows, int C, int fused_gelu, mtp_stream_t stream);
 /* out_bf16[r,c] = in[r,c] * row_scale[r / rows_per_group] (DropPath backward, [V]:31-39); colsum (optional) += column sums
  * of the scaled values (bias gradient of the Linear that produced the branch). */
 int mtp_scale_cast_bf16(const float* in, const float* row_scale, int rows_per_group, void* out_bf16, float* colsum,

@@ -19,7 +19,7 @@ class Epilogue(ctypes.Structure):
     """struct mtp_epilogue (include/mtp_b200.h)."""
     _fields_ = [("mode", c_int), ("ldo", c_int), ("bias", c_void_p), ("out", c_void_p), ("out2", c_void_p),
                 ("aux", c_void_p), ("row_scale", c_void_p), ("rows_per_group", c_int), ("pos_rows", c_int),
-                ("accumulate", c_int), ("ps_h", c_int), ("ps_w", c_int), ("ps_cout", c_int)]
+                ("accumulate", c_int), ("ps_h", c_int), ("ps_w", c_int), ("ps_cout", c_int), ("colsum", c_void_p)]
 
 
 class GemmDesc(ctypes.Structure):
@@ -39,7 +39,7 @@ _SIGNATURES = {
     "mtp_gemm_set_debug_mode": [c_int],
     "mtp_layernorm_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],
     "mtp_layernorm_bwd": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                          c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+                          c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "mtp_scale_cast_bf16": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "mtp_colsum_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "mtp_cast_f32_bf16": [c_void_p, c_void_p, c_size_t, c_void_p],

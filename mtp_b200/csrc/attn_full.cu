@@ -18,6 +18,7 @@ __host__ __device__ inline int fa_smem_floats(int gh, int gw) { return 4 * FA_BQ
 __global__ void __launch_bounds__(FA_THREADS)
 full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int gh, int gw, int C, int nH, int use_rel) {
+  MTP_PDL_ENTRY();
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + FA_BQ * FA_LD;
@@ -190,7 +191,7 @@ extern "C" int mtp_full_attn_fwd(const void* qkv_bf16, const float* rel_pos_h, c
     attr_smem = smem;
   }
   const dim3 grid(ceil_div(N, FA_BQ), nH, B);
-  full_attn_fwd_kernel<<<grid, FA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  (void)launch_k(full_attn_fwd_kernel, grid, FA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), rel_pos_h, rel_pos_w, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, N, gh,
       gw, C, nH, rel_pos_h != nullptr);
   return check_launch("full_attn_fwd_kernel");

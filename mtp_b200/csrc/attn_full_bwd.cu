@@ -96,6 +96,7 @@ full_attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                         const float* __restrict__ lse, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                         __nv_bfloat16* __restrict__ dqkv, float* __restrict__ Dbuf, float* __restrict__ d_rel_h,
                         float* __restrict__ d_rel_w, int N, int gh, int gw, int C, int nH, int use_rel) {
+  MTP_PDL_ENTRY();
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + FB_T * FB_LD;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(FB_THREADS)
 full_attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                          const float* __restrict__ lse, const float* __restrict__ Dbuf, const __nv_bfloat16* __restrict__ dout,
                          __nv_bfloat16* __restrict__ dqkv, int N, int gh, int gw, int C, int nH, int use_rel) {
+  MTP_PDL_ENTRY();
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + FB_T * FB_LD;
@@ -360,13 +362,13 @@ extern "C" int mtp_full_attn_bwd(const void* qkv_bf16, const float* rel_pos_h, c
     attr_dkv = smem_dkv;
   }
   const dim3 grid(ceil_div(N, FB_T), nH, B);
-  full_attn_bwd_dq_kernel<<<grid, FB_THREADS, smem_dq, st>>>(
+  (void)launch_k(full_attn_bwd_dq_kernel, grid, FB_THREADS, smem_dq, st, 
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), rel_pos_h, rel_pos_w, lse, reinterpret_cast<const __nv_bfloat16*>(out_bf16),
       reinterpret_cast<const __nv_bfloat16*>(dout_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), Dbuf, d_rel_pos_h, d_rel_pos_w, N,
       gh, gw, C, nH, use_rel);
   int rc = check_launch("full_attn_bwd_dq_kernel");
   if (rc) return rc;
-  full_attn_bwd_dkv_kernel<<<grid, FB_THREADS, smem_dkv, st>>>(
+  (void)launch_k(full_attn_bwd_dkv_kernel, grid, FB_THREADS, smem_dkv, st, 
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), rel_pos_h, rel_pos_w, lse, Dbuf, reinterpret_cast<const __nv_bfloat16*>(dout_bf16),
       reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), N, gh, gw, C, nH, use_rel);
   return check_launch("full_attn_bwd_dkv_kernel");

@@ -64,6 +64,7 @@ constexpr int FTF_SMEM = FT_TILE /*Q*/ + 2 * 2 * FT_TILE /*K,V*/ + 4 * FT_TILE /
 __global__ void __launch_bounds__(FT_THREADS)
 full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                         __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int gh, int gw, int C, int nH, int use_rel) {
+  MTP_PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Qs = sm;
   uint8_t* Ks = Qs + FT_TILE;              // 256 rows
@@ -228,7 +229,7 @@ int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* re
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_fwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  full_attn_fwd_tc_kernel<<<B * nH, FT_THREADS, FTF_SMEM, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
+  (void)launch_k(full_attn_fwd_tc_kernel, B * nH, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
                                                                 reinterpret_cast<__nv_bfloat16*>(out), lse, gh * gw, gh, gw, C, nH,
                                                                 rel_h != nullptr);
   return check_launch("full_attn_fwd_tc_kernel");
@@ -243,6 +244,7 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                         const float* __restrict__ lse, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                         __nv_bfloat16* __restrict__ dqkv, float* __restrict__ d_rel_h, float* __restrict__ d_rel_w, int N, int gh, int gw,
                         int C, int nH, int use_rel) {
+  MTP_PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Qs = sm;
   uint8_t* Gs = Qs + FT_TILE;
@@ -541,7 +543,7 @@ int launch_full_attn_bwd_tc(const void* qkv, const float* rel_h, const float* re
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_bwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  full_attn_bwd_tc_kernel<<<B * nH, FT_THREADS, FTB_SMEM, st>>>(
+  (void)launch_k(full_attn_bwd_tc_kernel, B * nH, FT_THREADS, FTB_SMEM, st, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w, lse, reinterpret_cast<const __nv_bfloat16*>(out),
       reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dqkv), d_rel_h, d_rel_w, gh * gw, gh, gw, C, nH,
       rel_h != nullptr);

@@ -19,6 +19,7 @@ namespace mtp {
 // (1) zero-padded 7x7 mean of the LN'd tokens: CTA = (image-window, 256-channel slab), thread = 4 channels
 __global__ void __launch_bounds__(64)
 rvsa_pool_fwd_kernel(const __nv_bfloat16* __restrict__ yn, float* __restrict__ pooled, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
   const int bw = blockIdx.x;
   const int b = bw / (g.nh * g.nw), win = bw % (g.nh * g.nw);
   const int wy = win / g.nw, wx = win % g.nw;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(256)
 rvsa_heads_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w_off, const float* __restrict__ b_off,
                       const float* __restrict__ w_sc, const float* __restrict__ b_sc, const float* __restrict__ w_ang,
                       const float* __restrict__ b_ang, float* __restrict__ params, int n_bw, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
   const int o = blockIdx.x, nH = g.nH, C = g.C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // output order: [0,2nH) offsets (head-major, x then y), [2nH,4nH) scales, [4nH,5nH) angle
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(64)
 rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
                      const float* __restrict__ rel_w, const float* __restrict__ bias_table, __nv_bfloat16* __restrict__ out,
                      float* __restrict__ lse, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
   extern __shared__ float sm[];
   float* Qs = sm;
   float* Ks = Qs + NTOK * LDS_ROW;
@@ -263,10 +266,10 @@ extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, co
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n_bw = B * g.nh * g.nw;
-  rvsa_pool_fwd_kernel<<<dim3(n_bw, ceil_div(C, 256)), 64, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g);
+  (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 64, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g);
   int rc = check_launch("rvsa_pool_fwd_kernel");
   if (rc) return rc;
-  rvsa_heads_fwd_kernel<<<5 * nH, 256, 0, st>>>(pooled, w_off, b_off, w_scale, b_scale, w_angle, b_angle, params, n_bw, g);
+  (void)launch_k(rvsa_heads_fwd_kernel, 5 * nH, 256, 0, st, pooled, w_off, b_off, w_scale, b_scale, w_angle, b_angle, params, n_bw, g);
   return check_launch("rvsa_heads_fwd_kernel");
 }
 
@@ -285,7 +288,7 @@ extern "C" int mtp_rvsa_attn_fwd(const void* qkv_bf16, const float* params, cons
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_fwd smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  rvsa_attn_fwd_kernel<<<B * g.nh * g.nw * nH, 64, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  (void)launch_k(rvsa_attn_fwd_kernel, B * g.nh * g.nw * nH, 64, smem, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), params, rel_pos_h, rel_pos_w, bias_table,
       reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, g);
   return check_launch("rvsa_attn_fwd_kernel");

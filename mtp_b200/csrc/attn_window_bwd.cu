@@ -70,6 +70,7 @@ rvsa_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
                      const float* __restrict__ rel_w, const float* __restrict__ bias_table, const float* __restrict__ lse,
                      const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dkv,
                      float* __restrict__ dparams, float* __restrict__ part_rel, float* __restrict__ part_table, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
   extern __shared__ float sm[];
   float* Qs = sm;                          // [49][68]
   float* Ks = Qs + NTOK * BW_LD;           // k~, later dk~
@@ -346,6 +347,7 @@ rvsa_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 __global__ void __launch_bounds__(256)
 rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __restrict__ part_table, float* __restrict__ d_rel_h,
                             float* __restrict__ d_rel_w, float* __restrict__ d_table, int n_rel_parts, int n_bw, int nH) {
+  MTP_PDL_ENTRY();
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int n_rel = 2 * (2 * WS - 1) * HD;
   if (i < n_rel) {
@@ -363,6 +365,7 @@ rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __r
 // dqkv[t, C + c] = bf16(dkv[t, c]) for c in [0, 2C)
 __global__ void __launch_bounds__(256)
 rvsa_kv_finalize_kernel(const float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, size_t T, int C) {
+  MTP_PDL_ENTRY();
   const size_t n4 = T * (size_t)(2 * C / 4);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const size_t t = i / (2 * C / 4);
@@ -382,6 +385,7 @@ __global__ void __launch_bounds__(256)
 rvsa_sampling_bwd_kernel(const float* __restrict__ dparams, const float* __restrict__ pooled, const float* __restrict__ w_off,
                          const float* __restrict__ w_sc, const float* __restrict__ w_ang, float* __restrict__ g_out,
                          float* __restrict__ dpooled, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
   __shared__ float gs[5 * 64];       // nH <= 64
   const int bw = blockIdx.x, nH = g.nH, C = g.C;
   for (int o = threadIdx.x; o < 5 * nH; o += 256) {
@@ -411,6 +415,7 @@ __global__ void __launch_bounds__(256)
 rvsa_sampling_wgrad_kernel(const float* __restrict__ g_out, const float* __restrict__ pooled, float* __restrict__ dw_off,
                            float* __restrict__ db_off, float* __restrict__ dw_sc, float* __restrict__ db_sc, float* __restrict__ dw_ang,
                            float* __restrict__ db_ang, int n_bw, int nH, int C) {
+  MTP_PDL_ENTRY();
   const int o = blockIdx.y;                      // 0 .. 5nH-1
   const int c = blockIdx.x * 256 + threadIdx.x;
   float* dw; float* db; int oo;
@@ -435,6 +440,7 @@ rvsa_sampling_wgrad_kernel(const float* __restrict__ g_out, const float* __restr
 // (3) dyn[t][c] += dpooled[window(t)][c] / 49   (AvgPool backward; only real tokens receive it)
 __global__ void __launch_bounds__(256)
 rvsa_pool_bwd_add_kernel(const float* __restrict__ dpooled, __nv_bfloat16* __restrict__ dyn, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
   const int c4n = g.C / 4;
   const size_t total = (size_t)g.B * g.h * g.w * c4n;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -497,7 +503,7 @@ extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, cons
       if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_bwd smem attr: %s", cudaGetErrorString(e));
       attr = true;
     }
-    rvsa_attn_bwd_kernel<<<n_cta, BW_THREADS, smem, st>>>(
+    (void)launch_k(rvsa_attn_bwd_kernel, n_cta, BW_THREADS, smem, st, 
         reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), params, rel_pos_h, rel_pos_w, bias_table, lse,
         reinterpret_cast<const __nv_bfloat16*>(dout_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dkv, dparams, part_rel, part_table, g);
     rc = check_launch("rvsa_attn_bwd_kernel");
@@ -505,13 +511,13 @@ extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, cons
   }
   if (rc) return rc;
   const int n_red = 2 * (2 * WS - 1) * HD + 169 * nH;
-  rvsa_partials_reduce_kernel<<<ceil_div(n_red, 256), 256, 0, st>>>(part_rel, part_table, d_rel_pos_h, d_rel_pos_w, d_bias_table, n_rel_parts,
+  (void)launch_k(rvsa_partials_reduce_kernel, ceil_div(n_red, 256), 256, 0, st, part_rel, part_table, d_rel_pos_h, d_rel_pos_w, d_bias_table, n_rel_parts,
                                                                     n_cta / nH, nH);
   rc = check_launch("rvsa_partials_reduce_kernel");
   if (rc) return rc;
   const size_t n4 = T * (size_t)(2 * C / 4);
   const int grid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)num_sms() * 8);
-  rvsa_kv_finalize_kernel<<<grid, 256, 0, st>>>(dkv, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), T, C);
+  (void)launch_k(rvsa_kv_finalize_kernel, grid, 256, 0, st, dkv, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), T, C);
   return check_launch("rvsa_kv_finalize_kernel");
 }
 
@@ -527,16 +533,16 @@ extern "C" int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, 
   const int n_bw = B * g.nh * g.nw;
   float* g_out = reinterpret_cast<float*>(workspace);            // [n_bw][5nH]
   float* dpooled = g_out + (size_t)n_bw * 5 * nH;                // [n_bw][C]
-  rvsa_sampling_bwd_kernel<<<dim3(n_bw, ceil_div(C, 256)), 256, 0, st>>>(dparams, pooled, w_off, w_scale, w_angle, g_out, dpooled, g);
+  (void)launch_k(rvsa_sampling_bwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, dparams, pooled, w_off, w_scale, w_angle, g_out, dpooled, g);
   int rc = check_launch("rvsa_sampling_bwd_kernel");
   if (rc) return rc;
-  rvsa_sampling_wgrad_kernel<<<dim3(ceil_div(C, 256), 5 * nH), 256, 0, st>>>(g_out, pooled, dw_off, db_off, dw_scale, db_scale, dw_angle,
+  (void)launch_k(rvsa_sampling_wgrad_kernel, dim3(ceil_div(C, 256), 5 * nH), 256, 0, st, g_out, pooled, dw_off, db_off, dw_scale, db_scale, dw_angle,
                                                                              db_angle, n_bw, nH, C);
   rc = check_launch("rvsa_sampling_wgrad_kernel");
   if (rc) return rc;
   const size_t total = (size_t)B * h * w * (C / 4);
   const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 8);
-  rvsa_pool_bwd_add_kernel<<<grid, 256, 0, st>>>(dpooled, reinterpret_cast<__nv_bfloat16*>(dyn_bf16), g);
+  (void)launch_k(rvsa_pool_bwd_add_kernel, grid, 256, 0, st, dpooled, reinterpret_cast<__nv_bfloat16*>(dyn_bf16), g);
   return check_launch("rvsa_pool_bwd_add_kernel");
 }
 

@@ -34,6 +34,7 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                         const float* __restrict__ rel_w, const float* __restrict__ bias_table, const float* __restrict__ lse,
                         const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dkv,
                         float* __restrict__ dparams, float* __restrict__ part_rel, float* __restrict__ part_table, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t sm[];
   uint8_t* Qs = sm;
   uint8_t* Ks = Qs + WB_TILE;
@@ -420,7 +421,7 @@ int launch_rvsa_attn_bwd_tc(const void* qkv, const float* params, const float* r
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_bwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  rvsa_attn_bwd_tc_kernel<<<g.B * g.nh * g.nw * (g.nH / 2), WB_THREADS, WB_SMEM, st>>>(
+  (void)launch_k(rvsa_attn_bwd_tc_kernel, g.B * g.nh * g.nw * (g.nH / 2), WB_THREADS, WB_SMEM, st, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), params, rel_h, rel_w, table, lse, reinterpret_cast<const __nv_bfloat16*>(dout),
       reinterpret_cast<__nv_bfloat16*>(dqkv), dkv, dparams, part_rel, part_table, g);
   return check_launch("rvsa_attn_bwd_tc_kernel");

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(WTC_THREADS)
 rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
                         const float* __restrict__ rel_w, const float* __restrict__ bias_table, __nv_bfloat16* __restrict__ out,
                         float* __restrict__ lse, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t sm[];      // indexed directly so every access stays in the shared state space
   uint8_t* Qs = sm;
   uint8_t* Ks = Qs + WTC_TILE;
@@ -241,7 +242,7 @@ int launch_rvsa_attn_fwd_tc(const void* qkv, const float* params, const float* r
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_fwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  rvsa_attn_fwd_tc_kernel<<<g.B * g.nh * g.nw * (g.nH / 2), WTC_THREADS, WTC_SMEM, st>>>(
+  (void)launch_k(rvsa_attn_fwd_tc_kernel, g.B * g.nh * g.nw * (g.nH / 2), WTC_THREADS, WTC_SMEM, st, 
       reinterpret_cast<const __nv_bfloat16*>(qkv), params, rel_h, rel_w, table, reinterpret_cast<__nv_bfloat16*>(out), lse, g);
   return check_launch("rvsa_attn_fwd_tc_kernel");
 }

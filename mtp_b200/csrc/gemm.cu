@@ -47,6 +47,7 @@ struct EpiParams {
   const void* aux;
   const float* row_scale;
   int rows_per_group, pos_rows, accumulate, ps_h, ps_w, ps_cout;
+  float* colsum;
 };
 
 // ---- epilogue ---------------------------------------------------------------------------------------------------------
@@ -169,10 +170,13 @@ __device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[
     return;
   }
   const int col = n + i * 8;
-  if (col >= N) return;
+  const bool col_ok = col < N;
+  float cs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cs[k] = 0.f;
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    if (!ok[p]) continue;
+    if (!ok[p] || !col_ok) continue;
     size_t row = (size_t)m[p];
     int ocol = col;
     if (ep.mode == MTP_EPI_BF16_PIXSHUF) {
@@ -200,6 +204,23 @@ __device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[
       }
     }
     store_bf16x8(o, t[p]);
+    if (ep.colsum != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] += __bfloat162float(__float2bfloat16_rn(t[p][k]));      // sums of the STORED values
+    }
+  }
+  if (ep.colsum != nullptr) {       // column sums over the warp's 32 rows: the 8 lane groups hold the same columns
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 4);
+      cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+      cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+    }
+    if (lane < 4 && col_ok) {
+      float* dst = ep.colsum + col;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
+    }
   }
 }
 
@@ -678,6 +699,9 @@ static int validate_problem(const HostProblem& h) {
     MTP_REQUIRE(ep.aux != nullptr, "mtp_gemm_bf16: epilogue mode %d needs aux", ep.mode);
   if (ep.mode == MTP_EPI_F32_RESID && ep.row_scale) MTP_REQUIRE(ep.rows_per_group > 0, "mtp_gemm_bf16: rows_per_group");
   if (ep.mode == MTP_EPI_F32_POS) MTP_REQUIRE(ep.pos_rows > 0, "mtp_gemm_bf16: pos_rows");
+  if (ep.colsum != nullptr)
+    MTP_REQUIRE((ep.mode == MTP_EPI_BF16 || ep.mode == MTP_EPI_BF16_DGELU) && ((uintptr_t)ep.colsum & 15) == 0,
+                "mtp_gemm_bf16: colsum needs a BF16 / BF16_DGELU epilogue and a 16-byte aligned pointer");
   if (ep.mode == MTP_EPI_BF16_PIXSHUF)
     MTP_REQUIRE(ep.ps_h > 0 && ep.ps_w > 0 && ep.ps_cout > 0 && ep.ps_cout % 32 == 0 && h.N == 4 * ep.ps_cout,
                 "mtp_gemm_bf16: bad pixel-shuffle geometry");
@@ -689,6 +713,7 @@ static EpiParams to_epi(const mtp_epilogue* ep) {
   p.mode = ep->mode; p.ldo = ep->ldo; p.bias = ep->bias; p.out = ep->out; p.out2 = ep->out2; p.aux = ep->aux;
   p.row_scale = ep->row_scale; p.rows_per_group = ep->rows_per_group; p.pos_rows = ep->pos_rows;
   p.accumulate = ep->accumulate; p.ps_h = ep->ps_h; p.ps_w = ep->ps_w; p.ps_cout = ep->ps_cout;
+  p.colsum = ep->colsum;
   return p;
 }
 

@@ -21,6 +21,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int cin, int H, int W, int gh, int gw) {
+  MTP_PDL_ENTRY();
   const int chunks_per_tok = cin * 16 * 4;                 // 4-element chunks per token row
   const size_t total = (size_t)B * gh * gw * chunks_per_tok;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -53,6 +54,7 @@ __device__ __forceinline__ void map_index(const MapGeom& g, int b, int Y, int X,
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 tok_to_nchw_kernel(const TIn* __restrict__ tok, int ld, TOut* __restrict__ out, const MapGeom g) {
+  MTP_PDL_ENTRY();
   __shared__ float tile[32][33];
   const int Ho = g.h << g.L, Wo = g.w << g.L;
   const int x_tiles = ceil_div(Wo, 32);
@@ -78,6 +80,7 @@ tok_to_nchw_kernel(const TIn* __restrict__ tok, int ld, TOut* __restrict__ out, 
 template <typename TIn, typename TOut, bool ACC>
 __global__ void __launch_bounds__(256)
 nchw_to_tok_kernel(const TIn* __restrict__ in, TOut* __restrict__ tok, int ld, const MapGeom g) {
+  MTP_PDL_ENTRY();
   __shared__ float tile[32][33];
   const int Ho = g.h << g.L, Wo = g.w << g.L;
   const int x_tiles = ceil_div(Wo, 32);
@@ -105,6 +108,7 @@ nchw_to_tok_kernel(const TIn* __restrict__ in, TOut* __restrict__ tok, int ld, c
 // token-major f32 [B, h, w, C] -> token-major f32 [B, h/2, w/2, C]                                   [V]:654
 __global__ void __launch_bounds__(256)
 maxpool2_tok_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int h, int w, int C) {
+  MTP_PDL_ENTRY();
   const int ho = h / 2, wo = w / 2, c4n = C / 4;
   const size_t total = (size_t)B * ho * wo * c4n;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -126,6 +130,7 @@ maxpool2_tok_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int 
 // dx[argmax position] += dy   (first maximum in scan order wins, as in ATen's max_pool2d backward)
 __global__ void __launch_bounds__(256)
 maxpool2_tok_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int h, int w, int C) {
+  MTP_PDL_ENTRY();
   const int ho = h / 2, wo = w / 2;
   const size_t total = (size_t)B * ho * wo * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -158,10 +163,10 @@ extern "C" int mtp_patchify(const void* img, int img_is_bf16, void* out_bf16, in
   const size_t total = (size_t)B * gh * gw * cin * 64;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (img_is_bf16)
-    patchify_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(img),
+    (void)launch_k(patchify_kernel<__nv_bfloat16>, grid_for(total, 256), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(img),
                                                                          reinterpret_cast<__nv_bfloat16*>(out_bf16), B, cin, H, W, gh, gw);
   else
-    patchify_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(img),
+    (void)launch_k(patchify_kernel<float>, grid_for(total, 256), 256, 0, st, reinterpret_cast<const float*>(img),
                                                                  reinterpret_cast<__nv_bfloat16*>(out_bf16), B, cin, H, W, gh, gw);
   return check_launch("patchify_kernel");
 }
@@ -173,7 +178,7 @@ extern "C" int mtp_tok_to_nchw(const void* tok, int tok_is_bf16, int ld, void* o
   const MapGeom g{B, h, w, C, level};
   const dim3 grid(ceil_div(w << level, 32) * (h << level), ceil_div(C, 32), B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define T2N(TI, TO) tok_to_nchw_kernel<TI, TO><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(tok), ld, reinterpret_cast<TO*>(out), g)
+#define T2N(TI, TO) (void)launch_k(tok_to_nchw_kernel<TI, TO>, grid, 256, 0, st, reinterpret_cast<const TI*>(tok), ld, reinterpret_cast<TO*>(out), g)
   if (tok_is_bf16 && out_is_bf16) T2N(__nv_bfloat16, __nv_bfloat16);
   else if (tok_is_bf16) T2N(__nv_bfloat16, float);
   else if (out_is_bf16) T2N(float, __nv_bfloat16);
@@ -189,7 +194,7 @@ extern "C" int mtp_nchw_to_tok(const void* in, int in_is_bf16, void* tok, int to
   const MapGeom g{B, h, w, C, level};
   const dim3 grid(ceil_div(w << level, 32) * (h << level), ceil_div(C, 32), B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define N2T(TI, TO, A) nchw_to_tok_kernel<TI, TO, A><<<grid, 256, 0, st>>>(reinterpret_cast<const TI*>(in), reinterpret_cast<TO*>(tok), ld, g)
+#define N2T(TI, TO, A) (void)launch_k(nchw_to_tok_kernel<TI, TO, A>, grid, 256, 0, st, reinterpret_cast<const TI*>(in), reinterpret_cast<TO*>(tok), ld, g)
   if (accumulate) {
     MTP_REQUIRE(!tok_is_bf16, "mtp_nchw_to_tok: accumulate needs an f32 destination");
     if (in_is_bf16) N2T(__nv_bfloat16, float, true); else N2T(float, float, true);
@@ -205,13 +210,13 @@ extern "C" int mtp_nchw_to_tok(const void* in, int in_is_bf16, void* tok, int to
 extern "C" int mtp_maxpool2_tok_fwd(const float* x, float* y, int B, int h, int w, int C, mtp_stream_t stream) {
   MTP_REQUIRE(x && y && B > 0 && h >= 2 && w >= 2 && C % 4 == 0, "mtp_maxpool2_tok_fwd: bad args");
   const size_t total = (size_t)B * (h / 2) * (w / 2) * (C / 4);
-  maxpool2_tok_fwd_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, h, w, C);
+  (void)launch_k(maxpool2_tok_fwd_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, y, B, h, w, C);
   return check_launch("maxpool2_tok_fwd_kernel");
 }
 
 extern "C" int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, int B, int h, int w, int C, mtp_stream_t stream) {
   MTP_REQUIRE(x && dy && dx && B > 0 && h >= 2 && w >= 2, "mtp_maxpool2_tok_bwd: bad args");
   const size_t total = (size_t)B * (h / 2) * (w / 2) * C;
-  maxpool2_tok_bwd_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, dy, dx, B, h, w, C);
+  (void)launch_k(maxpool2_tok_bwd_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, dy, dx, B, h, w, C);
   return check_launch("maxpool2_tok_bwd_kernel");
 }

@@ -12,6 +12,7 @@
 namespace mtp {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, size_t n4, float* __restrict__ out) {
+  MTP_PDL_ENTRY();
   float s = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ p16, const uint8_t* __restrict__ chunk_group, const float* __restrict__ group_lr,
              const float* __restrict__ group_wd, const float* __restrict__ state, size_t n4, AdamWArgs a) {
+  MTP_PDL_ENTRY();
   const float step = state[0];
   float lr = a.lr0;
   if (a.t_max > 0) lr = a.eta_min + (a.lr0 - a.eta_min) * 0.5f * (1.0f + cospif(fminf(step - 1.0f, (float)a.t_max) / (float)a.t_max));
@@ -79,6 +81,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 }
 
 __global__ void step_begin_kernel(float* state) {
+  MTP_PDL_ENTRY();
   state[0] += 1.0f;
   state[1] = 0.0f;
 }
@@ -89,7 +92,7 @@ using namespace mtp;
 
 extern "C" int mtp_optim_step_begin(float* state, mtp_stream_t stream) {
   MTP_REQUIRE(state, "mtp_optim_step_begin: null pointer");
-  step_begin_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(state);
+  (void)launch_k(step_begin_kernel, 1, 1, 0, reinterpret_cast<cudaStream_t>(stream), state);
   return check_launch("step_begin_kernel");
 }
 
@@ -98,7 +101,7 @@ extern "C" int mtp_sumsq_f32(const float* x, size_t n, float* out, mtp_stream_t 
   if (n == 0) return MTP_OK;
   const size_t n4 = n / 4;
   const int grid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)num_sms() * 8);
-  sumsq_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n4, out);
+  (void)launch_k(sumsq_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), x, n4, out);
   return check_launch("sumsq_kernel");
 }
 
@@ -112,7 +115,7 @@ extern "C" int mtp_adamw_step(float* p, const float* g, float* m, float* v, void
   AdamWArgs a{lr0, eta_min, beta1, beta2, eps, max_norm, grad_scale, t_max};
   const size_t n4 = n / 4;
   const int grid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)num_sms() * 16);
-  adamw_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), chunk_group,
+  (void)launch_k(adamw_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), chunk_group,
                                                                       group_lr_scale, group_weight_decay, state, n4, a);
   return check_launch("adamw_kernel");
 }

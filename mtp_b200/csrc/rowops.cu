@@ -34,6 +34,7 @@ template <typename TIn, int NV, bool GELU>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 ln_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows, float eps) {
+  MTP_PDL_ENTRY();
   constexpr int C = NV * 128;
   const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -78,22 +79,32 @@ ln_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma, const 
 // dx_out = dres (optional fp32 residual-path gradient) + LN'(dy)   where dy is the gradient w.r.t. the LN output
 // (for the GELU variant: w.r.t. the GELU output; the pre-GELU value is recomputed from x).
 // dgamma/dbeta: per-CTA partial sums over its rows (each lane owns fixed columns), cross-warp reduce in smem, one
-// atomicAdd per column per CTA.  Optionally also emits bf16(row_scale * dx_out) for the next dgrad/wgrad GEMM.
-template <typename TIn, typename TDx, int NV, bool GELU>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+// atomicAdd per column per CTA.
+// CAST: additionally emits g16 = bf16(row_scale[row / rows_per_group] * dx_out) -- the A operand of the next dgrad / wgrad GEMMs
+// (DropPath backward of the next residual branch) -- and accumulates its column sums (that branch's last bias gradient), which
+// saves the separate scale_cast pass over the fp32 gradient.
+// The CTA has blockDim.x / 32 warps, one row each per iteration; the host sizes it so that the rows fill the SMs in ONE wave.
+constexpr int LN_BWD_MAX_WARPS = 12;
+
+template <typename TIn, typename TDx, int NV, bool GELU, bool CAST>
+__global__ void __launch_bounds__(LN_BWD_MAX_WARPS * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
               const float* __restrict__ dres, TDx* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              const float* __restrict__ row_scale, int rows_per_group, __nv_bfloat16* __restrict__ g16, float* __restrict__ colsum16,
               int rows, int rows_per_cta) {
   constexpr int C = NV * 128;
-  __shared__ float red[ROW_WARPS][C];     // C <= 1024 -> 32 KB
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 ag[NV], ab[NV];
+  extern __shared__ float red[];          // [warps][C]
+  MTP_PDL_ENTRY();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  float4 ag[NV], ab[NV], ac[CAST ? NV : 1];
 #pragma unroll
   for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+#pragma unroll
+  for (int i = 0; i < (CAST ? NV : 1); ++i) ac[i] = make_float4(0, 0, 0, 0);
   const int row0 = blockIdx.x * rows_per_cta;
   const int row1 = min(rows, row0 + rows_per_cta);
-  for (int row = row0 + warp; row < row1; row += ROW_WARPS) {
+  for (int row = row0 + warp; row < row1; row += n_warps) {
     const float mu = mean[row], rs = rstd[row];
     const TIn* xr = x + (size_t)row * C;
     const __nv_bfloat16* dyr = dy + (size_t)row * C;
@@ -122,6 +133,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, c
     s1 = warp_sum(s1) * (1.0f / C);
     s2 = warp_sum(s2) * (1.0f / C);
     TDx* dxr = dx + (size_t)row * C;
+    const float sc = (CAST && row_scale != nullptr) ? __ldg(row_scale + row / rows_per_group) : 1.0f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
@@ -135,23 +147,28 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, c
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       Vec4<TDx>::store(dxr + c, o);
+      if (CAST) {
+        o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
+        Vec4<__nv_bfloat16>::store(g16 + (size_t)row * C + c, o);
+        ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
+      }
     }
   }
   // cross-warp reduction of the column sums
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (CAST ? 3 : 2); ++pass) {
+    float* dst = pass == 0 ? dgamma : pass == 1 ? dbeta : colsum16;
+    if (dst == nullptr) continue;          // uniform
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      *reinterpret_cast<float4*>(&red[warp][c]) = pass == 0 ? ag[i] : ab[i];
+      *reinterpret_cast<float4*>(&red[warp * C + c]) = pass == 0 ? ag[i] : pass == 1 ? ab[i] : ac[CAST ? i : 0];
     }
     __syncthreads();
-    float* dst = pass == 0 ? dgamma : dbeta;
-    for (int c = threadIdx.x; c < C; c += ROW_WARPS * 32) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < ROW_WARPS; ++w) t += red[w][c];
+      for (int w = 0; w < n_warps; ++w) t += red[w * C + c];
       atomicAdd(dst + c, t);
     }
   }
@@ -162,6 +179,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, c
 __global__ void __launch_bounds__(256)
 scale_cast_kernel(const float* __restrict__ in, const float* __restrict__ row_scale, int rows_per_group,
                   __nv_bfloat16* __restrict__ out, float* __restrict__ colsum, int rows, int C, int rows_per_cta) {
+  MTP_PDL_ENTRY();
   // thread owns 4 consecutive columns; CTA walks rows [row0, row1)
   const int row0 = blockIdx.y * rows_per_cta, row1 = min(rows, row0 + rows_per_cta);
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
@@ -183,6 +201,7 @@ scale_cast_kernel(const float* __restrict__ in, const float* __restrict__ row_sc
 // colsum[c] += sum_r in_bf16[r, c]
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ colsum, int rows, int C, int ld, int rows_per_cta) {
+  MTP_PDL_ENTRY();
   const int row0 = blockIdx.y * rows_per_cta, row1 = min(rows, row0 + rows_per_cta);
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= C) return;
@@ -196,12 +215,14 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ col
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n4) {
+  MTP_PDL_ENTRY();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
     Vec4<__nv_bfloat16>::store(out + i * 4, *reinterpret_cast<const float4*>(in + i * 4));
 }
 
 // out_f32 += in_bf16  (feature-map gradient joining the residual-stream gradient)
 __global__ void __launch_bounds__(256) add_bf16_into_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n4) {
+  MTP_PDL_ENTRY();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = Vec4<__nv_bfloat16>::load(in + i * 4);
     float4 o = *reinterpret_cast<float4*>(out + i * 4);
@@ -217,7 +238,7 @@ static int ln_fwd_dispatch(const void* x, const float* g, const float* b, void* 
   const TIn* xp = reinterpret_cast<const TIn*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   switch (C / 128) {
-#define LN_CASE(NV) case NV: ln_fwd_kernel<TIn, NV, GELU><<<grid, block, 0, st>>>(xp, g, b, yp, mean, rstd, rows, eps); break;
+#define LN_CASE(NV) case NV: (void)launch_k(ln_fwd_kernel<TIn, NV, GELU>, grid, block, 0, st, xp, g, b, yp, mean, rstd, rows, eps); break;
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
 #undef LN_CASE
     default: return set_error(MTP_ERR_INVALID, "layernorm: unsupported C=%d", C);
@@ -225,21 +246,39 @@ static int ln_fwd_dispatch(const void* x, const float* g, const float* b, void* 
   return check_launch("ln_fwd_kernel");
 }
 
-template <typename TIn, typename TDx, bool GELU>
+template <typename TIn, typename TDx, bool GELU, bool CAST>
 static int ln_bwd_dispatch(const void* dy, const void* x, const float* mean, const float* rstd, const float* g, const float* b,
-                           const float* dres, void* dx, float* dgamma, float* dbeta, int rows, int C, cudaStream_t st) {
-  const int ctas = min(ceil_div(rows, ROW_WARPS), 2 * num_sms());
-  const int rows_per_cta = ceil_div(rows, ctas);
-  const dim3 grid(ceil_div(rows, rows_per_cta)), block(ROW_WARPS * 32);
+                           const float* dres, void* dx, float* dgamma, float* dbeta, const float* row_scale, int rows_per_group,
+                           void* g16, float* colsum16, int rows, int C, cudaStream_t st) {
+  // one wave: every SM gets one CTA whose warps take one row each (rows <= 12 * SMs); beyond that CTAs loop over rows
+  const int per_sm = ceil_div(rows, num_sms());
+  const int warps = std::max(4, std::min(per_sm, LN_BWD_MAX_WARPS));
+  const int rows_per_cta = std::max(per_sm, warps);
+  const dim3 grid(ceil_div(rows, rows_per_cta)), block(warps * 32);
+  const size_t smem = (size_t)warps * C * sizeof(float);
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
   const TIn* xp = reinterpret_cast<const TIn*>(x);
   TDx* dxp = reinterpret_cast<TDx*>(dx);
+  __nv_bfloat16* g16p = reinterpret_cast<__nv_bfloat16*>(g16);
+  cudaError_t e = cudaSuccess;
   switch (C / 128) {
-#define LN_CASE(NV) case NV: ln_bwd_kernel<TIn, TDx, NV, GELU><<<grid, block, 0, st>>>(dyp, xp, mean, rstd, g, b, dres, dxp, dgamma, dbeta, rows, rows_per_cta); break;
+#define LN_CASE(NV)                                                                                                        \
+  case NV: {                                                                                                               \
+    auto kern = ln_bwd_kernel<TIn, TDx, NV, GELU, CAST>;                                                                   \
+    static bool attr = false;                                                                                              \
+    if (!attr && smem > 48 * 1024) {                                                                                       \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_BWD_MAX_WARPS * NV * 128 * 4);        \
+      if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "ln_bwd smem attr: %s", cudaGetErrorString(e));                 \
+      attr = true;                                                                                                         \
+    }                                                                                                                      \
+    e = launch_k(kern, grid, block, smem, st, dyp, xp, mean, rstd, g, b, dres, dxp, dgamma, dbeta, row_scale,              \
+                 rows_per_group, g16p, colsum16, rows, rows_per_cta);                                                      \
+  } break;
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
 #undef LN_CASE
     default: return set_error(MTP_ERR_INVALID, "layernorm bwd: unsupported C=%d", C);
   }
+  if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "ln_bwd_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("ln_bwd_kernel");
 }
 
@@ -262,15 +301,25 @@ extern "C" int mtp_layernorm_fwd(const void* x, int x_is_bf16, const float* gamm
 
 extern "C" int mtp_layernorm_bwd(const void* dy_bf16, const void* x, int x_is_bf16, const float* mean, const float* rstd,
                                  const float* gamma, const float* beta, const float* dres_f32, void* dx, int dx_is_bf16,
-                                 float* dgamma, float* dbeta, int rows, int C, int fused_gelu, mtp_stream_t stream) {
+                                 float* dgamma, float* dbeta, const float* cast_row_scale, int cast_rows_per_group,
+                                 void* cast_out_bf16, float* cast_colsum, int rows, int C, int fused_gelu, mtp_stream_t stream) {
   MTP_REQUIRE(dy_bf16 && x && mean && rstd && gamma && dx && dgamma && dbeta, "mtp_layernorm_bwd: null pointer");
   MTP_REQUIRE(rows > 0 && C % 128 == 0 && C <= 1024, "mtp_layernorm_bwd: rows=%d C=%d unsupported", rows, C);
   MTP_REQUIRE(!fused_gelu || beta, "mtp_layernorm_bwd: GELU variant needs beta");
+  MTP_REQUIRE(!cast_row_scale || cast_rows_per_group > 0, "mtp_layernorm_bwd: cast_rows_per_group");
+  MTP_REQUIRE(cast_out_bf16 || !cast_colsum, "mtp_layernorm_bwd: cast_colsum needs cast_out_bf16");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!x_is_bf16 && !dx_is_bf16 && !fused_gelu)
-    return ln_bwd_dispatch<float, float, false>(dy_bf16, x, mean, rstd, gamma, beta, dres_f32, dx, dgamma, dbeta, rows, C, st);
+  if (!x_is_bf16 && !dx_is_bf16 && !fused_gelu) {
+    if (cast_out_bf16)
+      return ln_bwd_dispatch<float, float, false, true>(dy_bf16, x, mean, rstd, gamma, beta, dres_f32, dx, dgamma, dbeta, cast_row_scale,
+                                                        cast_rows_per_group, cast_out_bf16, cast_colsum, rows, C, st);
+    return ln_bwd_dispatch<float, float, false, false>(dy_bf16, x, mean, rstd, gamma, beta, dres_f32, dx, dgamma, dbeta, nullptr, 0,
+                                                       nullptr, nullptr, rows, C, st);
+  }
+  MTP_REQUIRE(!cast_out_bf16, "mtp_layernorm_bwd: the fused cast is only available for the (f32 x, f32 dx, no gelu) variant");
   if (x_is_bf16 && dx_is_bf16 && fused_gelu)
-    return ln_bwd_dispatch<__nv_bfloat16, __nv_bfloat16, true>(dy_bf16, x, mean, rstd, gamma, beta, dres_f32, dx, dgamma, dbeta, rows, C, st);
+    return ln_bwd_dispatch<__nv_bfloat16, __nv_bfloat16, true, false>(dy_bf16, x, mean, rstd, gamma, beta, dres_f32, dx, dgamma, dbeta,
+                                                                      nullptr, 0, nullptr, nullptr, rows, C, st);
   return set_error(MTP_ERR_INVALID, "mtp_layernorm_bwd: unsupported variant (x_bf16=%d dx_bf16=%d gelu=%d)", x_is_bf16, dx_is_bf16, fused_gelu);
 }
 
@@ -282,7 +331,7 @@ extern "C" int mtp_scale_cast_bf16(const float* in, const float* row_scale, int 
   const int gx = ceil_div(C, 1024);
   const int gy = max(1, min(ceil_div(rows, 8), 4 * num_sms() / gx));
   const int rpc = ceil_div(rows, gy);
-  scale_cast_kernel<<<dim3(gx, ceil_div(rows, rpc)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  (void)launch_k(scale_cast_kernel, dim3(gx, ceil_div(rows, rpc)), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       in, row_scale, rows_per_group, reinterpret_cast<__nv_bfloat16*>(out_bf16), colsum, rows, C, rpc);
   return check_launch("scale_cast_kernel");
 }
@@ -293,7 +342,7 @@ extern "C" int mtp_colsum_bf16(const void* in_bf16, int ld, float* colsum, int r
   const int gx = ceil_div(C, 1024);
   const int gy = max(1, min(ceil_div(rows, 8), 4 * num_sms() / gx));
   const int rpc = ceil_div(rows, gy);
-  colsum_bf16_kernel<<<dim3(gx, ceil_div(rows, rpc)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  (void)launch_k(colsum_bf16_kernel, dim3(gx, ceil_div(rows, rpc)), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(in_bf16), colsum, rows, C, ld, rpc);
   return check_launch("colsum_bf16_kernel");
 }
@@ -303,7 +352,7 @@ extern "C" int mtp_cast_f32_bf16(const float* in, void* out_bf16, size_t n, mtp_
   if (n == 0) return MTP_OK;
   const size_t n4 = n / 4;
   const int grid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)num_sms() * 8);
-  cast_f32_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n4);
+  (void)launch_k(cast_f32_bf16_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), in, reinterpret_cast<__nv_bfloat16*>(out_bf16), n4);
   return check_launch("cast_f32_bf16_kernel");
 }
 
@@ -312,6 +361,6 @@ extern "C" int mtp_add_bf16_into_f32(const void* in_bf16, float* out, size_t n, 
   if (n == 0) return MTP_OK;
   const size_t n4 = n / 4;
   const int grid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)num_sms() * 8);
-  add_bf16_into_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(in_bf16), out, n4);
+  (void)launch_k(add_bf16_into_f32_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(in_bf16), out, n4);
   return check_launch("add_bf16_into_f32_kernel");
 }

@@ -40,17 +40,21 @@ class GradStore:
         return self.views[name]
 
 
-def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_BF16, aux=None):
+def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_BF16, aux=None, colsum=None):
     """y = x W^T + b with x [T, n_in], W [n_out, n_in], cotangent g [T, n_out].
     dW = g^T x (both operands MN-major, K = T) and dx = g W (B operand MN-major) only share the input g: they run as ONE
-    grouped launch whose tiles are spread over the SMs by a common schedule."""
+    grouped launch whose tiles are spread over the SMs by a common schedule.  ``colsum``: fp32 [n_in] that receives the column
+    sums of dx (the bias gradient of the Linear below) from the dgrad epilogue."""
     dx = torch.empty(T, n_in, device=g_bf16.device, dtype=BF16)
-    ops.gemm_dual(dict(A=g_bf16, B=w_bf16, M=T, N=n_in, K=n_out, out=dx, b_mn=True, mode=dgrad_mode, aux=aux, lda=n_out, ldb=n_in),
+    ops.gemm_dual(dict(A=g_bf16, B=w_bf16, M=T, N=n_in, K=n_out, out=dx, b_mn=True, mode=dgrad_mode, aux=aux, lda=n_out, ldb=n_in,
+                       colsum=colsum),
                   dict(A=g_bf16, B=x_bf16, M=n_out, N=n_in, K=T, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=n_out, ldb=n_in, ldo=n_in))
     return dx
 
 
-def _block_backward(i, d, s, dx2, G, B, gh, gw, nH, keep):
+def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
+    """``g2``: bf16(keep_mlp * dx2) when the kernel that produced dx2 already emitted it (else None).  ``nxt`` = (row_scale,
+    colsum) of the block below: its g2 is emitted by this block's last LayerNorm backward.  Returns (dx0, g2 of the block below)."""
     pre = f"blocks.{i}."
     T, C = dx2.shape
     N = gh * gw
@@ -58,13 +62,14 @@ def _block_backward(i, d, s, dx2, G, B, gh, gw, nH, keep):
     km = keep[i, 1] if keep is not None else None
     ka = keep[i, 0] if keep is not None else None
     # ---- MLP branch ([V]:509)
-    g2 = ops.scale_cast_bf16(dx2, km, N, colsum=G.g(pre + "mlp.fc2.bias"))
-    dh = _linear_bwd(g2, s["a"], d["fc2_w"], G.g(pre + "mlp.fc2.weight"), T, C, hid, dgrad_mode=L.EPI_BF16_DGELU, aux=s["hpre"])
-    ops.colsum_bf16(dh, G.g(pre + "mlp.fc1.bias"))
+    if g2 is None:
+        g2 = ops.scale_cast_bf16(dx2, km, N, colsum=G.g(pre + "mlp.fc2.bias"))
+    dh = _linear_bwd(g2, s["a"], d["fc2_w"], G.g(pre + "mlp.fc2.weight"), T, C, hid, dgrad_mode=L.EPI_BF16_DGELU, aux=s["hpre"],
+                     colsum=G.g(pre + "mlp.fc1.bias"))
     dy2 = _linear_bwd(dh, s["y2"], d["fc1_w"], G.g(pre + "mlp.fc1.weight"), T, hid, C)
-    dx1 = ops.layernorm_bwd(dy2, s["x1"], s["mean2"], s["rstd2"], d["norm2_w"], None, dx2, G.g(pre + "norm2.weight"), G.g(pre + "norm2.bias"))
-    # ---- attention branch ([V]:508)
-    g1 = ops.scale_cast_bf16(dx1, ka, N, colsum=G.g(pre + "attn.proj.bias"))
+    # ---- attention branch ([V]:508): its cotangent bf16(keep_attn * dx1) and the proj bias gradient come out of the LN backward
+    dx1, g1 = ops.layernorm_bwd(dy2, s["x1"], s["mean2"], s["rstd2"], d["norm2_w"], None, dx2, G.g(pre + "norm2.weight"),
+                                G.g(pre + "norm2.bias"), cast=(ka, N, G.g(pre + "attn.proj.bias")))
     do = _linear_bwd(g1, s["o"], d["proj_w"], G.g(pre + "attn.proj.weight"), T, C, C)
     if d["window"]:
         dqkv, dparams = ops.rvsa_attn_bwd(s["qkv"], s["params"], d["rel_h"], d["rel_w"], d["table"], s["lse"], do,
@@ -82,8 +87,11 @@ def _block_backward(i, d, s, dx2, G, B, gh, gw, nH, keep):
         ops.rvsa_sampling_bwd(dparams, s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],
                               G.g(a + "offsets.2.weight"), G.g(a + "offsets.2.bias"), G.g(a + "scales.2.weight"), G.g(a + "scales.2.bias"),
                               G.g(a + "angles.2.weight"), G.g(a + "angles.2.bias"), dy1, B, gh, gw, nH)
-    dx0 = ops.layernorm_bwd(dy1, s["x0"], s["mean1"], s["rstd1"], d["norm1_w"], None, dx1, G.g(pre + "norm1.weight"), G.g(pre + "norm1.bias"))
-    return dx0
+    if nxt is None:
+        dx0 = ops.layernorm_bwd(dy1, s["x0"], s["mean1"], s["rstd1"], d["norm1_w"], None, dx1, G.g(pre + "norm1.weight"), G.g(pre + "norm1.bias"))
+        return dx0, None
+    return ops.layernorm_bwd(dy1, s["x0"], s["mean1"], s["rstd1"], d["norm1_w"], None, dx1, G.g(pre + "norm1.weight"),
+                             G.g(pre + "norm1.bias"), cast=(nxt[0], N, nxt[1]))
 
 
 def _convt_grads(G, wname, bname, dWp, colsum4):
@@ -164,8 +172,10 @@ def backward_impl(m, x, S, grad_outs, grad_store=None, after_block=None):
     else:
         taps = {blk: k for k, blk in enumerate(m.out_indices)}
 
+    g16 = None                            # bf16(keep_mlp * dx) of the block about to be processed, when already emitted
+    tapped = lambda j: j in taps and grad_outs[taps[j]] is not None
     for i in range(W.depth - 1, -1, -1):
-        if i in taps and grad_outs[taps[i]] is not None:
+        if tapped(i):
             if dx is None:
                 dx = torch.zeros(T, C, device=dev, dtype=F32)
             _fpn_tap_backward(m, W, S, taps[i], grad_outs[taps[i]], dx, G, B, gh, gw)
@@ -176,7 +186,11 @@ def backward_impl(m, x, S, grad_outs, grad_store=None, after_block=None):
             ka = keep[i, 0] if keep is not None else None
             km = keep[i, 1] if keep is not None else None
             _, s = engine._block_forward(W.blocks[i], s["x0"], B, gh, gw, nH, ka, km, save=True)
-        dx = _block_backward(i, W.blocks[i], s, dx, G, B, gh, gw, nH, keep)
+        # the block below gets its MLP-branch cotangent from this block's last kernel unless a pyramid tap still adds into dx
+        nxt = None
+        if i > 0 and not tapped(i - 1):
+            nxt = (keep[i - 1, 1] if keep is not None else None, G.g(f"blocks.{i - 1}.mlp.fc2.bias"))
+        dx, g16 = _block_backward(i, W.blocks[i], s, dx, g16, G, B, gh, gw, nH, keep, nxt)
         S["blocks"][i] = None             # release activations as we go
         if after_block is not None:
             after_block(i)

@@ -21,10 +21,11 @@ def _chk(t, dtype, name):
 
 
 def gemm(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=None, out2=None, aux=None, row_scale=None,
-         rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None, ps=None, force_bn=0):
+         rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None, ps=None, force_bn=0, colsum=None):
     """acc[m,n] = sum_k A[m,k] B[n,k] with fused epilogue; see include/mtp_b200.h."""
     ep = L.Epilogue()
     ep.mode = mode
+    ep.colsum = _p(colsum)
     ep.ldo = int(ldo if ldo is not None else out.shape[-1])
     ep.bias, ep.out, ep.out2, ep.aux, ep.row_scale = _p(bias), _p(out), _p(out2), _p(aux), _p(row_scale)
     ep.rows_per_group, ep.pos_rows, ep.accumulate = int(rows_per_group), int(pos_rows), int(bool(accumulate))
@@ -38,9 +39,10 @@ def gemm(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=No
 
 
 def _desc(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=None, out2=None, aux=None, row_scale=None,
-          rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None):
+          rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None, colsum=None):
     ep = L.Epilogue()
     ep.mode = mode
+    ep.colsum = _p(colsum)
     ep.ldo = int(ldo if ldo is not None else out.shape[-1])
     ep.bias, ep.out, ep.out2, ep.aux, ep.row_scale = _p(bias), _p(out), _p(out2), _p(aux), _p(row_scale)
     ep.rows_per_group, ep.pos_rows, ep.accumulate = int(rows_per_group), int(pos_rows), int(bool(accumulate))
@@ -69,13 +71,19 @@ def layernorm_fwd(x, gamma, beta, eps=1e-6, gelu=False, save_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, beta, dres, dgamma, dbeta, gelu=False):
+def layernorm_bwd(dy, x, mean, rstd, gamma, beta, dres, dgamma, dbeta, gelu=False, cast=None):
+    """``cast=(row_scale|None, rows_per_group, colsum|None)``: also return bf16(row_scale * dx) (+ its column sums into colsum)."""
     rows, C = x.shape
     dx = torch.empty(rows, C, device=x.device, dtype=x.dtype)
+    g16 = None
+    sc, rpg, cs = (None, 0, None)
+    if cast is not None:
+        sc, rpg, cs = cast
+        g16 = torch.empty(rows, C, device=x.device, dtype=BF16)
     L.call("mtp_layernorm_bwd", dy.data_ptr(), x.data_ptr(), int(x.dtype == BF16), mean.data_ptr(), rstd.data_ptr(),
            gamma.data_ptr(), _p(beta), _p(dres), dx.data_ptr(), int(dx.dtype == BF16), dgamma.data_ptr(), dbeta.data_ptr(),
-           rows, C, int(gelu), _stream())
-    return dx
+           _p(sc), int(rpg), _p(g16), _p(cs), rows, C, int(gelu), _stream())
+    return dx if cast is None else (dx, g16)
 
 
 def scale_cast_bf16(x, row_scale=None, rows_per_group=0, colsum=None):

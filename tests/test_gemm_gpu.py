@@ -158,3 +158,21 @@ def test_grouped_dual_launch_matches_separate():
         ref_dW = dy.float().t() @ x.float()
         assert ((dx.float() - ref_dx).abs() <= 8e-3 * ref_dx.abs() + 1e-2).all(), force
         assert (dW - ref_dW).norm().item() / ref_dW.norm().item() < 1e-5, force
+
+
+@pytest.mark.parametrize("bn", [0, 64, 192, 1256])
+def test_epilogue_column_sums(bn):
+    """colsum of the BF16 / BF16_DGELU epilogues = column sums of the stored bf16 output (bias gradient of the Linear below)."""
+    from mtp_b200 import ops, _lib as L
+    M, N, K = 1568, 1096, 264          # ragged M (12.25 tiles) and N
+    A, Bm = _mk((M, K), seed=31), _mk((K, N), 0.1, seed=32)
+    h = _mk((M, N), seed=33)
+    for mode, aux in ((L.EPI_BF16, None), (L.EPI_BF16_DGELU, h)):
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        cs = torch.zeros(N, device="cuda")
+        ops.gemm(A, Bm, M, N, K, out, b_mn=True, mode=mode, aux=aux, colsum=cs, force_bn=bn)
+        ref = out.float().sum(0)
+        assert (cs - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+        out2 = torch.empty_like(out)
+        ops.gemm(A, Bm, M, N, K, out2, b_mn=True, mode=mode, aux=aux, force_bn=bn)
+        assert torch.equal(out, out2)

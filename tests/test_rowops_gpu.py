@@ -69,3 +69,30 @@ def test_casts_and_colsums():
     acc = torch.ones(rows, C, device="cuda")
     ops.add_bf16_into_f32(z, acc)
     assert torch.equal(acc, 1 + z.float())
+
+
+@pytest.mark.parametrize("rows", [37, 1568, 6272])
+def test_layernorm_bwd_fused_cast_matches_scale_cast(rows):
+    """The cast/colsum outputs of mtp_layernorm_bwd equal a separate mtp_scale_cast_bf16 of its fp32 result."""
+    from mtp_b200 import ops
+    torch.manual_seed(5)
+    C, ntok = 1024, 196 if rows % 196 == 0 else 37
+    x = torch.randn(rows, C, device="cuda")
+    g = torch.randn(C, device="cuda") * 0.2 + 1
+    _, mean, rstd = ops.layernorm_fwd(x, g, torch.zeros_like(g))
+    dy = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
+    dres = torch.randn(rows, C, device="cuda")
+    keep = (torch.rand(rows // ntok, device="cuda") > 0.3).float() / 0.7
+    dg, db, cs = (torch.zeros(C, device="cuda") for _ in range(3))
+    dx, g16 = ops.layernorm_bwd(dy, x, mean, rstd, g, None, dres, dg, db, cast=(keep, ntok, cs))
+    dg2, db2, cs2 = (torch.zeros(C, device="cuda") for _ in range(3))
+    dx2 = ops.layernorm_bwd(dy, x, mean, rstd, g, None, dres, dg2, db2)
+    ref16 = ops.scale_cast_bf16(dx2, keep, ntok, cs2)
+    assert torch.equal(dx, dx2)
+    assert torch.equal(g16, ref16)
+    assert (dg - dg2).abs().max().item() <= 1e-4 * dg2.abs().max().item()
+    assert (cs - cs2).abs().max().item() <= 1e-4 * max(1.0, cs2.abs().max().item())
+    # without a row scale
+    cs3 = torch.zeros(C, device="cuda")
+    _, g16b = ops.layernorm_bwd(dy, x, mean, rstd, g, None, dres, dg, db, cast=(None, 0, cs3))
+    assert torch.equal(g16b, dx2.to(torch.bfloat16))
