@@ -1,12 +1,15 @@
 // RVSA window attention backward on tcgen05 tensor cores (autograd of attn_window_tc.cu; [V]:372-428).
 //
-// Same CTA shape as the forward: two (window, head) problems stacked on the 128 rows of one UMMA tile.
+// Same tile shape as the forward: two (window, head) problems stacked on the 128 rows of one UMMA tile.  256 threads: thread
+// `row` (0..127) owns accumulator row `row`; its helper `row + 128` (same TMEM lane quarter) takes the second half of the
+// row's columns in the phases that split (rel-pos terms, dq, TMEM read-out) and joins the cooperative phases.
 //   gather : q, dO rows and the bilinearly blended k~, v~ rows -> bf16 swizzled tiles
 //   MMA 1  : S  = Q K~^T , dP = dO V~^T                              (M = N = 128, K = 64)
 //   rows   : thread r: P = exp(S - lse), D = sum P dP, dS = P (dP - D); P and dS written block-diagonally (bf16);
 //            row sums of dS per key row / key column (rel-pos), bias-table partials via shared-memory atomics
 //   MMA 2  : dQ = dS K~ ,  dK~ = dS^T Q ,  dV~ = P^T dO              (M = 128, N = 64, K = 128; transposes via MN-major A)
-//   tail   : thread r: dq row (+ rel-pos terms) -> dqkv; its dk~ / dv~ row scattered through the 4 bilinear taps with
+//   tail   : dq rows (+ rel-pos terms) -> dqkv; dk~ / dv~ rows are staged TMEM -> smem, then 8 lanes per sample row (16 B of
+//            k and of v each, all 4 taps' loads in flight at once) scatter them through the bilinear taps with coalesced
 //            red.global.add.v4.f32 into the fp32 scratch; tap dot-products -> d(coords) -> d(ox, oy, sx, sy, theta)
 // Partials for rel_pos_h/w are written per CTA (both heads summed), bias-table partials per (window, head).
 #include "common.h"
@@ -16,10 +19,10 @@
 
 namespace mtp {
 
-constexpr int WB_THREADS = 128;
+constexpr int WB_THREADS = 256;
 constexpr int WB_TILE = 128 * 128;
-// Q | K~ | V~ | dO | P (2 atoms) | dS (2 atoms) | W (2 atoms) | rel tables | bias tables | coords | dSh,dSw | red | mbar | slot
-constexpr int WB_SMEM = 10 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 2 * 128 * 8 + 64) * 4 + 64;
+// Q | K~ | V~ | dO | P (2 atoms) | dS (2 atoms) | W (2 atoms) | rel tables | bias tables | coords | dSh,dSw | rw | gxy | red | mbar | slot
+constexpr int WB_SMEM = 10 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 3 * 128 * 8 + 2 * 128 + 64) * 4 + 64;
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -49,7 +52,9 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   float* cpy = cpx + 98;
   float* dSh = cpy + 98;                      // [128][8]
   float* dSw = dSh + 128 * 8;
-  float* red = dSw + 128 * 8;                 // [64]
+  float* rwS = dSw + 128 * 8;                 // [128][8] rel-pos column terms computed by the helper threads
+  float* gxy = rwS + 128 * 8;                 // [128][2] d(sample coords)
+  float* red = gxy + 2 * 128;                 // [64]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
@@ -68,8 +73,13 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     mbar_init(mbar, 1);
     fence_barrier_init();
   }
-  smem_zero(Qs, 4 * WB_TILE, tid, WB_THREADS);
-  smem_zero(Wt + WB_TILE, WB_TILE, tid, WB_THREADS);
+  // padding rows (49..63 of each problem) of the four operand tiles; every other row is written by the gather.  The second
+  // atom of W is left as is: it only feeds rows 64..127 of the d(rel table) product, which nobody reads.
+  for (int i = tid; i < 4 * 30 * 8; i += WB_THREADS) {
+    const int tile = i / 240, rr = (i % 240) >> 3, c = i & 7;
+    const int row = rr < 15 ? NTOK + rr : 64 + NTOK + (rr - 15);
+    *reinterpret_cast<uint4*>(Qs + tile * WB_TILE + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
+  }
   for (int i = tid; i < 2 * 13 * 64; i += WB_THREADS) relt[i] = i < 13 * 64 ? rel_h[i] : rel_w[i - 13 * 64];
   for (int i = tid; i < 2 * 169; i += WB_THREADS) tabs[i] = bias_table[(i % 169) * g.nH + 2 * hp + i / 169];
   if (tid < 98) {
@@ -98,6 +108,9 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       const size_t t = (size_t)(b * g.h + y) * g.w + x;
       *reinterpret_cast<uint4*>(Qs + soff) = *reinterpret_cast<const uint4*>(qkv + t * C3 + head * HD + c * 8);
       *reinterpret_cast<uint4*>(Gs + soff) = *reinterpret_cast<const uint4*>(dout + t * C + head * HD + c * 8);
+    } else {
+      *reinterpret_cast<uint4*>(Qs + soff) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Gs + soff) = make_uint4(0, 0, 0, 0);
     }
     const float px = cpx[i], py = cpy[i];
     const float fx0 = floorf(px), fy0 = floorf(py);
@@ -146,30 +159,43 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     }
     __syncwarp();
   }
-  const int p = tid >> 6, q = tid & 63;
+  const int row = tid & 127;
+  const bool helper = tid >= 128;
+  const int p = row >> 6, q = row & 63;
   const bool qvalid = q < NTOK;
   const int qy = q / WS, qx = q % WS;
   const int head = 2 * hp + p;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // TMEM lane quarter of this thread's row
+  // rel-pos terms of the row: the owner computes the height terms, its helper the width terms (handed over through smem)
   float rh[WS], rw[WS];
 #pragma unroll
   for (int k = 0; k < WS; ++k) { rh[k] = 0.f; rw[k] = 0.f; }
   if (qvalid) {
+    const float* tbase = relt + (helper ? 13 * 64 : 0);
+    const int qq = helper ? qx : qy;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(Qs + tile_chunk_off(tid, c));
+      const uint4 u = *reinterpret_cast<const uint4*>(Qs + tile_chunk_off(row, c));
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
       float qv[8];
 #pragma unroll
       for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
 #pragma unroll
       for (int k = 0; k < WS; ++k) {
-        const float4* th = reinterpret_cast<const float4*>(relt + (qy - k + WS - 1) * HD + c * 8);
-        const float4* tw = reinterpret_cast<const float4*>(relt + 13 * 64 + (qx - k + WS - 1) * HD + c * 8);
-        const float4 h0 = th[0], h1 = th[1], w0 = tw[0], w1 = tw[1];
+        const float4* th = reinterpret_cast<const float4*>(tbase + (qq - k + WS - 1) * HD + c * 8);
+        const float4 h0 = th[0], h1 = th[1];
         rh[k] += qv[0] * h0.x + qv[1] * h0.y + qv[2] * h0.z + qv[3] * h0.w + qv[4] * h1.x + qv[5] * h1.y + qv[6] * h1.z + qv[7] * h1.w;
-        rw[k] += qv[0] * w0.x + qv[1] * w0.y + qv[2] * w0.z + qv[3] * w0.w + qv[4] * w1.x + qv[5] * w1.y + qv[6] * w1.z + qv[7] * w1.w;
       }
     }
+  }
+  if (helper) {
+#pragma unroll
+    for (int k = 0; k < WS; ++k) rwS[row * 8 + k] = rh[k];
+  }
+  __syncthreads();
+  if (!helper) {
+#pragma unroll
+    for (int k = 0; k < WS; ++k) rw[k] = rwS[row * 8 + k];
   }
   mbar_wait(mbar, 0);
   tc_fence_after();
@@ -178,9 +204,8 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   float sh[WS], sw[WS];
 #pragma unroll
   for (int k = 0; k < WS; ++k) { sh[k] = 0.f; sw[k] = 0.f; }
-  {
+  if (!helper) {
     uint32_t r0[32], r1[32];
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     tmem_ld_32x32(T_S + lane_base + 64 * p, r0);
     tmem_ld_32x32(T_S + lane_base + 64 * p + 32, r1);
     tmem_ld_wait();
@@ -208,14 +233,14 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       sw[j % WS] += ds[j];
     }
 #pragma unroll
-    for (int k = 0; k < WS; ++k) { dSh[tid * 8 + k] = sh[k]; dSw[tid * 8 + k] = sw[k]; }
+    for (int k = 0; k < WS; ++k) { dSh[row * 8 + k] = sh[k]; dSw[row * 8 + k] = sw[k]; }
     {   // row q of W: column r < 13 -> dSh[q][qy - r + 6], column 13 + r -> dSw[q][qx - r + 6] (0 when out of range)
       float wv[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
         float v = 0.f;
-        if (r < 13) { const int k = qy - r + WS - 1; if (qvalid && k >= 0 && k < WS) v = dSh[tid * 8 + k]; }
-        else if (r < 26) { const int k = qx - (r - 13) + WS - 1; if (qvalid && k >= 0 && k < WS) v = dSw[tid * 8 + k]; }
+        if (r < 13) { const int k = qy - r + WS - 1; if (qvalid && k >= 0 && k < WS) v = dSh[row * 8 + k]; }
+        else if (r < 26) { const int k = qx - (r - 13) + WS - 1; if (qvalid && k >= 0 && k < WS) v = dSw[row * 8 + k]; }
         wv[r] = v;
       }
 #pragma unroll
@@ -225,7 +250,7 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
           u.x = pack_bf16x2(wv[8 * c], wv[8 * c + 1]); u.y = pack_bf16x2(wv[8 * c + 2], wv[8 * c + 3]);
           u.z = pack_bf16x2(wv[8 * c + 4], wv[8 * c + 5]); u.w = pack_bf16x2(wv[8 * c + 6], wv[8 * c + 7]);
         }
-        *reinterpret_cast<uint4*>(Wt + tile_chunk_off(tid, c)) = u;
+        *reinterpret_cast<uint4*>(Wt + tile_chunk_off(row, c)) = u;
       }
     }
     uint8_t* p_mine = Pt + p * WB_TILE;
@@ -243,11 +268,11 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       }
       uint4 u;
       u.x = pack_bf16x2(vp[0], vp[1]); u.y = pack_bf16x2(vp[2], vp[3]); u.z = pack_bf16x2(vp[4], vp[5]); u.w = pack_bf16x2(vp[6], vp[7]);
-      *reinterpret_cast<uint4*>(p_mine + tile_chunk_off(tid, c)) = u;
+      *reinterpret_cast<uint4*>(p_mine + tile_chunk_off(row, c)) = u;
       u.x = pack_bf16x2(vs[0], vs[1]); u.y = pack_bf16x2(vs[2], vs[3]); u.z = pack_bf16x2(vs[4], vs[5]); u.w = pack_bf16x2(vs[6], vs[7]);
-      *reinterpret_cast<uint4*>(s_mine + tile_chunk_off(tid, c)) = u;
-      *reinterpret_cast<uint4*>(p_other + tile_chunk_off(tid, c)) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(s_other + tile_chunk_off(tid, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(s_mine + tile_chunk_off(row, c)) = u;
+      *reinterpret_cast<uint4*>(p_other + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(s_other + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
     }
   }
   tc_fence_before();
@@ -280,7 +305,6 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   mbar_wait(mbar, 1);
   tc_fence_after();
 
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
   if (warp == 0) {          // rows 0..12 = d rel_pos_h partial, rows 13..25 = d rel_pos_w partial (both heads of this CTA)
     uint32_t r0[32], r1[32];
     tmem_ld_32x32(T_DR + lane_base, r0);
@@ -295,93 +319,131 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       }
     }
   }
+  const int hb = helper ? 1 : 0;          // which 32 of the row's 64 head dims this thread reads out of TMEM
   // ---- dq row -> dqkv
   {
     const int y = wy * WS + qy - g.pt, x = wx * WS + qx - g.pl;
     const bool tok_ok = qvalid && y >= 0 && y < g.h && x >= 0 && x < g.w;
+    uint32_t r0[32];
+    tmem_ld_32x32(T_DQ + lane_base + 32 * hb, r0);
+    tmem_ld_wait();
+    if (tok_ok) {
+      float o[32];
 #pragma unroll
-    for (int hb = 0; hb < 2; ++hb) {
-      uint32_t r0[32];
-      tmem_ld_32x32(T_DQ + lane_base + 32 * hb, r0);
-      tmem_ld_wait();
-      if (tok_ok) {
-        float o[32];
+      for (int e = 0; e < 32; ++e) o[e] = scale * __uint_as_float(r0[e]);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[e] = scale * __uint_as_float(r0[e]);
+      for (int k = 0; k < WS; ++k) {
+        const float shk = dSh[row * 8 + k], swk = dSw[row * 8 + k];
+        const float4* th = reinterpret_cast<const float4*>(relt + (qy - k + WS - 1) * HD + 32 * hb);
+        const float4* tw = reinterpret_cast<const float4*>(relt + 13 * 64 + (qx - k + WS - 1) * HD + 32 * hb);
 #pragma unroll
-        for (int k = 0; k < WS; ++k) {
-          const float* th = relt + (qy - k + WS - 1) * HD + 32 * hb;
-          const float* tw = relt + 13 * 64 + (qx - k + WS - 1) * HD + 32 * hb;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[e] += sh[k] * th[e] + sw[k] * tw[e];
+        for (int e = 0; e < 8; ++e) {
+          const float4 a = th[e], c = tw[e];
+          o[4 * e] += shk * a.x + swk * c.x;
+          o[4 * e + 1] += shk * a.y + swk * c.y;
+          o[4 * e + 2] += shk * a.z + swk * c.z;
+          o[4 * e + 3] += shk * a.w + swk * c.w;
         }
-        __nv_bfloat16* dst = dqkv + ((size_t)(b * g.h + y) * g.w + x) * C3 + head * HD + 32 * hb;
+      }
+      __nv_bfloat16* dst = dqkv + ((size_t)(b * g.h + y) * g.w + x) * C3 + head * HD + 32 * hb;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          u.x = pack_bf16x2(o[8 * c], o[8 * c + 1]); u.y = pack_bf16x2(o[8 * c + 2], o[8 * c + 3]);
-          u.z = pack_bf16x2(o[8 * c + 4], o[8 * c + 5]); u.w = pack_bf16x2(o[8 * c + 6], o[8 * c + 7]);
-          *reinterpret_cast<uint4*>(dst + 8 * c) = u;
-        }
+      for (int c = 0; c < 4; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(o[8 * c], o[8 * c + 1]); u.y = pack_bf16x2(o[8 * c + 2], o[8 * c + 3]);
+        u.z = pack_bf16x2(o[8 * c + 4], o[8 * c + 5]); u.w = pack_bf16x2(o[8 * c + 6], o[8 * c + 7]);
+        *reinterpret_cast<uint4*>(dst + 8 * c) = u;
       }
     }
   }
 
-  // ---- scatter of this thread's dk~ / dv~ row (sample j = q of problem p) and its coordinate gradient
-  float gx = 0.f, gy = 0.f;
+  // ---- dk~ (scaled) / dv~ rows: TMEM -> fp32 staging over the dead operand tiles, 256 B per row, 16-byte chunk c of row r at
+  //      chunk (c & 8) | ((c ^ r) & 7) so that both the row-per-lane writes and the 8-lanes-per-row reads are conflict-free
+  uint8_t* DKs = Qs;                     // 32 KB (Q and K~ tiles)
+  uint8_t* DVs = Vs;                     // 32 KB (V~ and dO tiles)
   {
-    const float px = qvalid ? cpx[p * NTOK + q] : 0.f, py = qvalid ? cpy[p * NTOK + q] : 0.f;
-    const float fx0 = floorf(px), fy0 = floorf(py);
-    const float ax = px - fx0, ay = py - fy0;
-    const int x0 = (int)fx0 - g.pl, y0 = (int)fy0 - g.pt;
-    const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + head * HD;
-    float* dk_b = dkv + (size_t)b * g.h * g.w * 2 * C + head * HD;
-    float tapdot[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t rk[32], rv[32];
+    tmem_ld_32x32(T_DK + lane_base + 32 * hb, rk);
+    tmem_ld_32x32(T_DV + lane_base + 32 * hb, rv);
+    tmem_ld_wait();
 #pragma unroll
-    for (int hb = 0; hb < 2; ++hb) {
-      uint32_t rk[32], rv[32];
-      tmem_ld_32x32(T_DK + lane_base + 32 * hb, rk);
-      tmem_ld_32x32(T_DV + lane_base + 32 * hb, rv);
-      tmem_ld_wait();
-      if (qvalid) {
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t off = (uint32_t)row * 256u + (uint32_t)(((8 * hb) | ((c ^ row) & 7)) << 4);
+      *reinterpret_cast<float4*>(DKs + off) = make_float4(scale * __uint_as_float(rk[4 * c]), scale * __uint_as_float(rk[4 * c + 1]),
+                                                          scale * __uint_as_float(rk[4 * c + 2]), scale * __uint_as_float(rk[4 * c + 3]));
+      *reinterpret_cast<float4*>(DVs + off) = make_float4(__uint_as_float(rv[4 * c]), __uint_as_float(rv[4 * c + 1]),
+                                                          __uint_as_float(rv[4 * c + 2]), __uint_as_float(rv[4 * c + 3]));
+    }
+  }
+  __syncthreads();
+
+  // ---- scatter through the bilinear taps + coordinate gradients: 8 lanes per sample row; lane c8 owns head dims
+  //      [4 c8, 4 c8 + 4) and [32 + 4 c8, 32 + 4 c8 + 4), so every warp-wide access covers whole 128-byte lines
+  {
+    const int c8 = tid & 7;
+    constexpr int ROWS_PER_PASS = WB_THREADS / 8;
+#pragma unroll 1
+    for (int pass = 0; pass < (2 * NTOK + ROWS_PER_PASS - 1) / ROWS_PER_PASS; ++pass) {
+      const int i = pass * ROWS_PER_PASS + (tid >> 3);
+      const bool valid = i < 2 * NTOK;
+      const int ii = valid ? i : 0;
+      const int pp = ii / NTOK, j = ii % NTOK, r = 64 * pp + j, hd = 2 * hp + pp;
+      const float px = cpx[ii], py = cpy[ii];
+      const float fx0 = floorf(px), fy0 = floorf(py);
+      const float ax = px - fx0, ay = py - fy0;
+      const int x0 = (int)fx0 - g.pl, y0 = (int)fy0 - g.pt;
+      const uint32_t offA = (uint32_t)r * 256u + (uint32_t)(((c8 ^ r) & 7) << 4), offB = offA + 128u;
+      const float4 gkA = *reinterpret_cast<const float4*>(DKs + offA), gkB = *reinterpret_cast<const float4*>(DKs + offB);
+      const float4 gvA = *reinterpret_cast<const float4*>(DVs + offA), gvB = *reinterpret_cast<const float4*>(DVs + offB);
+      const __nv_bfloat16* qkv_b = qkv + (size_t)b * g.h * g.w * C3 + hd * HD + 4 * c8;
+      float* dk_b = dkv + (size_t)b * g.h * g.w * 2 * C + hd * HD + 4 * c8;
+      uint2 kA[4], kB[4], vA[4], vB[4];
+      bool ok[4];
+      size_t pix[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+      for (int t = 0; t < 4; ++t) {
+        const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+        ok[t] = valid && xx >= 0 && xx < g.w && yy >= 0 && yy < g.h;
+        pix[t] = ok[t] ? (size_t)(yy * g.w + xx) : 0;
+        const __nv_bfloat16* src = qkv_b + pix[t] * C3;
+        kA[t] = *reinterpret_cast<const uint2*>(src + C);
+        kB[t] = *reinterpret_cast<const uint2*>(src + C + 32);
+        vA[t] = *reinterpret_cast<const uint2*>(src + 2 * C);
+        vB[t] = *reinterpret_cast<const uint2*>(src + 2 * C + 32);
+      }
+      float td[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 a0 = unpack_bf16x2(kA[t].x), a1 = unpack_bf16x2(kA[t].y), b0 = unpack_bf16x2(kB[t].x), b1 = unpack_bf16x2(kB[t].y);
+        const float2 c0 = unpack_bf16x2(vA[t].x), c1 = unpack_bf16x2(vA[t].y), d0 = unpack_bf16x2(vB[t].x), d1 = unpack_bf16x2(vB[t].y);
+        float d = gkA.x * a0.x + gkA.y * a0.y + gkA.z * a1.x + gkA.w * a1.y + gkB.x * b0.x + gkB.y * b0.y + gkB.z * b1.x + gkB.w * b1.y;
+        d += gvA.x * c0.x + gvA.y * c0.y + gvA.z * c1.x + gvA.w * c1.y + gvB.x * d0.x + gvB.y * d0.y + gvB.z * d1.x + gvB.w * d1.y;
+        td[t] = ok[t] ? d : 0.f;
+        if (ok[t]) {
           const float wgt = ((t & 1) ? ax : 1.f - ax) * ((t >> 1) ? ay : 1.f - ay);
-          if (xx >= 0 && xx < g.w && yy >= 0 && yy < g.h) {
-            const size_t pix = (size_t)(yy * g.w + xx);
-            const __nv_bfloat16* src = qkv_b + pix * C3 + 32 * hb;
-            float* dst = dk_b + pix * 2 * C + 32 * hb;
-            float td = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 ku = *reinterpret_cast<const uint4*>(src + C + 8 * c);
-              const uint4 vu = *reinterpret_cast<const uint4*>(src + 2 * C + 8 * c);
-              const uint32_t kw4[4] = {ku.x, ku.y, ku.z, ku.w}, vw4[4] = {vu.x, vu.y, vu.z, vu.w};
-              float gk[8], gv[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) { gk[e] = scale * __uint_as_float(rk[8 * c + e]); gv[e] = __uint_as_float(rv[8 * c + e]); }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 kf = unpack_bf16x2(kw4[e]), vf = unpack_bf16x2(vw4[e]);
-                td += gk[2 * e] * kf.x + gk[2 * e + 1] * kf.y + gv[2 * e] * vf.x + gv[2 * e + 1] * vf.y;
-              }
-              red_add_f32x4(dst + 8 * c, wgt * gk[0], wgt * gk[1], wgt * gk[2], wgt * gk[3]);
-              red_add_f32x4(dst + 8 * c + 4, wgt * gk[4], wgt * gk[5], wgt * gk[6], wgt * gk[7]);
-              red_add_f32x4(dst + C + 8 * c, wgt * gv[0], wgt * gv[1], wgt * gv[2], wgt * gv[3]);
-              red_add_f32x4(dst + C + 8 * c + 4, wgt * gv[4], wgt * gv[5], wgt * gv[6], wgt * gv[7]);
-            }
-            tapdot[t] += td;
-          }
+          float* dst = dk_b + pix[t] * 2 * C;
+          red_add_f32x4(dst, wgt * gkA.x, wgt * gkA.y, wgt * gkA.z, wgt * gkA.w);
+          red_add_f32x4(dst + 32, wgt * gkB.x, wgt * gkB.y, wgt * gkB.z, wgt * gkB.w);
+          red_add_f32x4(dst + C, wgt * gvA.x, wgt * gvA.y, wgt * gvA.z, wgt * gvA.w);
+          red_add_f32x4(dst + C + 32, wgt * gvB.x, wgt * gvB.y, wgt * gvB.z, wgt * gvB.w);
         }
       }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        td[t] += __shfl_xor_sync(0xffffffffu, td[t], 1);
+        td[t] += __shfl_xor_sync(0xffffffffu, td[t], 2);
+        td[t] += __shfl_xor_sync(0xffffffffu, td[t], 4);
+      }
+      if (c8 == 0 && valid) {
+        gxy[2 * r] = (1.f - ay) * (td[1] - td[0]) + ay * (td[3] - td[2]);
+        gxy[2 * r + 1] = (1.f - ax) * (td[2] - td[0]) + ax * (td[3] - td[1]);
+      }
     }
-    gx = (1.f - ay) * (tapdot[1] - tapdot[0]) + ay * (tapdot[3] - tapdot[2]);
-    gy = (1.f - ax) * (tapdot[2] - tapdot[0]) + ax * (tapdot[3] - tapdot[1]);
   }
+  __syncthreads();
+  const float gx = (qvalid && !helper) ? gxy[2 * row] : 0.f, gy = (qvalid && !helper) ? gxy[2 * row + 1] : 0.f;
   // ---- chain to (ox, oy, sx, sy, theta) and reduce over the 49 samples of each problem (2 warps per problem)
   float v5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (qvalid) {
+  if (qvalid && !helper) {
     const float* prm = params + ((size_t)bw * g.nH + head) * 8;
     const float inv_w = 2.0f / (float)(g.Wq - 1), inv_h = 2.0f / (float)(g.Hq - 1);
     const float bx = (float)(qx - WS / 2) * inv_w, by = (float)(qy - WS / 2) * inv_h;
@@ -398,7 +460,7 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const float r = warp_sum(v5[k]);
-    if (lane == 0) red[warp * 8 + k] = r;
+    if (lane == 0 && !helper) red[warp * 8 + k] = r;
   }
   tc_fence_before();
   __syncthreads();
