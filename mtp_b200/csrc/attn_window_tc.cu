@@ -1,7 +1,8 @@
 // RVSA window attention forward on tcgen05 tensor cores.                    [V]:372-428, SURVEY.md K5
 //
-// One CTA (128 threads) handles TWO (window, head) problems of the same window stacked on the 128 rows of one UMMA tile
-// (rows 0..48 = head 2p, rows 64..112 = head 2p+1; 15 padding rows each):
+// One CTA handles TWO (window, head) problems of the same window stacked on the 128 rows of one UMMA tile (rows 0..48 = head 2p,
+// rows 64..112 = head 2p+1; 15 padding rows each).  256 threads: thread `row` owns accumulator row `row`, its helper `row + 128`
+// (same TMEM lane quarter) computes the width rel-pos terms, stores the second half of the output row and joins the gather:
 //   gather : threads blend the 4 bilinear taps of every sampled K / V row in fp32 and write bf16 rows straight into
 //            128B-swizzled shared-memory tiles (the layout the UMMA descriptors read) together with the Q rows
 //   S      : tcgen05.mma  S[128x128] = Q K~^T (K = 64) into TMEM; only the two diagonal 64x64 blocks are meaningful
@@ -16,10 +17,10 @@
 
 namespace mtp {
 
-constexpr int WTC_THREADS = 128;
+constexpr int WTC_THREADS = 256;
 constexpr int WTC_TILE = 128 * 128;                       // bytes of one 128-row tile
-// smem: Q | K~ | V~ | P (2 atoms) | rel_h,rel_w fp32 [2][13][64] | table [2][169] | coords [2][98] | mbar | tmem slot
-constexpr int WTC_SMEM = 5 * WTC_TILE + 2 * 13 * 64 * 4 + 2 * 169 * 4 + 2 * 98 * 4 + 64;
+// smem: Q | K~ | V~ | P (2 atoms) | rel_h,rel_w fp32 [2][13][64] | table [2][169] | coords [2][98] | rw [128][8] | mbar | tmem slot
+constexpr int WTC_SMEM = 5 * WTC_TILE + 2 * 13 * 64 * 4 + 2 * 169 * 4 + 2 * 98 * 4 + 128 * 8 * 4 + 64;
 
 __global__ void __launch_bounds__(WTC_THREADS)
 rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
@@ -35,7 +36,8 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   float* tabs = relt + 2 * 13 * 64;                       // [2 heads][169]
   float* cpx = tabs + 2 * 169;                            // [98]
   float* cpy = cpx + 98;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(cpy + 98);
+  float* rwS = cpy + 98;                                  // [128][8]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(rwS + 128 * 8);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -52,7 +54,11 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     mbar_init(mbar, 1);
     fence_barrier_init();
   }
-  smem_zero(Qs, 3 * WTC_TILE, tid, WTC_THREADS);          // padding rows of Q / K~ / V~ must be zero
+  for (int i = tid; i < 3 * 30 * 8; i += WTC_THREADS) {   // padding rows of Q / K~ / V~ must be zero (the gather writes the rest)
+    const int tile = i / 240, rr = (i % 240) >> 3, c = i & 7;
+    const int row = rr < 15 ? NTOK + rr : 64 + NTOK + (rr - 15);
+    *reinterpret_cast<uint4*>(Qs + tile * WTC_TILE + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
+  }
   for (int i = tid; i < 2 * 13 * 64; i += WTC_THREADS) relt[i] = i < 13 * 64 ? rel_h[i] : rel_w[i - 13 * 64];
   for (int i = tid; i < 2 * 169; i += WTC_THREADS) tabs[i] = bias_table[(i % 169) * g.nH + 2 * hp + i / 169];
   if (tid < 98) {
@@ -77,6 +83,8 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     const int y = wy * WS + j / WS - g.pt, x = wx * WS + j % WS - g.pl;
     if (y >= 0 && y < g.h && x >= 0 && x < g.w)
       *reinterpret_cast<uint4*>(Qs + soff) = *reinterpret_cast<const uint4*>(qkv_b + (size_t)(y * g.w + x) * C3);
+    else
+      *reinterpret_cast<uint4*>(Qs + soff) = make_uint4(0, 0, 0, 0);
     const float px = cpx[i], py = cpy[i];
     const float fx0 = floorf(px), fy0 = floorf(py);
     const float ax = px - fx0, ay = py - fy0;
@@ -124,37 +132,49 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     __syncwarp();
   }
   // meanwhile: decomposed rel-pos terms of this thread's row (fp32, UNscaled q)
-  const int p = tid >> 6, q = tid & 63;
+  const int row = tid & 127;
+  const bool helper = tid >= 128;
+  const int p = row >> 6, q = row & 63;
   const bool qvalid = q < NTOK;
   const int qy = q / WS, qx = q % WS;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   float rh[WS], rw[WS];
 #pragma unroll
   for (int k = 0; k < WS; ++k) { rh[k] = 0.f; rw[k] = 0.f; }
-  if (qvalid) {
+  if (qvalid) {          // the owner computes the height terms, the helper the width terms
+    const float* tbase = relt + (helper ? 13 * 64 : 0);
+    const int qq = helper ? qx : qy;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(Qs + tile_chunk_off(tid, c));
+      const uint4 u = *reinterpret_cast<const uint4*>(Qs + tile_chunk_off(row, c));
       const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
       float qv[8];
 #pragma unroll
       for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
 #pragma unroll
       for (int k = 0; k < WS; ++k) {
-        const float4* th = reinterpret_cast<const float4*>(relt + (qy - k + WS - 1) * HD + c * 8);
-        const float4* tw = reinterpret_cast<const float4*>(relt + 13 * 64 + (qx - k + WS - 1) * HD + c * 8);
-        const float4 h0 = th[0], h1 = th[1], w0 = tw[0], w1 = tw[1];
+        const float4* th = reinterpret_cast<const float4*>(tbase + (qq - k + WS - 1) * HD + c * 8);
+        const float4 h0 = th[0], h1 = th[1];
         rh[k] += qv[0] * h0.x + qv[1] * h0.y + qv[2] * h0.z + qv[3] * h0.w + qv[4] * h1.x + qv[5] * h1.y + qv[6] * h1.z + qv[7] * h1.w;
-        rw[k] += qv[0] * w0.x + qv[1] * w0.y + qv[2] * w0.z + qv[3] * w0.w + qv[4] * w1.x + qv[5] * w1.y + qv[6] * w1.z + qv[7] * w1.w;
       }
     }
+  }
+  if (helper) {
+#pragma unroll
+    for (int k = 0; k < WS; ++k) rwS[row * 8 + k] = rh[k];
+  }
+  __syncthreads();
+  if (!helper) {
+#pragma unroll
+    for (int k = 0; k < WS; ++k) rw[k] = rwS[row * 8 + k];
   }
   mbar_wait(mbar, 0);
   tc_fence_after();
 
   // ---- softmax of this thread's row over its problem's 49 keys
-  {
+  if (!helper) {
     uint32_t r0[32], r1[32];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 64 * p;
+    const uint32_t taddr = tmem + lane_base + 64 * p;
     tmem_ld_32x32(taddr, r0);
     tmem_ld_32x32(taddr + 32, r1);
     tmem_ld_wait();
@@ -182,8 +202,8 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       for (int e = 0; e < 8; ++e) v[e] = (c * 8 + e < NTOK) ? s[(c * 8 + e < NTOK) ? c * 8 + e : 0] * inv : 0.f;
       uint4 u;
       u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(prow_mine + tile_chunk_off(tid, c)) = u;
-      *reinterpret_cast<uint4*>(prow_other + tile_chunk_off(tid, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(prow_mine + tile_chunk_off(row, c)) = u;
+      *reinterpret_cast<uint4*>(prow_other + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
     }
   }
   tc_fence_before();
@@ -202,14 +222,13 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   mbar_wait(mbar, 1);
   tc_fence_after();
   {
-    uint32_t r0[32], r1[32];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 128;
-    tmem_ld_32x32(taddr, r0);
-    tmem_ld_32x32(taddr + 32, r1);
+    const int hb = helper ? 1 : 0;          // owner stores head dims 0..31 of its row, the helper 32..63
+    uint32_t r0[32];
+    tmem_ld_32x32(tmem + lane_base + 128 + 32 * hb, r0);
     tmem_ld_wait();
     const int y = wy * WS + qy - g.pt, x = wx * WS + qx - g.pl;
     if (qvalid && y >= 0 && y < g.h && x >= 0 && x < g.w) {
-      __nv_bfloat16* dst = out + ((size_t)(b * g.h + y) * g.w + x) * C + (2 * hp + p) * HD;
+      __nv_bfloat16* dst = out + ((size_t)(b * g.h + y) * g.w + x) * C + (2 * hp + p) * HD + 32 * hb;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 u;
@@ -218,11 +237,6 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         u.z = pack_bf16x2(__uint_as_float(r0[8 * c + 4]), __uint_as_float(r0[8 * c + 5]));
         u.w = pack_bf16x2(__uint_as_float(r0[8 * c + 6]), __uint_as_float(r0[8 * c + 7]));
         *reinterpret_cast<uint4*>(dst + 8 * c) = u;
-        u.x = pack_bf16x2(__uint_as_float(r1[8 * c]), __uint_as_float(r1[8 * c + 1]));
-        u.y = pack_bf16x2(__uint_as_float(r1[8 * c + 2]), __uint_as_float(r1[8 * c + 3]));
-        u.z = pack_bf16x2(__uint_as_float(r1[8 * c + 4]), __uint_as_float(r1[8 * c + 5]));
-        u.w = pack_bf16x2(__uint_as_float(r1[8 * c + 6]), __uint_as_float(r1[8 * c + 7]));
-        *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
       }
     }
   }
