@@ -58,9 +58,35 @@ __device__ __forceinline__ void ft_rel_terms(const uint8_t* Qs, const float* rel
   }
 }
 
+// Grid side known at compile time (G = 14: the 224^2 headline case): the rel terms stay in registers and every key index of the
+// softmax / dS loops is a constant, so the per-element shared-memory traffic of the generic path disappears.
+template <int G>
+__device__ __forceinline__ void ft_rel_terms_fixed(const uint8_t* Qs, const float* relh_t, const float* relw_t, int row, int qy, int qx,
+                                                   float (&rh)[G], float (&rw)[G]) {
+#pragma unroll
+  for (int k = 0; k < G; ++k) { rh[k] = 0.f; rw[k] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(Qs + tile_chunk_off(row, c));
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+    float qv[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const float4* th = reinterpret_cast<const float4*>(relh_t + (qy - k + G - 1) * 64 + c * 8);
+      const float4* tw = reinterpret_cast<const float4*>(relw_t + (qx - k + G - 1) * 64 + c * 8);
+      const float4 h0 = th[0], h1 = th[1], w0 = tw[0], w1 = tw[1];
+      rh[k] += qv[0] * h0.x + qv[1] * h0.y + qv[2] * h0.z + qv[3] * h0.w + qv[4] * h1.x + qv[5] * h1.y + qv[6] * h1.z + qv[7] * h1.w;
+      rw[k] += qv[0] * w0.x + qv[1] * w0.y + qv[2] * w0.z + qv[3] * w0.w + qv[4] * w1.x + qv[5] * w1.y + qv[6] * w1.z + qv[7] * w1.w;
+    }
+  }
+}
+
 // ================================================================================================== forward
 constexpr int FTF_SMEM = FT_TILE /*Q*/ + 2 * 2 * FT_TILE /*K,V*/ + 4 * FT_TILE /*P*/ + (2 * FT_TAB + 2 * 128 * 17) * 4 + 64;
 
+template <int G>      // G > 0: gh == gw == G known at compile time (and rel-pos in use); G == 0: generic
 __global__ void __launch_bounds__(FT_THREADS)
 full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                         __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int gh, int gw, int C, int nH, int use_rel) {
@@ -117,14 +143,55 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     const int qy = qvalid ? q / gw : 0, qx = qvalid ? q % gw : 0;
     float* rh = rh_s + tid * 17;
     float* rw = rw_s + tid * 17;
-    if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
+    constexpr int GG = G > 0 ? G : 1;
+    float rhr[GG], rwr[GG];
+    if constexpr (G > 0) ft_rel_terms_fixed<G>(Qs, relh_t, relw_t, tid, qy, qx, rhr, rwr);
+    else if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
 
     const int n_chunks = (N + 31) / 32;
-    // pass 1: row maximum
     float m = -INFINITY;
+    float sum = 0.f;
+    if constexpr (G > 0) {
+      constexpr int NF = G * G, NCH = (NF + 31) / 32;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {          // pass 1: row maximum
+        uint32_t r[32];
+        tmem_ld_32x32(T_S + lane_base + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = c * 32 + e;
+          if (j < NF) m = fmaxf(m, __uint_as_float(r[e]) + rhr[j / G] + rwr[j % G]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {          // pass 2: exp, sum, P (bf16, unnormalised) -> smem
+        uint32_t r[32];
+        tmem_ld_32x32(T_S + lane_base + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = c * 32 + e;
+          float p = 0.f;
+          if (j < NF) p = qvalid ? __expf(scale * (__uint_as_float(r[e]) + rhr[j / G] + rwr[j % G] - m)) : 0.f;
+          pv[e] = p;
+          sum += p;
+        }
+        uint8_t* atom = Pt + (c >> 1) * FT_TILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 u;
+          u.x = pack_bf16x2(pv[8 * k], pv[8 * k + 1]); u.y = pack_bf16x2(pv[8 * k + 2], pv[8 * k + 3]);
+          u.z = pack_bf16x2(pv[8 * k + 4], pv[8 * k + 5]); u.w = pack_bf16x2(pv[8 * k + 6], pv[8 * k + 7]);
+          *reinterpret_cast<uint4*>(atom + tile_chunk_off(tid, (c & 1) * 4 + k)) = u;
+        }
+      }
+    } else {
+    // pass 1: row maximum
     {
       int jy = 0, jx = 0;
       for (int c = 0; c < n_chunks; ++c) {
@@ -144,7 +211,6 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       }
     }
     // pass 2: exp, sum, P (bf16, unnormalised) -> smem
-    float sum = 0.f;
     {
       int jy = 0, jx = 0;
       for (int c = 0; c < n_chunks; ++c) {
@@ -174,6 +240,7 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
           *reinterpret_cast<uint4*>(atom + tile_chunk_off(tid, (c & 1) * 4 + k)) = u;
         }
       }
+    }
     }
     tc_fence_before();
     fence_proxy_async_smem();
@@ -225,13 +292,17 @@ int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* re
                             int nH, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(full_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FTF_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(full_attn_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FTF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(full_attn_fwd_tc_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, FTF_SMEM);
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_fwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  (void)launch_k(full_attn_fwd_tc_kernel, B * nH, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
-                                                                reinterpret_cast<__nv_bfloat16*>(out), lse, gh * gw, gh, gw, C, nH,
-                                                                rel_h != nullptr);
+  if (gh == 14 && gw == 14 && rel_h != nullptr)
+    (void)launch_k(full_attn_fwd_tc_kernel<14>, B * nH, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
+                   reinterpret_cast<__nv_bfloat16*>(out), lse, gh * gw, gh, gw, C, nH, 1);
+  else
+    (void)launch_k(full_attn_fwd_tc_kernel<0>, B * nH, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
+                   reinterpret_cast<__nv_bfloat16*>(out), lse, gh * gw, gh, gw, C, nH, rel_h != nullptr);
   return check_launch("full_attn_fwd_tc_kernel");
 }
 
@@ -239,6 +310,7 @@ int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* re
 // smem: Q | dO | K (256 rows) | V (256 rows) | P (2 atoms) | dS (2 atoms) | tables | per-row rel terms | dSh, dSw | D, lse
 constexpr int FTB_SMEM = 2 * FT_TILE + 4 * FT_TILE + 4 * FT_TILE + (2 * FT_TAB + 4 * 128 * 17 + 2 * 128) * 4 + 64;
 
+template <int G>      // G > 0: gh == gw == G known at compile time (and rel-pos in use); G == 0: generic
 __global__ void __launch_bounds__(FT_THREADS)
 full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                         const float* __restrict__ lse, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
@@ -268,8 +340,9 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   const int C3 = 3 * C;
   const float scale = 0.125f;
   const __nv_bfloat16* base = qkv + (size_t)b * N * C3 + n * 64;
-  const int N16 = (N + 15) & ~15;
-  const int n_halves = (N + 127) / 128;
+  const int N16 = G > 0 ? ((G * G + 15) & ~15) : ((N + 15) & ~15);
+  const int n_halves = G > 0 ? (G * G + 127) / 128 : (N + 127) / 128;
+  constexpr int GG = G > 0 ? G : 1;
 
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid == 32) { mbar_init(mbar, 1); fence_barrier_init(); }
@@ -323,11 +396,16 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     __syncthreads();
     float* rh = rh_s + tid * 17;
     float* rw = rw_s + tid * 17;
-    if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
+    float rhr[GG], rwr[GG], dShr[GG], dSwr[GG];
+#pragma unroll
+    for (int k = 0; k < GG; ++k) { dShr[k] = 0.f; dSwr[k] = 0.f; }
+    if constexpr (G > 0) ft_rel_terms_fixed<G>(Qs, relh_t, relw_t, tid, qy, qx, rhr, rwr);
+    else if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
     float dq[64];
 #pragma unroll
     for (int d = 0; d < 64; ++d) dq[d] = 0.f;
 
+#pragma unroll
     for (int h = 0; h < n_halves; ++h) {
       const int k0 = h * 128;
       const int nk16 = min(128, N16 - k0);                 // keys of this half, multiple of 16
@@ -347,6 +425,7 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         const float l = lse_s[tid], D = D_s[tid];
         int jy = k0 / gw, jx = k0 % gw;
         const int n_chunks = (nk16 + 31) / 32;
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
           float pv[32], dv[32];
           if (c < n_chunks) {
@@ -358,7 +437,15 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
             for (int e = 0; e < 32; ++e) {
               const int j = k0 + c * 32 + e;
               float p = 0.f, ds = 0.f;
-              if (j < N && c * 32 + e < nk16) {
+              if constexpr (G > 0) {
+                if (j < G * G) {          // j is a compile-time constant here (h, c, e unrolled)
+                  const float s = __uint_as_float(r0[e]) + rhr[(j / GG) % GG] + rwr[j % GG];
+                  p = qvalid ? __expf(scale * s - l) : 0.f;
+                  ds = p * (__uint_as_float(r1[e]) - D);
+                  dShr[(j / GG) % GG] += ds;
+                  dSwr[j % GG] += ds;
+                }
+              } else if (j < N && c * 32 + e < nk16) {
                 float s = __uint_as_float(r0[e]);
                 if (use_rel) s += rh[jy] + rw[jx];
                 p = qvalid ? __expf(scale * s - l) : 0.f;
@@ -417,9 +504,28 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       tc_fence_after();
     }
 
+    if constexpr (G > 0) {      // the W tile below reads the row sums with run-time indices: park them in shared memory
+#pragma unroll
+      for (int k = 0; k < G; ++k) { dSh[tid * 17 + k] = dShr[k]; dSw[tid * 17 + k] = dSwr[k]; }
+    }
     // dq = scale * (dS K + sum_k dSh[k] Rh[qy-k+gh-1] + sum_k dSw[k] Rw[qx-k+gw-1])
     if (qvalid) {
-      if (use_rel) {
+      if constexpr (G > 0) {
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          const float ch = dShr[k], cw = dSwr[k];
+          const float4* th = reinterpret_cast<const float4*>(relh_t + (qy - k + G - 1) * 64);
+          const float4* tw = reinterpret_cast<const float4*>(relw_t + (qx - k + G - 1) * 64);
+#pragma unroll
+          for (int d = 0; d < 16; ++d) {
+            const float4 a = th[d], c = tw[d];
+            dq[4 * d] += ch * a.x + cw * c.x;
+            dq[4 * d + 1] += ch * a.y + cw * c.y;
+            dq[4 * d + 2] += ch * a.z + cw * c.z;
+            dq[4 * d + 3] += ch * a.w + cw * c.w;
+          }
+        }
+      } else if (use_rel) {
         for (int k = 0; k < gh; ++k) {
           const float ch = dSh[tid * 17 + k];
           const float* th = relh_t + (qy - k + gh - 1) * 64;
@@ -539,11 +645,13 @@ int launch_full_attn_bwd_tc(const void* qkv, const float* rel_h, const float* re
                             void* dqkv, float* d_rel_h, float* d_rel_w, int B, int gh, int gw, int C, int nH, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(full_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FTB_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(full_attn_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FTB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(full_attn_bwd_tc_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, FTB_SMEM);
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_bwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  (void)launch_k(full_attn_bwd_tc_kernel, B * nH, FT_THREADS, FTB_SMEM, st, 
+  auto kern = (gh == 14 && gw == 14 && rel_h != nullptr) ? full_attn_bwd_tc_kernel<14> : full_attn_bwd_tc_kernel<0>;
+  (void)launch_k(kern, B * nH, FT_THREADS, FTB_SMEM, st,
       reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w, lse, reinterpret_cast<const __nv_bfloat16*>(out),
       reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dqkv), d_rel_h, d_rel_w, gh * gw, gh, gw, C, nH,
       rel_h != nullptr);
