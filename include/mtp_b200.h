@@ -163,7 +163,8 @@ int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, int B, int 
  * Attention backward (autograd of the forward entry points above; everything is recomputed from qkv + lse).
  * All parameter-gradient outputs (d_rel_pos_*, d_bias_table, dw_*, db_*) are ACCUMULATED into (+=).
  * mtp_rvsa_attn_bwd: dqkv_bf16 [T, 3C] is fully written (q slot directly; k|v slots from an fp32 scatter scratch);
- *   dparams [B*nWin, nH, 8] receives d(ox, oy, sx, sy, theta); workspace >= mtp_rvsa_bwd_workspace_bytes().
+ *   dparams [B*nWin, nH, 8] receives d(ox, oy, sx, sy, theta) (slots 5..7 zero); d_qkv_bias (optional, [3C]) += column sums
+ *   of dqkv (the qkv bias gradient, [V]:390); workspace >= mtp_rvsa_bwd_workspace_bytes().
  * mtp_rvsa_sampling_bwd: backward of the pooled 1x1-conv heads ([V]:228-243): accumulates the six conv gradients and
  *   adds the AvgPool-path gradient into dyn_bf16 [T, C] (the cotangent of the LN1 output);
  *   workspace >= mtp_rvsa_sampling_bwd_workspace_bytes().
@@ -172,8 +173,8 @@ int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, int B, int 
 size_t mtp_rvsa_bwd_workspace_bytes(int B, int h, int w, int C, int nH);
 int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,
                       const float* bias_table, const float* lse, const void* dout_bf16, void* dqkv_bf16, float* dparams,
-                      float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, void* workspace, int B, int h, int w, int C,
-                      int nH, mtp_stream_t stream);
+                      float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace, int B, int h,
+                      int w, int C, int nH, mtp_stream_t stream);
 size_t mtp_rvsa_sampling_bwd_workspace_bytes(int B, int h, int w, int C, int nH);
 int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, const float* w_off, const float* w_scale,
                           const float* w_angle, float* dw_off, float* db_off, float* dw_scale, float* db_scale, float* dw_angle,

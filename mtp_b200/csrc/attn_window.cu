@@ -16,28 +16,39 @@
 namespace mtp {
 
 // ------------------------------------------------------------------------------------------------ sampling params
-// (1) zero-padded 7x7 mean of the LN'd tokens: CTA = (image-window, 256-channel slab), thread = 4 channels
-__global__ void __launch_bounds__(64)
+// (1) zero-padded 7x7 mean of the LN'd tokens: CTA = (image-window, 256-channel slab); thread = (token group of 4, 4 channels):
+//     the <= 13 token loads of a thread are all in flight at once, the four groups combine through shared memory
+__global__ void __launch_bounds__(256)
 rvsa_pool_fwd_kernel(const __nv_bfloat16* __restrict__ yn, float* __restrict__ pooled, const RvsaGeom g) {
   MTP_PDL_ENTRY();
+  __shared__ float4 part[4][64];
   const int bw = blockIdx.x;
   const int b = bw / (g.nh * g.nw), win = bw % (g.nh * g.nw);
   const int wy = win / g.nw, wx = win % g.nw;
-  const int c = blockIdx.y * 256 + threadIdx.x * 4;
-  if (c >= g.C) return;
+  const int tg = threadIdx.x >> 6, cq = threadIdx.x & 63;
+  const int c = blockIdx.y * 256 + cq * 4;
   float4 s = make_float4(0, 0, 0, 0);
-#pragma unroll 7
-  for (int i = 0; i < WS * WS; ++i) {
-    const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
-    if (y >= 0 && y < g.h && x >= 0 && x < g.w) {
-      const uint2 u = *reinterpret_cast<const uint2*>(yn + ((size_t)(b * g.h + y) * g.w + x) * g.C + c);
-      const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y);
-      s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
+  if (c < g.C) {
+#pragma unroll
+    for (int k = 0; k < (WS * WS + 3) / 4; ++k) {
+      const int i = tg + 4 * k;
+      const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
+      if (i < WS * WS && y >= 0 && y < g.h && x >= 0 && x < g.w) {
+        const uint2 u = *reinterpret_cast<const uint2*>(yn + ((size_t)(b * g.h + y) * g.w + x) * g.C + c);
+        const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y);
+        s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
+      }
     }
   }
-  const float inv = 1.0f / (WS * WS);                    // zeros of the padding are part of the mean ([V]:347,354)
-  s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
-  *reinterpret_cast<float4*>(pooled + (size_t)bw * g.C + c) = s;
+  part[tg][cq] = s;
+  __syncthreads();
+  if (tg == 0 && c < g.C) {
+    const float4 p1 = part[1][cq], p2 = part[2][cq], p3 = part[3][cq];
+    const float inv = 1.0f / (WS * WS);                    // zeros of the padding are part of the mean ([V]:347,354)
+    s.x = (s.x + p1.x + p2.x + p3.x) * inv; s.y = (s.y + p1.y + p2.y + p3.y) * inv;
+    s.z = (s.z + p1.z + p2.z + p3.z) * inv; s.w = (s.w + p1.w + p2.w + p3.w) * inv;
+    *reinterpret_cast<float4*>(pooled + (size_t)bw * g.C + c) = s;
+  }
 }
 
 // (2) the three 1x1 convs on LeakyReLU(pooled): CTA = one of the 5nH output channels, its weight row kept in registers,
@@ -74,6 +85,7 @@ rvsa_heads_fwd_kernel(const float* __restrict__ pooled, const float* __restrict_
     }
     s = warp_sum(s) + bias;
     if (lane == 0) params[((size_t)bw * nH + n) * 8 + slot] = s / div;
+    if (slot == 4 && lane >= 1 && lane < 4) params[((size_t)bw * nH + n) * 8 + 4 + lane] = 0.f;      // unused slots 5..7
   }
 }
 
@@ -266,7 +278,7 @@ extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, co
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n_bw = B * g.nh * g.nw;
-  (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 64, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g);
+  (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g);
   int rc = check_launch("rvsa_pool_fwd_kernel");
   if (rc) return rc;
   (void)launch_k(rvsa_heads_fwd_kernel, 5 * nH, 256, 0, st, pooled, w_off, b_off, w_scale, b_scale, w_angle, b_angle, params, n_bw, g);

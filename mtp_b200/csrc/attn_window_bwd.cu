@@ -339,43 +339,80 @@ rvsa_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
     if (lane == 0) red[warp * 8 + k] = r;
   }
   __syncthreads();
-  if (tid < 5) dparams[((size_t)bw * g.nH + n) * 8 + tid] = red[tid] + red[8 + tid];
+  if (tid < 8) dparams[((size_t)bw * g.nH + n) * 8 + tid] = tid < 5 ? red[tid] + red[8 + tid] : 0.f;      // slots 5..7 unused
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
-// d_rel[2][13][64] += sum over CTAs ; d_table[169][nH] += sum over (image, window)
+// d_rel[2][13][64] += sum over CTAs ; d_table[169][nH] += sum over (image, window).
+// A warp owns 32 consecutive outputs (coalesced rows of the partial arrays) and one slice of the partials, all of its loads in
+// flight at once; the 8 warps of a CTA hold the 8 slices of the same outputs and combine through shared memory.
+constexpr int PR_SLICES = 8;
 __global__ void __launch_bounds__(256)
 rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __restrict__ part_table, float* __restrict__ d_rel_h,
                             float* __restrict__ d_rel_w, float* __restrict__ d_table, int n_rel_parts, int n_bw, int nH) {
   MTP_PDL_ENTRY();
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  __shared__ float red[PR_SLICES][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_rel = 2 * (2 * WS - 1) * HD;
-  if (i < n_rel) {
-    float s = 0.f;
-    for (int c = 0; c < n_rel_parts; ++c) s += part_rel[(size_t)c * n_rel + i];
-    if (i < n_rel / 2) d_rel_h[i] += s; else d_rel_w[i - n_rel / 2] += s;
-  } else if (i < n_rel + 169 * nH) {
-    const int e = i - n_rel, idx = e / nH, n = e % nH;
-    float s = 0.f;
-    for (int bw = 0; bw < n_bw; ++bw) s += part_table[((size_t)bw * nH + n) * 169 + idx];
-    d_table[idx * nH + n] += s;
+  const int rel_blocks = n_rel / 32;                       // 52
+  const int tab_blocks = (169 + 31) / 32;                  // per head
+  float s = 0.f;
+  float* dst = nullptr;
+  if ((int)blockIdx.x < rel_blocks) {
+    const int i = blockIdx.x * 32 + lane;
+    const int per = (n_rel_parts + PR_SLICES - 1) / PR_SLICES;
+    const int c0 = warp * per, c1 = min(n_rel_parts, c0 + per);
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) s += part_rel[(size_t)c * n_rel + i];
+    dst = i < n_rel / 2 ? d_rel_h + i : d_rel_w + (i - n_rel / 2);
+  } else {
+    const int e = blockIdx.x - rel_blocks;                 // (head, 32-wide displacement block)
+    const int n = e / tab_blocks, idx = (e % tab_blocks) * 32 + lane;
+    if (n < nH && idx < 169) {
+      const int per = (n_bw + PR_SLICES - 1) / PR_SLICES;
+      const int c0 = warp * per, c1 = min(n_bw, c0 + per);
+#pragma unroll 8
+      for (int bw = c0; bw < c1; ++bw) s += part_table[((size_t)bw * nH + n) * 169 + idx];
+      dst = d_table + idx * nH + n;
+    }
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && dst != nullptr) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < PR_SLICES; ++w) t += red[w][lane];
+    *dst += t;
   }
 }
 
-// dqkv[t, C + c] = bf16(dkv[t, c]) for c in [0, 2C)
+// dqkv[t, C + c] = bf16(dkv[t, c]) for c in [0, 2C); optionally colsum[0, 3C) += column sums of the finished bf16 dqkv (the qkv
+// bias gradient), reading the dq part the attention kernel wrote.  Thread = 4 consecutive columns, CTA = a band of rows.
 __global__ void __launch_bounds__(256)
-rvsa_kv_finalize_kernel(const float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, size_t T, int C) {
+rvsa_kv_finalize_kernel(const float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int T, int C,
+                        int rows_per_cta) {
   MTP_PDL_ENTRY();
-  const size_t n4 = T * (size_t)(2 * C / 4);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t t = i / (2 * C / 4);
-    const int c = (int)(i % (2 * C / 4)) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(dkv + t * 2 * C + c);
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;       // column of dqkv
+  if (c >= 3 * C) return;
+  if (c < C && colsum == nullptr) return;
+  const int row0 = blockIdx.y * rows_per_cta, row1 = min(T, row0 + rows_per_cta);
+  float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 8
+  for (int t = row0; t < row1; ++t) {
     uint2 u;
-    u.x = pack_bf16x2(v.x, v.y);
-    u.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(dqkv + t * 3 * C + C + c) = u;
+    if (c < C) {
+      u = *reinterpret_cast<const uint2*>(dqkv + (size_t)t * 3 * C + c);
+    } else {
+      const float4 v = *reinterpret_cast<const float4*>(dkv + (size_t)t * 2 * C + (c - C));
+      u.x = pack_bf16x2(v.x, v.y);
+      u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(dqkv + (size_t)t * 3 * C + c) = u;
+    }
+    const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y);
+    acc.x += a.x; acc.y += a.y; acc.z += d.x; acc.w += d.y;
   }
+  if (colsum != nullptr)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + c), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ sampling heads bwd
@@ -400,10 +437,12 @@ rvsa_sampling_bwd_kernel(const float* __restrict__ dparams, const float* __restr
   const int c = blockIdx.y * 256 + threadIdx.x;          // CTA = (image-window, 256-channel slab)
   if (c < C) {
     float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
     for (int o = 0; o < 2 * nH; ++o) {
       s0 += gs[o] * __ldg(w_off + (size_t)o * C + c);
       s1 += gs[2 * nH + o] * __ldg(w_sc + (size_t)o * C + c);
     }
+#pragma unroll 8
     for (int o = 0; o < nH; ++o) s0 += gs[4 * nH + o] * __ldg(w_ang + (size_t)o * C + c);
     const float p = pooled[(size_t)bw * C + c];
     dpooled[(size_t)bw * C + c] = (p >= 0.f ? 1.0f : 0.01f) * (s0 + s1);
@@ -424,6 +463,7 @@ rvsa_sampling_wgrad_kernel(const float* __restrict__ g_out, const float* __restr
   else { dw = dw_ang; db = db_ang; oo = o - 4 * nH; }
   if (c < C) {
     float s = 0.f;
+#pragma unroll 8
     for (int bw = 0; bw < n_bw; ++bw) {
       const float p = pooled[(size_t)bw * C + c];
       s += g_out[(size_t)bw * 5 * nH + o] * (p >= 0.f ? p : 0.01f * p);
@@ -432,6 +472,7 @@ rvsa_sampling_wgrad_kernel(const float* __restrict__ g_out, const float* __restr
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     float s = 0.f;
+#pragma unroll 8
     for (int bw = 0; bw < n_bw; ++bw) s += g_out[(size_t)bw * 5 * nH + o];
     db[oo] += s;
   }
@@ -476,8 +517,8 @@ extern "C" size_t mtp_rvsa_bwd_workspace_bytes(int B, int h, int w, int C, int n
 
 extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,
                                  const float* bias_table, const float* lse, const void* dout_bf16, void* dqkv_bf16, float* dparams,
-                                 float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, void* workspace, int B, int h, int w,
-                                 int C, int nH, mtp_stream_t stream) {
+                                 float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace, int B,
+                                 int h, int w, int C, int nH, mtp_stream_t stream) {
   MTP_REQUIRE(qkv_bf16 && params && rel_pos_h && rel_pos_w && bias_table && lse && dout_bf16 && dqkv_bf16 && dparams &&
                   d_rel_pos_h && d_rel_pos_w && d_bias_table && workspace, "mtp_rvsa_attn_bwd: null pointer");
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD, "mtp_rvsa_attn_bwd: B=%d h=%d w=%d C=%d nH=%d unsupported", B, h, w, C, nH);
@@ -510,14 +551,16 @@ extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, cons
     n_rel_parts = n_cta;
   }
   if (rc) return rc;
-  const int n_red = 2 * (2 * WS - 1) * HD + 169 * nH;
-  (void)launch_k(rvsa_partials_reduce_kernel, ceil_div(n_red, 256), 256, 0, st, part_rel, part_table, d_rel_pos_h, d_rel_pos_w, d_bias_table, n_rel_parts,
-                                                                    n_cta / nH, nH);
+  const int n_red_blocks = 2 * (2 * WS - 1) * HD / 32 + nH * ((169 + 31) / 32);
+  (void)launch_k(rvsa_partials_reduce_kernel, n_red_blocks, 256, 0, st, part_rel, part_table, d_rel_pos_h, d_rel_pos_w, d_bias_table,
+                 n_rel_parts, n_cta / nH, nH);
   rc = check_launch("rvsa_partials_reduce_kernel");
   if (rc) return rc;
-  const size_t n4 = T * (size_t)(2 * C / 4);
-  const int grid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)num_sms() * 8);
-  (void)launch_k(rvsa_kv_finalize_kernel, grid, 256, 0, st, dkv, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), T, C);
+  const int gx = ceil_div(3 * C, 1024);
+  const int gy = std::max(1, std::min(ceil_div((int)T, 8), 4 * num_sms() / gx));
+  const int rpc = ceil_div((int)T, gy);
+  (void)launch_k(rvsa_kv_finalize_kernel, dim3(gx, ceil_div((int)T, rpc)), 256, 0, st, dkv, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16),
+                 d_qkv_bias, (int)T, C, rpc);
   return check_launch("rvsa_kv_finalize_kernel");
 }
 

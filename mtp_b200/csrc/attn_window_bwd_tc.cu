@@ -464,9 +464,9 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   }
   tc_fence_before();
   __syncthreads();
-  if (tid < 10) {
-    const int pp = tid / 5, k = tid % 5;
-    dparams[((size_t)bw * g.nH + 2 * hp + pp) * 8 + k] = red[(2 * pp) * 8 + k] + red[(2 * pp + 1) * 8 + k];
+  if (tid < 16) {          // slots 5..7 of a parameter row are unused: written as zeros
+    const int pp = tid >> 3, k = tid & 7;
+    dparams[((size_t)bw * g.nH + 2 * hp + pp) * 8 + k] = k < 5 ? red[(2 * pp) * 8 + k] + red[(2 * pp + 1) * 8 + k] : 0.f;
   }
   if (warp == 0) {
     tc_fence_after();

@@ -74,13 +74,14 @@ def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
     if d["window"]:
         dqkv, dparams = ops.rvsa_attn_bwd(s["qkv"], s["params"], d["rel_h"], d["rel_w"], d["table"], s["lse"], do,
                                           G.g(pre + "attn.rel_pos_h"), G.g(pre + "attn.rel_pos_w"),
-                                          G.g(pre + "attn.relative_position_bias_table"), B, gh, gw, nH)
+                                          G.g(pre + "attn.relative_position_bias_table"), B, gh, gw, nH,
+                                          d_qkv_bias=G.g(pre + "attn.qkv.bias"))
     else:
         has_rel = d["rel_h"] is not None
         dqkv = ops.full_attn_bwd(s["qkv"], d["rel_h"], d["rel_w"], s["lse"], s["o"], do,
                                  G.g(pre + "attn.full_attn_rel_pos_h") if has_rel else None,
                                  G.g(pre + "attn.full_attn_rel_pos_w") if has_rel else None, B, gh, gw, nH)
-    ops.colsum_bf16(dqkv, G.g(pre + "attn.qkv.bias"))
+        ops.colsum_bf16(dqkv, G.g(pre + "attn.qkv.bias"))
     dy1 = _linear_bwd(dqkv, s["y1"], d["qkv_w"], G.g(pre + "attn.qkv.weight"), T, 3 * C, C)
     if d["window"]:
         a = pre + "attn.sampling_"

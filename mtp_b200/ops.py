@@ -114,7 +114,7 @@ def add_bf16_into_f32(src, dst):
 def rvsa_sampling_fwd(yn, w_off, b_off, w_sc, b_sc, w_ang, b_ang, B, h, w, nH, save_pooled=True):
     C = yn.shape[-1]
     nwin = ((h + 6) // 7) * ((w + 6) // 7)
-    params = torch.zeros(B * nwin, nH, 8, device=yn.device, dtype=F32)
+    params = torch.empty(B * nwin, nH, 8, device=yn.device, dtype=F32)       # all 8 slots are written by the kernel
     pooled = torch.empty(B * nwin, C, device=yn.device, dtype=F32)       # written by the pooling kernel, read by the conv kernel
     L.call("mtp_rvsa_sampling_fwd", yn.data_ptr(), w_off.data_ptr(), b_off.data_ptr(), w_sc.data_ptr(), b_sc.data_ptr(),
            w_ang.data_ptr(), b_ang.data_ptr(), _p(pooled), params.data_ptr(), B, h, w, C, nH, _stream())
@@ -177,14 +177,14 @@ def _workspace(nbytes, device):
     return torch.empty((nbytes + 3) // 4, device=device, dtype=F32)
 
 
-def rvsa_attn_bwd(qkv, params, rel_h, rel_w, table, lse, dout, d_rel_h, d_rel_w, d_table, B, h, w, nH):
+def rvsa_attn_bwd(qkv, params, rel_h, rel_w, table, lse, dout, d_rel_h, d_rel_w, d_table, B, h, w, nH, d_qkv_bias=None):
     C = qkv.shape[-1] // 3
     dqkv = torch.empty_like(qkv)
-    dparams = torch.zeros_like(params)
+    dparams = torch.empty_like(params)
     ws = _workspace(L.load().mtp_rvsa_bwd_workspace_bytes(B, h, w, C, nH), qkv.device)
     L.call("mtp_rvsa_attn_bwd", qkv.data_ptr(), params.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(), table.data_ptr(), lse.data_ptr(),
            dout.data_ptr(), dqkv.data_ptr(), dparams.data_ptr(), d_rel_h.data_ptr(), d_rel_w.data_ptr(), d_table.data_ptr(),
-           ws.data_ptr(), B, h, w, C, nH, _stream())
+           _p(d_qkv_bias), ws.data_ptr(), B, h, w, C, nH, _stream())
     return dqkv, dparams
 
 

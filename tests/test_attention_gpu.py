@@ -161,8 +161,13 @@ def test_rvsa_backward_vs_oracle_autograd(grid, B, nH, big):
     _, lse = ops.rvsa_attn_fwd(qkv_d, params, rel_h, rel_w, table, B, grid, grid, nH)
     z = lambda t: torch.zeros_like(t)
     g_rel_h, g_rel_w, g_table = z(rel_h), z(rel_w), z(table)
+    g_qkv_bias = torch.zeros(3 * C, device="cuda")
     dqkv, dparams = ops.rvsa_attn_bwd(qkv_d, params, rel_h, rel_w, table, lse, d(gout.reshape(-1, C)).to(torch.bfloat16),
-                                      g_rel_h, g_rel_w, g_table, B, grid, grid, nH)
+                                      g_rel_h, g_rel_w, g_table, B, grid, grid, nH, d_qkv_bias=g_qkv_bias)
+    # fused qkv-bias gradient = column sums of the stored bf16 dqkv; unused parameter slots are zero
+    ref_bias = dqkv.float().sum(0)
+    assert (g_qkv_bias - ref_bias).abs().max().item() <= 1e-3 * max(1.0, ref_bias.abs().max().item())
+    assert (dparams[..., 5:] == 0).all() and (params[..., 5:] == 0).all()
     w = {k: d(P[f"a.sampling_{k}.2.weight"].reshape(-1, C)) for k in ("offsets", "scales", "angles")}
     gw = {k: z(v) for k, v in w.items()}
     gb = {k: torch.zeros(v.shape[0], device="cuda") for k, v in w.items()}
