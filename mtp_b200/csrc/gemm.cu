@@ -538,10 +538,10 @@ struct HostProblem {
   EpiParams ep;
 };
 
-// Cycles of one 64-deep k-block of a BN-wide tile (measured with the in-kernel phase stamps, tools/gemm_phases.py): the MMAs
-// take 2*BN cycles; the TMA unit of an SM delivers one 128-byte row of a box per ~1.8 cycles, and a cta_group::2 pair halves
-// the B rows each SM stages.
-static double kblock_cycles(int bn, bool cl2) { return std::max(2.0 * bn, 1.8 * (128.0 + (cl2 ? bn / 2 : bn))); }
+// Cycles of one 64-deep k-block of a BN-wide tile (fit to the in-kernel phase stamps, tools/gemm_phases.py: 0.27 / 0.27 / 0.31 /
+// 0.34 us for BN = 64 / 128 / 192 / 256, 0.27 us for a 256-wide pair): the MMAs take 2*BN cycles, the operand fill of the SM
+// ~400 cycles for the A box plus ~1 cycle per 128-byte row of B, and a cta_group::2 pair halves the B rows each SM stages.
+static double kblock_cycles(int bn, bool cl2) { return std::max(2.0 * bn, 400.0 + 1.05 * (cl2 ? bn / 2 : bn)); }
 static const double kTileFixedCycles = 2500.0;      // epilogue / pipeline fill per tile
 static const double kClusterLaunchCycles = 5000.0;  // a cluster launch starts / retires ~2.5 us later than a plain one (tools/gemm_gaps.py)
 
