@@ -75,6 +75,8 @@ typedef struct mtp_epilogue {
   int ps_h, ps_w, ps_cout;
   float* colsum;          /* BF16 / BF16_DGELU: optional [N] fp32, += column sums of the stored values (the bias gradient of the
                              Linear whose cotangent this GEMM produces); 16-byte aligned */
+  int b_static;           /* 1: operand B is NOT written by the kernels just before this one in the stream (weights, activations
+                             saved earlier): its first tiles may be fetched before the programmatic-dependent-launch wait */
 } mtp_epilogue;
 
 int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N, int K,

@@ -19,7 +19,7 @@ class Epilogue(ctypes.Structure):
     """struct mtp_epilogue (include/mtp_b200.h)."""
     _fields_ = [("mode", c_int), ("ldo", c_int), ("bias", c_void_p), ("out", c_void_p), ("out2", c_void_p),
                 ("aux", c_void_p), ("row_scale", c_void_p), ("rows_per_group", c_int), ("pos_rows", c_int),
-                ("accumulate", c_int), ("ps_h", c_int), ("ps_w", c_int), ("ps_cout", c_int), ("colsum", c_void_p)]
+                ("accumulate", c_int), ("ps_h", c_int), ("ps_w", c_int), ("ps_cout", c_int), ("colsum", c_void_p), ("b_static", c_int)]
 
 
 class GemmDesc(ctypes.Structure):

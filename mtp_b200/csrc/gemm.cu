@@ -48,6 +48,7 @@ struct EpiParams {
   const float* row_scale;
   int rows_per_group, pos_rows, accumulate, ps_h, ps_w, ps_cout;
   float* colsum;
+  int b_static;
 };
 
 // ---- epilogue ---------------------------------------------------------------------------------------------------------
@@ -308,7 +309,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   if (CL2) cluster_sync_all();       // peer barriers are initialised before any remote signal can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  MTP_PDL_ENTRY();                   // everything above overlapped the previous kernel's tail; operands are read below
+  // Everything above overlapped the previous kernel's tail (programmatic dependent launch).  Each warp role passes the
+  // dependency wait itself: the producer first prefetches B tiles that do not depend on the predecessor (weights).
   if (threadIdx.x == 0) MTP_STAMP(1);
 
 #define MTP_DECODE_ITEM(IT)                                                                      \
@@ -326,6 +328,39 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
     // one elected lane issues.  Issuing from inside a divergent `if (lane == 0)` makes the compiler wrap every UTMALDG /
     // UTCHMMA in an ELECT + R2UR.BROADCAST waterfall loop (measured: ~175 cycles per MMA instead of its N/2).
     {
+      // B tiles of the first item's first k-blocks that are independent of the stream predecessor (ep.b_static: weights, saved
+      // activations) are requested BEFORE the dependency wait, so their HBM latency overlaps the predecessor's tail
+      int pre = 0;
+      if (n_items > 0 && sched.dbg_mode == 0) {
+        MTP_DECODE_ITEM(0)
+        if (P.ep.b_static) {
+          pre = min(STAGES, k_blocks);
+          for (int kb = 0; kb < pre; ++kb) {
+            uint8_t* sb = smem + kb * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+            if (elect_one()) {
+              if (!CL2) {
+                mbar_arrive_expect_tx(&full_bar[kb], Cfg::STAGE_BYTES);
+                if (!P.b_mn) {
+                  tma_load_2d(sb, &P.tmB, &full_bar[kb], kb * BK, n0);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[kb], n0 + j * 64, kb * BK);
+                }
+              } else {
+                if (crank == 0) mbar_arrive_expect_tx(&full_bar[kb], 2 * Cfg::STAGE_BYTES);
+                if (!P.b_mn) {
+                  tma_load_2d_2sm(sb, &P.tmB, &full_bar[kb], kb * BK, n0 + crank * (BN / 2));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &P.tmB, &full_bar[kb], n0 + crank * (BN / 2) + j * 64, kb * BK);
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      MTP_PDL_ENTRY();
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_items; ++it) {
@@ -334,18 +369,20 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          const bool b_done = it == 0 && kb < pre;      // this stage's B half (and its expect_tx) were issued above
           if (elect_one()) {
             if (sched.dbg_mode == 1) {
               if (!CL2 || crank == 0) mbar_arrive(&full_bar[stage]);
             } else if (!CL2) {
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              if (!b_done) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               if (!P.a_mn) {
                 tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
               } else {
 #pragma unroll
                 for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
               }
-              if (!P.b_mn) {
+              if (b_done) {
+              } else if (!P.b_mn) {
                 tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * BK, n0);
               } else {
 #pragma unroll
@@ -353,14 +390,15 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
               }
             } else {
               // both CTAs' bytes are credited to the LEADER's full barrier (only the leader waits on it and issues the MMAs)
-              if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              if (crank == 0 && !b_done) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
               if (!P.a_mn) {
                 tma_load_2d_2sm(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
               } else {
 #pragma unroll
                 for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
               }
-              if (!P.b_mn) {       // my half of the pair's B tile: columns [n0 + crank*BN/2, +BN/2)
+              if (b_done) {
+              } else if (!P.b_mn) {       // my half of the pair's B tile: columns [n0 + crank*BN/2, +BN/2)
                 tma_load_2d_2sm(sb, &P.tmB, &full_bar[stage], kb * BK, n0 + crank * (BN / 2));
               } else {
 #pragma unroll
@@ -375,6 +413,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
+    MTP_PDL_ENTRY();
     if (!CL2 || crank == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -429,6 +468,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    MTP_PDL_ENTRY();
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int hsel = (warp - 2) >> 2;       // which alternate chunks this warp takes
     const int et = threadIdx.x - 64;        // 0..255 within the epilogue group
@@ -714,6 +754,7 @@ static EpiParams to_epi(const mtp_epilogue* ep) {
   p.row_scale = ep->row_scale; p.rows_per_group = ep->rows_per_group; p.pos_rows = ep->pos_rows;
   p.accumulate = ep->accumulate; p.ps_h = ep->ps_h; p.ps_w = ep->ps_w; p.ps_cout = ep->ps_cout;
   p.colsum = ep->colsum;
+  p.b_static = ep->b_static;
   return p;
 }
 

@@ -115,7 +115,7 @@ def _block_forward(d, x0, B, gh, gw, nH, keep_a, keep_m, save):
     N = gh * gw
     y1, mean1, rstd1 = ops.layernorm_fwd(x0, d["norm1_w"], d["norm1_b"], save_stats=save)
     qkv = torch.empty(T, 3 * C, device=x0.device, dtype=BF16)
-    ops.gemm(y1, d["qkv_w"], T, 3 * C, C, qkv, bias=d["qkv_b"])
+    ops.gemm(y1, d["qkv_w"], T, 3 * C, C, qkv, bias=d["qkv_b"], b_static=True)
     params = pooled = None
     if d["window"]:
         params, pooled = ops.rvsa_sampling_fwd(y1, d["off_w"], d["off_b"], d["sc_w"], d["sc_b"], d["ang_w"], d["ang_b"], B, gh, gw, nH,
@@ -124,14 +124,14 @@ def _block_forward(d, x0, B, gh, gw, nH, keep_a, keep_m, save):
     else:
         o, lse = ops.full_attn_fwd(qkv, d["rel_h"], d["rel_w"], B, gh, gw, nH, save_lse=save)
     x1 = torch.empty_like(x0) if save else x0
-    ops.gemm(o, d["proj_w"], T, C, C, x1, mode=L.EPI_F32_RESID, bias=d["proj_b"], aux=x0, row_scale=keep_a, rows_per_group=N)
+    ops.gemm(o, d["proj_w"], T, C, C, x1, mode=L.EPI_F32_RESID, bias=d["proj_b"], aux=x0, row_scale=keep_a, rows_per_group=N, b_static=True)
     y2, mean2, rstd2 = ops.layernorm_fwd(x1, d["norm2_w"], d["norm2_b"], save_stats=save)
     hid = d["fc1_w"].shape[0]
     a = torch.empty(T, hid, device=x0.device, dtype=BF16)
     hpre = torch.empty(T, hid, device=x0.device, dtype=BF16) if save else None
-    ops.gemm(y2, d["fc1_w"], T, hid, C, a, mode=L.EPI_BF16_GELU, bias=d["fc1_b"], out2=hpre)
+    ops.gemm(y2, d["fc1_w"], T, hid, C, a, mode=L.EPI_BF16_GELU, bias=d["fc1_b"], out2=hpre, b_static=True)
     x2 = torch.empty_like(x0) if save else x1
-    ops.gemm(a, d["fc2_w"], T, C, hid, x2, mode=L.EPI_F32_RESID, bias=d["fc2_b"], aux=x1, row_scale=keep_m, rows_per_group=N)
+    ops.gemm(a, d["fc2_w"], T, C, hid, x2, mode=L.EPI_F32_RESID, bias=d["fc2_b"], aux=x1, row_scale=keep_m, rows_per_group=N, b_static=True)
     saved = None
     if save:
         saved = dict(x0=x0, mean1=mean1, rstd1=rstd1, y1=y1, qkv=qkv, params=params, pooled=pooled, lse=lse, o=o, x1=x1,
@@ -152,15 +152,15 @@ def _fpn_forward(m, W, feats, B, gh, gw, out_dtype, save):
     # fpn1: ConvT -> Norm2d(LN over C) -> GELU -> ConvT ; rows of u1 viewed as [4T, C] are the 2x-upsampled pixels
     a0 = feats[0] if feats[0].dtype == BF16 else ops.cast_f32_bf16(feats[0])
     u1 = torch.empty(T, 4 * C, device=a0.device, dtype=BF16)
-    ops.gemm(a0, F_["fpn1_0_w"], T, 4 * C, C, u1, bias=F_["fpn1_0_b"])
+    ops.gemm(a0, F_["fpn1_0_w"], T, 4 * C, C, u1, bias=F_["fpn1_0_b"], b_static=True)
     z, mean, rstd = ops.layernorm_fwd(u1.view(4 * T, C), F_["ln_w"], F_["ln_b"], gelu=True, save_stats=save)
     u2 = torch.empty(4 * T, 4 * C, device=a0.device, dtype=BF16)
-    ops.gemm(z, F_["fpn1_3_w"], 4 * T, 4 * C, C, u2, bias=F_["fpn1_3_b"])
+    ops.gemm(z, F_["fpn1_3_w"], 4 * T, 4 * C, C, u2, bias=F_["fpn1_3_b"], b_static=True)
     outs.append(ops.tok_to_nchw(u2, B, gh, gw, C, 2, out_dtype))
     # fpn2: ConvT
     a1 = feats[1] if feats[1].dtype == BF16 else ops.cast_f32_bf16(feats[1])
     v1 = torch.empty(T, 4 * C, device=a0.device, dtype=BF16)
-    ops.gemm(a1, F_["fpn2_0_w"], T, 4 * C, C, v1, bias=F_["fpn2_0_b"])
+    ops.gemm(a1, F_["fpn2_0_w"], T, 4 * C, C, v1, bias=F_["fpn2_0_b"], b_static=True)
     outs.append(ops.tok_to_nchw(v1, B, gh, gw, C, 1, out_dtype))
     # fpn3: identity
     outs.append(ops.tok_to_nchw(feats[2], B, gh, gw, C, 0, out_dtype))
@@ -196,9 +196,9 @@ def _forward_impl(m, x, keep, save):
     xres = torch.empty(T, C, device=x.device, dtype=F32)
     K0 = patches.shape[1]
     if W.pos is not None:
-        ops.gemm(patches, W.pe_w, T, C, K0, xres, mode=L.EPI_F32_POS, bias=W.pe_b, aux=W.pos, pos_rows=gh * gw)
+        ops.gemm(patches, W.pe_w, T, C, K0, xres, mode=L.EPI_F32_POS, bias=W.pe_b, aux=W.pos, pos_rows=gh * gw, b_static=True)
     else:
-        ops.gemm(patches, W.pe_w, T, C, K0, xres, mode=L.EPI_F32, bias=W.pe_b)
+        ops.gemm(patches, W.pe_w, T, C, K0, xres, mode=L.EPI_F32, bias=W.pe_b, b_static=True)
     ckpt = save and m.use_checkpoint
     feats, blocks_saved = [], []
     for i, d in enumerate(W.blocks):

@@ -46,9 +46,11 @@ def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_
     grouped launch whose tiles are spread over the SMs by a common schedule.  ``colsum``: fp32 [n_in] that receives the column
     sums of dx (the bias gradient of the Linear below) from the dgrad epilogue."""
     dx = torch.empty(T, n_in, device=g_bf16.device, dtype=BF16)
+    # b_static: the weights and the activation saved by the forward are not written by the kernel just before this launch
     ops.gemm_dual(dict(A=g_bf16, B=w_bf16, M=T, N=n_in, K=n_out, out=dx, b_mn=True, mode=dgrad_mode, aux=aux, lda=n_out, ldb=n_in,
-                       colsum=colsum),
-                  dict(A=g_bf16, B=x_bf16, M=n_out, N=n_in, K=T, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=n_out, ldb=n_in, ldo=n_in))
+                       colsum=colsum, b_static=True),
+                  dict(A=g_bf16, B=x_bf16, M=n_out, N=n_in, K=T, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=n_out, ldb=n_in, ldo=n_in,
+                       b_static=True))
     return dx
 
 

@@ -176,3 +176,32 @@ def test_epilogue_column_sums(bn):
         out2 = torch.empty_like(out)
         ops.gemm(A, Bm, M, N, K, out2, b_mn=True, mode=mode, aux=aux, force_bn=bn)
         assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("bn", [0, 64, 128, 256, 1128, 1256])
+@pytest.mark.parametrize("b_mn", [False, True])
+def test_b_static_prefetch_matches(bn, b_mn):
+    """b_static only moves the first B loads ahead of the dependency wait: results are bit-identical, also for K shorter than the ring."""
+    from mtp_b200 import ops, _lib as L
+    for K in (72, 456, 1024):
+        M, N = 704, 512
+        A = _mk((M, K), seed=41)
+        B = _mk((K, N) if b_mn else (N, K), seed=42)
+        o0 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        o1 = torch.empty_like(o0)
+        ops.gemm(A, B, M, N, K, o0, b_mn=b_mn, force_bn=bn)
+        ops.gemm(A, B, M, N, K, o1, b_mn=b_mn, force_bn=bn, b_static=True)
+        torch.cuda.synchronize()
+        assert torch.equal(o0, o1)
+    # grouped launch: dgrad-like (K-major A, MN-major B) + wgrad-like (both MN-major) sharing A
+    G = _mk((704, 512), seed=45)
+    Wt, X = _mk((512, 512), seed=44), _mk((704, 512), seed=43)
+    outs = []
+    for st in (False, True):
+        dx = torch.empty(704, 512, device="cuda", dtype=torch.bfloat16)
+        dW = torch.empty(512, 512, device="cuda")
+        ops.gemm_dual(dict(A=G, B=Wt, M=704, N=512, K=512, out=dx, b_mn=True, b_static=st),
+                      dict(A=G, B=X, M=512, N=512, K=704, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, b_static=st), force_bn=bn)
+        outs.append((dx, dW))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
