@@ -224,7 +224,7 @@ def gemm_profile(trainer, x):
 def count_launches(trainer, x):
     """Kernels of libmtp_b200.so launched per step (entry point -> kernels it enqueues)."""
     from mtp_b200 import _lib
-    per_call = {"mtp_rvsa_attn_bwd": 3, "mtp_rvsa_sampling_bwd": 3, "mtp_full_attn_bwd": 2}
+    per_call = {"mtp_rvsa_sampling_fwd": 2, "mtp_rvsa_attn_bwd": 3, "mtp_rvsa_sampling_bwd": 3}
     n = [0]
     orig = _lib.call
 
@@ -314,6 +314,28 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (t.item() / args.steps / 1e3)
+
+    # ---- GEMM time inside the graph-replayed step: the same step re-captured with empty GEMM launches (mtp_gemm_set_debug_mode 4);
+    #      the difference is what the tcgen05 GEMM kernels cost in situ (operands in the state the step leaves them, PDL overlap
+    #      included).  Run last: the training state is garbage afterwards.
+    gemm_ms_graph = None
+    if args.graph and world == 1:
+        try:
+            _lib.call("mtp_gemm_set_debug_mode", 4)
+            trainer.graph = None
+            for _ in range(3):
+                trainer.step(x)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                trainer.step(x)
+            e1.record()
+            torch.cuda.synchronize()
+            gemm_ms_graph = ms_step - e0.elapsed_time(e1) / args.steps
+        finally:
+            _lib.call("mtp_gemm_set_debug_mode", 0)
+        if gemm_ms_graph is not None and gemm_ms_graph > 0:
+            gemm_ms_eager, gemm_ms = gemm_ms, gemm_ms_graph
 
     if rank == 0:
         pk = peaks()

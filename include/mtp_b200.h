@@ -94,7 +94,8 @@ typedef struct mtp_gemm_desc {
 int mtp_gemm_bf16_dual(const mtp_gemm_desc* g0, const mtp_gemm_desc* g1, int force_bn, mtp_stream_t stream);
 /* Tuning aid: device buffer [grid][8] of int64 that receives per-CTA globaltimer stamps of the pipeline phases (NULL = off). */
 int mtp_gemm_set_debug(void* device_buffer);
-/* Tuning aid: 0 normal; 1 = skip the TMA loads (isolates the MMA pipeline; results are garbage); 2 = skip the MMAs. */
+/* Tuning aid: 0 normal; 1 = skip the TMA loads (isolates the MMA pipeline; results are garbage); 2 = skip the MMAs;
+ * 3 = skip the epilogue stores; 4 = empty launches (bench.py measures the GEMM share of a graph-replayed step with it). */
 int mtp_gemm_set_debug_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -160,6 +161,9 @@ int mtp_nchw_to_tok(const void* in, int in_is_bf16, void* tok, int tok_is_bf16, 
                     int level, mtp_stream_t stream);
 int mtp_maxpool2_tok_fwd(const float* x, float* y, int B, int h, int w, int C, mtp_stream_t stream);
 int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, int B, int h, int w, int C, mtp_stream_t stream);
+/* Stand-in objective when no decoder heads are attached (the reference's heads are third-party code): for one bf16
+ * feature map of n elements (n % 8 == 0)  *loss += 0.5 * mean(f^2)  and  grad = f / n. */
+int mtp_sqloss_fwd_bwd(const void* feat_bf16, void* grad_bf16, float* loss, size_t n, mtp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Attention backward (autograd of the forward entry points above; everything is recomputed from qkv + lse).

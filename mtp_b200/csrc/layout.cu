@@ -152,6 +152,37 @@ maxpool2_tok_bwd_kernel(const float* __restrict__ x, const float* __restrict__ d
 
 static inline int grid_for(size_t n, int block) { return (int)std::min<size_t>((n + block - 1) / block, (size_t)num_sms() * 16); }
 
+// Stand-in objective of the pretraining step when no decoder heads are attached (trainer.synthetic_heads, bench.py):
+// loss += 0.5 * mean(f^2), d loss / d f = f / n, one pass over the bf16 feature map.
+__global__ void __launch_bounds__(256)
+sqloss_kernel(const __nv_bfloat16* __restrict__ f, __nv_bfloat16* __restrict__ g, float* __restrict__ loss, size_t n8, float inv_n) {
+  MTP_PDL_ENTRY();
+  __shared__ float red[8];
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(f + i * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 v = unpack_bf16x2(w[t]);
+      s += v.x * v.x + v.y * v.y;
+      o[t] = pack_bf16x2(v.x * inv_n, v.y * inv_n);
+    }
+    *reinterpret_cast<uint4*>(g + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = red[threadIdx.x];
+    t += __shfl_xor_sync(0xffu, t, 4);
+    t += __shfl_xor_sync(0xffu, t, 2);
+    t += __shfl_xor_sync(0xffu, t, 1);
+    if (threadIdx.x == 0) atomicAdd(loss, 0.5f * inv_n * t);
+  }
+}
+
 }  // namespace mtp
 
 using namespace mtp;
@@ -219,4 +250,13 @@ extern "C" int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, 
   const size_t total = (size_t)B * (h / 2) * (w / 2) * C;
   (void)launch_k(maxpool2_tok_bwd_kernel, grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, dy, dx, B, h, w, C);
   return check_launch("maxpool2_tok_bwd_kernel");
+}
+
+extern "C" int mtp_sqloss_fwd_bwd(const void* feat_bf16, void* grad_bf16, float* loss, size_t n, mtp_stream_t stream) {
+  MTP_REQUIRE(feat_bf16 && grad_bf16 && loss && n > 0 && n % 8 == 0, "mtp_sqloss_fwd_bwd: bad args (n must be a positive multiple of 8)");
+  const size_t n8 = n / 8;
+  const int grid = (int)std::min<size_t>((n8 + 255) / 256, (size_t)num_sms() * 8);
+  (void)launch_k(sqloss_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(feat_bf16),
+                 reinterpret_cast<__nv_bfloat16*>(grad_bf16), loss, n8, 1.0f / (float)n);
+  return check_launch("sqloss_kernel");
 }

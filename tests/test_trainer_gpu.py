@@ -56,3 +56,15 @@ def test_fused_step_matches_torch_adamw(graph):
     # second step runs (graph replay path) and changes the loss
     l3 = tr.step(x)
     assert l3.item() != l1v
+
+
+def test_fused_stand_in_heads_match_torch():
+    """mtp_sqloss_fwd_bwd (one pass per map) = the torch formulation of the stand-in objective."""
+    from mtp_b200.trainer import synthetic_heads
+    torch.manual_seed(3)
+    feats = [torch.randn(2, 64, s, s, device="cuda").to(torch.bfloat16) for s in (56, 28, 14, 7)]
+    loss, grads = synthetic_heads(feats)
+    ref_loss = sum((f.float() ** 2).mean() * 0.5 for f in feats)
+    assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item())
+    for f, g in zip(feats, grads):
+        assert torch.equal(g, (f.float() * (1.0 / f.numel())).to(torch.bfloat16))
