@@ -92,6 +92,8 @@ typedef struct mtp_gemm_desc {
   const mtp_epilogue* ep;
 } mtp_gemm_desc;
 int mtp_gemm_bf16_dual(const mtp_gemm_desc* g0, const mtp_gemm_desc* g1, int force_bn, mtp_stream_t stream);
+/* Tile configuration the heuristic (or force_bn) selected for the most recent GEMM launch: width + 1000 for cta_group::2 pairs. */
+int mtp_gemm_last_config(void);
 /* Tuning aid: device buffer [grid][8] of int64 that receives per-CTA globaltimer stamps of the pipeline phases (NULL = off). */
 int mtp_gemm_set_debug(void* device_buffer);
 /* Tuning aid: 0 normal; 1 = skip the TMA loads (isolates the MMA pipeline; results are garbage); 2 = skip the MMAs;

@@ -668,6 +668,7 @@ static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
   return &cache.emplace(key, best).first->second;
 }
 
+static int g_last_config = 0;
 static long long* g_gemm_dbg = nullptr;
 static int g_gemm_dbg_mode = 0;
 
@@ -770,6 +771,7 @@ static int run_grouped(const HostProblem* pr, int np, int force_bn, cudaStream_t
   }
   const Config* cfg = get_config(pr, np, force_bn);
   if (cfg == nullptr) return set_error(MTP_ERR_INVALID, "mtp_gemm_bf16: no valid tile configuration (force_bn=%d)", force_bn);
+  g_last_config = cfg->bn + (cfg->cl2 ? 1000 : 0);
 #define MTP_LAUNCH(BN_)                                                             \
   case BN_:                                                                         \
     return cfg->cl2 ? launch_grouped<BN_, true>(pr, np, cfg->sched, stream) : launch_grouped<BN_, false>(pr, np, cfg->sched, stream);
@@ -801,6 +803,7 @@ extern "C" int mtp_gemm_set_debug(void* device_buffer) {
   g_gemm_dbg = reinterpret_cast<long long*>(device_buffer);
   return MTP_OK;
 }
+extern "C" int mtp_gemm_last_config(void) { return g_last_config; }
 extern "C" int mtp_gemm_set_debug_mode(int mode) {
   g_gemm_dbg_mode = mode;
   return MTP_OK;

@@ -57,6 +57,8 @@ for name, M, N, K, a_mn, b_mn, mode in shapes:
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / n
             row[f"bn{bn}"] = (round(us, 1), round(2.0 * M * N * K / us / 1e6, 0))
+            if bn == 0:
+                row["picked"] = L.load().mtp_gemm_last_config()
         except Exception as ex:
             row[f"bn{bn}"] = str(ex)[:40]
     # cuBLAS reference for context

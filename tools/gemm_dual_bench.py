@@ -35,6 +35,8 @@ for name, n_out, n_in, mode in layers:
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / n
             row[f"bn{bn}"] = (round(us, 1), round(4.0 * T * n_in * n_out / us / 1e6, 0))
+            if bn == 0:
+                row["picked"] = L.load().mtp_gemm_last_config()
         except Exception as ex:
             row[f"bn{bn}"] = str(ex)[:40]
     res.append(row)
