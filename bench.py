@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
     ap.add_argument("--graph", type=int, default=1, help="capture the step into a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-blocks", type=int, default=2, help="transformer blocks per gradient all-reduce bucket (N > 1)")
+    ap.add_argument("--comm-sms", type=int, default=16, help="SMs left to NCCL while the backward runs (N > 1)")
     ap.add_argument("--cpu-batch", type=int, default=1, help="images per CPU-reference step (bounded sample)")
     return ap.parse_args()
 
@@ -253,13 +255,16 @@ def main():
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     if world > 1:
+        if args.comm_sms > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_sms))       # the SMs PretrainStep(comm_sms=) leaves to the all-reduce kernels
         dist.init_process_group("nccl", device_id=dev)
     from mtp_b200 import _lib
     from mtp_b200.trainer import PretrainStep
     _lib.load()
     B = args.batch
     model = build_model(dev)
-    trainer = PretrainStep(model, lr=6e-5, weight_decay=0.05, max_norm=5.0, t_max=80000, use_cuda_graph=bool(args.graph))
+    trainer = PretrainStep(model, lr=6e-5, weight_decay=0.05, max_norm=5.0, t_max=80000, use_cuda_graph=bool(args.graph),
+                           bucket_blocks=args.bucket_blocks, comm_sms=args.comm_sms)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn(B, 3, 224, 224, device=dev, generator=g).to(torch.bfloat16)
     x_host = x.cpu().pin_memory()

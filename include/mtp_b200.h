@@ -38,6 +38,10 @@ int mtp_num_sms(void);
 /* Programmatic dependent launch for every kernel of the library (default on): each kernel may be scheduled while its stream
  * predecessor drains and holds at griddepcontrol.wait until the predecessor's results are visible.  Off = plain stream order. */
 int mtp_set_pdl(int enabled);
+/* SM budget of the persistent / wave-sized kernels (GEMM grids and static tile schedules, LayerNorm-backward waves): launches
+ * made while a limit n > 0 is set use at most n SMs.  The data-parallel trainer lowers it during the backward so that the NCCL
+ * all-reduce running beside it (NCCL_MAX_CTAS channels) does not push a 148-CTA persistent GEMM into a second wave.  0 = all. */
+int mtp_set_sm_limit(int n);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GEMM on tcgen05 tensor cores:  acc[m,n] = sum_k A[m,k] * B[n,k]   (bf16 in, fp32 accumulate in TMEM)

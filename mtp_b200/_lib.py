@@ -35,6 +35,7 @@ _SIGNATURES = {
     "mtp_gemm_bf16": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_int, c_void_p],
     "mtp_gemm_bf16_dual": [ctypes.POINTER(GemmDesc), ctypes.POINTER(GemmDesc), c_int, c_void_p],
     "mtp_set_pdl": [c_int],
+    "mtp_set_sm_limit": [c_int],
     "mtp_gemm_last_config": [],
     "mtp_gemm_set_debug": [c_void_p],
     "mtp_gemm_set_debug_mode": [c_int],

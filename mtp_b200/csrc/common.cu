@@ -1,5 +1,6 @@
 #include "common.h"
 
+#include <algorithm>
 #include <cstring>
 
 namespace mtp {
@@ -18,6 +19,9 @@ static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl(bool on) { g_pdl = on; }
 
+static int g_sm_limit = 0;
+void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+
 int num_sms() {
   static int cached = 0;
   if (cached == 0) {
@@ -26,9 +30,9 @@ int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
       cached = n;
     else
-      return 148;
+      return g_sm_limit > 0 ? std::min(148, g_sm_limit) : 148;
   }
-  return cached;
+  return g_sm_limit > 0 ? std::min(cached, g_sm_limit) : cached;
 }
 
 }  // namespace mtp
@@ -40,3 +44,7 @@ extern "C" int mtp_set_pdl(int enabled) {
   return MTP_OK;
 }
 extern "C" int mtp_num_sms(void) { return mtp::num_sms(); }
+extern "C" int mtp_set_sm_limit(int n) {
+  mtp::set_sm_limit(n);
+  return MTP_OK;
+}

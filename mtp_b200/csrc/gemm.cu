@@ -642,7 +642,7 @@ struct Config { int bn; bool cl2; Sched sched; };
 
 static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
   static std::map<std::vector<int>, Config> cache;
-  std::vector<int> key = {force_bn, np};
+  std::vector<int> key = {force_bn, np, num_sms()};
   for (int p = 0; p < np; ++p) { key.push_back(pr[p].M); key.push_back(pr[p].N); key.push_back(pr[p].K); key.push_back(pr[p].b_mn); }
   auto it = cache.find(key);
   if (it != cache.end()) return &it->second;

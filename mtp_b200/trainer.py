@@ -60,7 +60,7 @@ def synthetic_heads(feats: Sequence[torch.Tensor]):
 class PretrainStep:
     def __init__(self, model, lr=6e-5, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, max_norm=5.0, t_max=0, eta_min=0.0,
                  layer_decay_rate=0.9, name_prefix="encoder.", heads: Optional[Callable] = None, process_group=None,
-                 bucket_blocks=4, use_cuda_graph=False):
+                 bucket_blocks=4, use_cuda_graph=False, comm_sms=16):
         self.model = model
         self.heads = heads or synthetic_heads
         self.lr, self.eta_min, self.t_max = lr, eta_min, t_max
@@ -68,6 +68,9 @@ class PretrainStep:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.bucket_blocks = bucket_blocks
+        # SMs left to the NCCL all-reduce kernels while the backward runs beside them (set NCCL_MAX_CTAS to the same number):
+        # the persistent GEMM grids of the backward are sized for the remaining SMs instead of spilling into a second wave
+        self.comm_sms = comm_sms if self.world > 1 else 0
         dev = next(model.parameters()).device
         assert dev.type == "cuda", "PretrainStep needs the model on a CUDA device"
         self.dev = dev
@@ -152,8 +155,14 @@ class PretrainStep:
         self.flat_g[:self.small_end].zero_()
         self.G.touched = set()
         buckets = self._bucket_ranges() if self.world > 1 else {}
-        engine_bwd.backward_impl(m, x, ctx, douts, grad_store=self.G,
-                                 after_block=(lambda i: on_bucket([buckets[i]]) if i in buckets else None))
+        if self.comm_sms:
+            L.call("mtp_set_sm_limit", max(8, L.load().mtp_num_sms() - self.comm_sms))
+        try:
+            engine_bwd.backward_impl(m, x, ctx, douts, grad_store=self.G,
+                                     after_block=(lambda i: on_bucket([buckets[i]]) if i in buckets else None))
+        finally:
+            if self.comm_sms:
+                L.call("mtp_set_sm_limit", 0)
         if self.world > 1:
             # remaining pieces: the small region and the GEMM weights outside the blocks (patch embed, fpn)
             on_bucket(self.layout.tail_ranges(len(m.blocks), self.bucket_blocks))
