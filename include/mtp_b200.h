@@ -79,6 +79,8 @@ typedef struct mtp_epilogue {
   int ps_h, ps_w, ps_cout;
   float* colsum;          /* BF16 / BF16_DGELU: optional [N] fp32, += column sums of the stored values (the bias gradient of the
                              Linear whose cotangent this GEMM produces); 16-byte aligned */
+  float* sumsq;           /* F32: optional scalar, += sum of squares of the stored outputs (gradient-norm clipping without a
+                             separate pass over the weight gradients) */
   int b_static;           /* 1: operand B is NOT written by the kernels just before this one in the stream (weights, activations
                              saved earlier): its first tiles may be fetched before the programmatic-dependent-launch wait */
 } mtp_epilogue;
@@ -176,7 +178,8 @@ int mtp_sqloss_fwd_bwd(const void* feat_bf16, void* grad_bf16, float* loss, size
  * All parameter-gradient outputs (d_rel_pos_*, d_bias_table, dw_*, db_*) are ACCUMULATED into (+=).
  * mtp_rvsa_attn_bwd: dqkv_bf16 [T, 3C] is fully written (q slot directly; k|v slots from an fp32 scatter scratch);
  *   dparams [B*nWin, nH, 8] receives d(ox, oy, sx, sy, theta) (slots 5..7 zero); d_qkv_bias (optional, [3C]) += column sums
- *   of dqkv (the qkv bias gradient, [V]:390); workspace >= mtp_rvsa_bwd_workspace_bytes().
+ *   of dqkv (the qkv bias gradient, [V]:390); workspace >= mtp_rvsa_bwd_workspace_bytes().  scratch_zeroed = 1: the caller keeps
+ *   the workspace between calls, it is all-zero on entry (zero it once) and is handed back all-zero (no memset per call).
  * mtp_rvsa_sampling_bwd: backward of the pooled 1x1-conv heads ([V]:228-243): accumulates the six conv gradients and
  *   adds the AvgPool-path gradient into dyn_bf16 [T, C] (the cotangent of the LN1 output);
  *   workspace >= mtp_rvsa_sampling_bwd_workspace_bytes().
@@ -185,8 +188,8 @@ int mtp_sqloss_fwd_bwd(const void* feat_bf16, void* grad_bf16, float* loss, size
 size_t mtp_rvsa_bwd_workspace_bytes(int B, int h, int w, int C, int nH);
 int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,
                       const float* bias_table, const float* lse, const void* dout_bf16, void* dqkv_bf16, float* dparams,
-                      float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace, int B, int h,
-                      int w, int C, int nH, mtp_stream_t stream);
+                      float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace,
+                      int scratch_zeroed, int B, int h, int w, int C, int nH, mtp_stream_t stream);
 size_t mtp_rvsa_sampling_bwd_workspace_bytes(int B, int h, int w, int C, int nH);
 int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, const float* w_off, const float* w_scale,
                           const float* w_angle, float* dw_off, float* db_off, float* dw_scale, float* db_scale, float* dw_angle,

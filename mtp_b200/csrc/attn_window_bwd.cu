@@ -389,8 +389,8 @@ rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __r
 // dqkv[t, C + c] = bf16(dkv[t, c]) for c in [0, 2C); optionally colsum[0, 3C) += column sums of the finished bf16 dqkv (the qkv
 // bias gradient), reading the dq part the attention kernel wrote.  Thread = 4 consecutive columns, CTA = a band of rows.
 __global__ void __launch_bounds__(256)
-rvsa_kv_finalize_kernel(const float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int T, int C,
-                        int rows_per_cta) {
+rvsa_kv_finalize_kernel(float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int T, int C,
+                        int rows_per_cta, int rezero) {
   MTP_PDL_ENTRY();
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;       // column of dqkv
   if (c >= 3 * C) return;
@@ -403,7 +403,9 @@ rvsa_kv_finalize_kernel(const float* __restrict__ dkv, __nv_bfloat16* __restrict
     if (c < C) {
       u = *reinterpret_cast<const uint2*>(dqkv + (size_t)t * 3 * C + c);
     } else {
-      const float4 v = *reinterpret_cast<const float4*>(dkv + (size_t)t * 2 * C + (c - C));
+      float4* src = reinterpret_cast<float4*>(dkv + (size_t)t * 2 * C + (c - C));
+      const float4 v = *src;
+      if (rezero) *src = make_float4(0.f, 0.f, 0.f, 0.f);      // hand the scatter scratch back all-zero (no memset next time)
       u.x = pack_bf16x2(v.x, v.y);
       u.y = pack_bf16x2(v.z, v.w);
       *reinterpret_cast<uint2*>(dqkv + (size_t)t * 3 * C + c) = u;
@@ -517,8 +519,8 @@ extern "C" size_t mtp_rvsa_bwd_workspace_bytes(int B, int h, int w, int C, int n
 
 extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,
                                  const float* bias_table, const float* lse, const void* dout_bf16, void* dqkv_bf16, float* dparams,
-                                 float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace, int B,
-                                 int h, int w, int C, int nH, mtp_stream_t stream) {
+                                 float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace,
+                                 int scratch_zeroed, int B, int h, int w, int C, int nH, mtp_stream_t stream) {
   MTP_REQUIRE(qkv_bf16 && params && rel_pos_h && rel_pos_w && bias_table && lse && dout_bf16 && dqkv_bf16 && dparams &&
                   d_rel_pos_h && d_rel_pos_w && d_bias_table && workspace, "mtp_rvsa_attn_bwd: null pointer");
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD, "mtp_rvsa_attn_bwd: B=%d h=%d w=%d C=%d nH=%d unsupported", B, h, w, C, nH);
@@ -529,8 +531,11 @@ extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, cons
   float* part_table = part_rel + (size_t)n_cta * (2 * (2 * WS - 1) * HD);
   float* dkv = part_table + (size_t)n_cta * 169;
   const size_t T = (size_t)B * h * w;
-  cudaError_t e = cudaMemsetAsync(dkv, 0, T * 2 * C * sizeof(float), st);
-  if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa bwd memset: %s", cudaGetErrorString(e));
+  cudaError_t e = cudaSuccess;
+  if (!scratch_zeroed) {
+    e = cudaMemsetAsync(dkv, 0, T * 2 * C * sizeof(float), st);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa bwd memset: %s", cudaGetErrorString(e));
+  }
   int rc, n_rel_parts;
   if (nH % 2 == 0) {       // tensor-core path (two heads per UMMA tile); rel-pos partials are per CTA = per head pair
     rc = launch_rvsa_attn_bwd_tc(qkv_bf16, params, rel_pos_h, rel_pos_w, bias_table, lse, dout_bf16, dqkv_bf16, dkv, dparams, part_rel,
@@ -560,7 +565,7 @@ extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, cons
   const int gy = std::max(1, std::min(ceil_div((int)T, 8), 4 * num_sms() / gx));
   const int rpc = ceil_div((int)T, gy);
   (void)launch_k(rvsa_kv_finalize_kernel, dim3(gx, ceil_div((int)T, rpc)), 256, 0, st, dkv, reinterpret_cast<__nv_bfloat16*>(dqkv_bf16),
-                 d_qkv_bias, (int)T, C, rpc);
+                 d_qkv_bias, (int)T, C, rpc, scratch_zeroed);
   return check_launch("rvsa_kv_finalize_kernel");
 }
 

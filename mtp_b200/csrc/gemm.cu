@@ -49,6 +49,7 @@ struct EpiParams {
   int rows_per_group, pos_rows, accumulate, ps_h, ps_w, ps_cout;
   float* colsum;
   int b_static;
+  float* sumsq;
 };
 
 // ---- epilogue ---------------------------------------------------------------------------------------------------------
@@ -131,7 +132,7 @@ __device__ __forceinline__ void load_aux(const EpiParams& ep, AuxRegs& a, const 
 }
 
 __device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[4][8], const AuxRegs& a, const float* bias_s,
-                                                const int (&m)[4], const bool (&ok)[4], int n, int N, int lane) {
+                                                const int (&m)[4], const bool (&ok)[4], int n, int N, int lane, float& sq) {
   const int i = lane & 3;
   const bool f32 = mode_is_f32(ep.mode);
   if (bias_s != nullptr) {             // smem; columns >= N hold zeros
@@ -165,6 +166,7 @@ __device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[
             x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
           }
           *reinterpret_cast<float4*>(o + col) = x;
+          sq += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;      // sum of squares of the stored values (ep.sumsq: gradient norm)
         }
       }
     }
@@ -475,6 +477,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
     const int et = threadIdx.x - 64;        // 0..255 within the epilogue group
     int acc = 0;
     uint32_t acc_phase = 0;
+    float sq0 = 0.f, sq1 = 0.f;             // per problem: sum of squares of the fp32 outputs this thread stored
     for (int it = 0; it < n_items; ++it) {
       MTP_DECODE_ITEM(it)
       (void)k_blocks;
@@ -515,7 +518,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         float t[4][8];
         if (f32) lane_transpose<true>(v, t, lane);
         else lane_transpose<false>(v, t, lane);
-        epilogue_pieces(ep, t, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane);
+        epilogue_pieces(ep, t, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, item_ < items0 ? sq0 : sq1);
       }
       tc_fence_before();
       __syncwarp();
@@ -524,6 +527,14 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         else mbar_arrive(&tmem_empty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p0.ep.sumsq != nullptr) {           // one atomic per warp and launch
+      sq0 = warp_sum(sq0);
+      if (lane == 0 && sq0 != 0.f) atomicAdd(p0.ep.sumsq, sq0);
+    }
+    if (p1.tiles_m > 0 && p1.ep.sumsq != nullptr) {
+      sq1 = warp_sum(sq1);
+      if (lane == 0 && sq1 != 0.f) atomicAdd(p1.ep.sumsq, sq1);
     }
   }
 #undef MTP_DECODE_ITEM
@@ -744,6 +755,7 @@ static int validate_problem(const HostProblem& h) {
   if (ep.colsum != nullptr)
     MTP_REQUIRE((ep.mode == MTP_EPI_BF16 || ep.mode == MTP_EPI_BF16_DGELU) && ((uintptr_t)ep.colsum & 15) == 0,
                 "mtp_gemm_bf16: colsum needs a BF16 / BF16_DGELU epilogue and a 16-byte aligned pointer");
+  if (ep.sumsq != nullptr) MTP_REQUIRE(ep.mode == MTP_EPI_F32, "mtp_gemm_bf16: sumsq needs the F32 epilogue");
   if (ep.mode == MTP_EPI_BF16_PIXSHUF)
     MTP_REQUIRE(ep.ps_h > 0 && ep.ps_w > 0 && ep.ps_cout > 0 && ep.ps_cout % 32 == 0 && h.N == 4 * ep.ps_cout,
                 "mtp_gemm_bf16: bad pixel-shuffle geometry");
@@ -757,6 +769,7 @@ static EpiParams to_epi(const mtp_epilogue* ep) {
   p.accumulate = ep->accumulate; p.ps_h = ep->ps_h; p.ps_w = ep->ps_w; p.ps_cout = ep->ps_cout;
   p.colsum = ep->colsum;
   p.b_static = ep->b_static;
+  p.sumsq = ep->sumsq;
   return p;
 }
 

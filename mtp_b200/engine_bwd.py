@@ -35,12 +35,14 @@ class GradStore:
             self.views[name] = self.flat[o:o + p.numel()].view(p.shape)
         self.touched = set()
 
+    sumsq = None       # optional fp32 scalar: the wgrad GEMMs add the sum of squares of the weight gradients they store (trainer)
+
     def g(self, name):
         self.touched.add(name)
         return self.views[name]
 
 
-def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_BF16, aux=None, colsum=None):
+def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_BF16, aux=None, colsum=None, sumsq=None):
     """y = x W^T + b with x [T, n_in], W [n_out, n_in], cotangent g [T, n_out].
     dW = g^T x (both operands MN-major, K = T) and dx = g W (B operand MN-major) only share the input g: they run as ONE
     grouped launch whose tiles are spread over the SMs by a common schedule.  ``colsum``: fp32 [n_in] that receives the column
@@ -50,7 +52,7 @@ def _linear_bwd(g_bf16, x_bf16, w_bf16, dW, T, n_out, n_in, *, dgrad_mode=L.EPI_
     ops.gemm_dual(dict(A=g_bf16, B=w_bf16, M=T, N=n_in, K=n_out, out=dx, b_mn=True, mode=dgrad_mode, aux=aux, lda=n_out, ldb=n_in,
                        colsum=colsum, b_static=True),
                   dict(A=g_bf16, B=x_bf16, M=n_out, N=n_in, K=T, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=n_out, ldb=n_in, ldo=n_in,
-                       b_static=True))
+                       b_static=True, sumsq=sumsq))
     return dx
 
 
@@ -67,12 +69,12 @@ def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
     if g2 is None:
         g2 = ops.scale_cast_bf16(dx2, km, N, colsum=G.g(pre + "mlp.fc2.bias"))
     dh = _linear_bwd(g2, s["a"], d["fc2_w"], G.g(pre + "mlp.fc2.weight"), T, C, hid, dgrad_mode=L.EPI_BF16_DGELU, aux=s["hpre"],
-                     colsum=G.g(pre + "mlp.fc1.bias"))
-    dy2 = _linear_bwd(dh, s["y2"], d["fc1_w"], G.g(pre + "mlp.fc1.weight"), T, hid, C)
+                     colsum=G.g(pre + "mlp.fc1.bias"), sumsq=G.sumsq)
+    dy2 = _linear_bwd(dh, s["y2"], d["fc1_w"], G.g(pre + "mlp.fc1.weight"), T, hid, C, sumsq=G.sumsq)
     # ---- attention branch ([V]:508): its cotangent bf16(keep_attn * dx1) and the proj bias gradient come out of the LN backward
     dx1, g1 = ops.layernorm_bwd(dy2, s["x1"], s["mean2"], s["rstd2"], d["norm2_w"], None, dx2, G.g(pre + "norm2.weight"),
                                 G.g(pre + "norm2.bias"), cast=(ka, N, G.g(pre + "attn.proj.bias")))
-    do = _linear_bwd(g1, s["o"], d["proj_w"], G.g(pre + "attn.proj.weight"), T, C, C)
+    do = _linear_bwd(g1, s["o"], d["proj_w"], G.g(pre + "attn.proj.weight"), T, C, C, sumsq=G.sumsq)
     if d["window"]:
         dqkv, dparams = ops.rvsa_attn_bwd(s["qkv"], s["params"], d["rel_h"], d["rel_w"], d["table"], s["lse"], do,
                                           G.g(pre + "attn.rel_pos_h"), G.g(pre + "attn.rel_pos_w"),
@@ -84,7 +86,7 @@ def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
                                  G.g(pre + "attn.full_attn_rel_pos_h") if has_rel else None,
                                  G.g(pre + "attn.full_attn_rel_pos_w") if has_rel else None, B, gh, gw, nH)
         ops.colsum_bf16(dqkv, G.g(pre + "attn.qkv.bias"))
-    dy1 = _linear_bwd(dqkv, s["y1"], d["qkv_w"], G.g(pre + "attn.qkv.weight"), T, 3 * C, C)
+    dy1 = _linear_bwd(dqkv, s["y1"], d["qkv_w"], G.g(pre + "attn.qkv.weight"), T, 3 * C, C, sumsq=G.sumsq)
     if d["window"]:
         a = pre + "attn.sampling_"
         ops.rvsa_sampling_bwd(dparams, s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],
@@ -126,7 +128,7 @@ def _fpn_tap_backward(m, W, S, k, grad, dx, G, B, gh, gw):
         cs = torch.zeros(4 * C, device=dev, dtype=F32)
         ops.colsum_bf16(dv1, cs)
         dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
-        ops.gemm(dv1, sv["a1"], 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C)
+        ops.gemm(dv1, sv["a1"], 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C, sumsq=G.sumsq)
         _convt_grads(G, "fpn2.0.weight", "fpn2.0.bias", dWp, cs)
         ops.gemm(dv1, F_["fpn2_0_w"], T, C, 4 * C, dx, b_mn=True, mode=L.EPI_F32, accumulate=True, lda=4 * C, ldb=C)
         return
@@ -136,7 +138,7 @@ def _fpn_tap_backward(m, W, S, k, grad, dx, G, B, gh, gw):
     cs = torch.zeros(4 * C, device=dev, dtype=F32)
     ops.colsum_bf16(du2, cs)
     dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
-    ops.gemm(du2, sv["z"], 4 * C, C, 4 * T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C)
+    ops.gemm(du2, sv["z"], 4 * C, C, 4 * T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C, sumsq=G.sumsq)
     _convt_grads(G, "fpn1.3.weight", "fpn1.3.bias", dWp, cs)
     dz = torch.empty(4 * T, C, device=dev, dtype=BF16)
     ops.gemm(du2, F_["fpn1_3_w"], 4 * T, C, 4 * C, dz, b_mn=True, lda=4 * C, ldb=C)
@@ -145,7 +147,7 @@ def _fpn_tap_backward(m, W, S, k, grad, dx, G, B, gh, gw):
     cs = torch.zeros(4 * C, device=dev, dtype=F32)
     ops.colsum_bf16(du1, cs)
     dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
-    ops.gemm(du1, sv["a0"], 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C)
+    ops.gemm(du1, sv["a0"], 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C, sumsq=G.sumsq)
     _convt_grads(G, "fpn1.0.weight", "fpn1.0.bias", dWp, cs)
     ops.gemm(du1, F_["fpn1_0_w"], T, C, 4 * C, dx, b_mn=True, mode=L.EPI_F32, accumulate=True, lda=4 * C, ldb=C)
 
@@ -207,7 +209,7 @@ def backward_impl(m, x, S, grad_outs, grad_store=None, after_block=None):
             L.call("mtp_scale_cast_bf16", dx.data_ptr(), 0, 0, scratch.data_ptr(), dpos.data_ptr(), B, gh * gw * C, ops._stream())
         K0 = S["patches"].shape[1]
         ops.gemm(g, S["patches"], C, K0, T, G.g("patch_embed.proj.weight").view(C, K0), a_mn=True, b_mn=True, mode=L.EPI_F32,
-                 lda=C, ldb=K0, ldo=K0)
+                 lda=C, ldb=K0, ldo=K0, sumsq=G.sumsq)
 
     out = []
     for (name, p) in m.named_parameters():

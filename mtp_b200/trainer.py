@@ -122,6 +122,11 @@ class PretrainStep:
         self.G.flat = self.flat_g
         self.G.views = {n: self.flat_g[self.offsets[n]:self.offsets[n] + p.numel()].view(p.shape) for n, p in named}
         self.G.touched = set()
+        # world size 1: the wgrad GEMM epilogues accumulate the squared norm of the weight gradients they store, so the clip
+        # needs a reduction pass over the small region only (verified once against the full pass, see _forward_backward)
+        self.fused_norm = self.world == 1 and bool(self.max_norm and self.max_norm > 0)
+        self._norm_checked = False
+        self.G.sumsq = self.state[1:2] if self.fused_norm else None
         # ---- all-reduce buckets over the big region (in backward order) + one bucket for the small region
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.graph = None
@@ -155,6 +160,8 @@ class PretrainStep:
         self.flat_g[:self.small_end].zero_()
         self.G.touched = set()
         buckets = self._bucket_ranges() if self.world > 1 else {}
+        if self.fused_norm:                          # ++step, squared norm = 0 BEFORE the wgrad epilogues add to it
+            L.call("mtp_optim_step_begin", self.state.data_ptr(), ops._stream())
         if self.comm_sms:
             L.call("mtp_set_sm_limit", max(8, L.load().mtp_num_sms() - self.comm_sms))
         try:
@@ -166,13 +173,23 @@ class PretrainStep:
         if self.world > 1:
             # remaining pieces: the small region and the GEMM weights outside the blocks (patch embed, fpn)
             on_bucket(self.layout.tail_ranges(len(m.blocks), self.bucket_blocks))
+        if self.fused_norm and not self._norm_checked and not torch.cuda.is_current_stream_capturing():
+            self._norm_checked = True
+            fused = float(self.state[1].item()) + float((self.flat_g[:self.small_end].double() ** 2).sum().item())
+            full = float((self.flat_g.double() ** 2).sum().item())
+            if abs(fused - full) > 1e-3 * max(full, 1e-30):      # some weight gradient did not come out of a wgrad epilogue
+                self.fused_norm, self.G.sumsq = False, None
+                self.state[0] -= 1.0                 # the optimizer's own step_begin counts this step and recomputes the norm
         return loss
 
     def _optimizer(self):
         stream = ops._stream()
-        L.call("mtp_optim_step_begin", self.state.data_ptr(), stream)
-        if self.max_norm and self.max_norm > 0:
-            L.call("mtp_sumsq_f32", self.flat_g.data_ptr(), self.total, self.state.data_ptr() + 4, stream)
+        if self.fused_norm:
+            L.call("mtp_sumsq_f32", self.flat_g.data_ptr(), self.small_end, self.state.data_ptr() + 4, stream)
+        else:
+            L.call("mtp_optim_step_begin", self.state.data_ptr(), stream)
+            if self.max_norm and self.max_norm > 0:
+                L.call("mtp_sumsq_f32", self.flat_g.data_ptr(), self.total, self.state.data_ptr() + 4, stream)
         L.call("mtp_adamw_step", self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.flat_m.data_ptr(), self.flat_v.data_ptr(),
                self.flat_p16.data_ptr(), self.chunk_group.data_ptr(), self.group_lr.data_ptr(), self.group_wd.data_ptr(),
                self.state.data_ptr(), self.total, float(self.lr), float(self.eta_min), int(self.t_max), float(self.betas[0]),

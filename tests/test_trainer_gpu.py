@@ -68,3 +68,21 @@ def test_fused_stand_in_heads_match_torch():
     assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item())
     for f, g in zip(feats, grads):
         assert torch.equal(g, (f.float() * (1.0 / f.numel())).to(torch.bfloat16))
+
+
+def test_fused_gradient_norm_matches_full_pass():
+    """World size 1: squared gradient norm = wgrad-epilogue partial sums + small-region pass (mtp_epilogue.sumsq)."""
+    from mtp_b200 import _lib as L, ops
+    from mtp_b200.trainer import PretrainStep
+    g = load_golden("tiny224")
+    m = build_module("tiny224")
+    m.load_state_dict(g["sd"], strict=True)
+    m = m.cuda().train()
+    x = g["x"].cuda().to(torch.bfloat16)
+    tr = PretrainStep(m, lr=1e-4, max_norm=5.0)
+    assert tr.fused_norm
+    tr._forward_backward(x, lambda r: None)
+    assert tr.fused_norm, "the one-time check against the full reduction disabled the fused norm"
+    L.call("mtp_sumsq_f32", tr.flat_g.data_ptr(), tr.small_end, tr.state.data_ptr() + 4, ops._stream())
+    full = float((tr.flat_g.double() ** 2).sum().item())
+    assert abs(float(tr.state[1].item()) - full) <= 1e-4 * full
