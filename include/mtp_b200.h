@@ -122,6 +122,10 @@ int mtp_layernorm_bwd(const void* dy_bf16, const void* x, int x_is_bf16, const f
                       /* optional fused mtp_scale_cast_bf16 of dx (f32 variant only; all NULL/0 = off): cast_out_bf16[r,c] =
                        * bf16(dx[r,c] * cast_row_scale[r / cast_rows_per_group]), cast_colsum += its column sums */
                       const float* cast_row_scale, int cast_rows_per_group, void* cast_out_bf16, float* cast_colsum,
+                      /* optional (f32 variant): AvgPool backward of the RVSA sampling heads folded in -- dy[t, :] is used as
+                       * dy[t, :] + pool_add[window(t), :] / 49 for the [pool_h, pool_w] token grid (rows = B * pool_h * pool_w);
+                       * pool_add = the dpooled block mtp_rvsa_sampling_bwd leaves in its workspace */
+                      const float* pool_add, int pool_h, int pool_w,
                       int rows, int C, int fused_gelu, mtp_stream_t stream);
 /* out_bf16[r,c] = in[r,c] * row_scale[r / rows_per_group] (DropPath backward, [V]:31-39); colsum (optional) += column sums
  * of the scaled values (bias gradient of the Linear that produced the branch). */
@@ -181,7 +185,8 @@ int mtp_sqloss_fwd_bwd(const void* feat_bf16, void* grad_bf16, float* loss, size
  *   of dqkv (the qkv bias gradient, [V]:390); workspace >= mtp_rvsa_bwd_workspace_bytes().  scratch_zeroed = 1: the caller keeps
  *   the workspace between calls, it is all-zero on entry (zero it once) and is handed back all-zero (no memset per call).
  * mtp_rvsa_sampling_bwd: backward of the pooled 1x1-conv heads ([V]:228-243): accumulates the six conv gradients and
- *   adds the AvgPool-path gradient into dyn_bf16 [T, C] (the cotangent of the LN1 output);
+ *   adds the AvgPool-path gradient into dyn_bf16 [T, C] (the cotangent of the LN1 output) -- or, with dyn_bf16 = NULL, leaves
+ *   dpooled [B*nWin, C] fp32 at workspace + B*nWin*5*nH floats for mtp_layernorm_bwd(pool_add = ...) to fold in;
  *   workspace >= mtp_rvsa_sampling_bwd_workspace_bytes().
  * mtp_full_attn_bwd: dqkv_bf16 fully written; workspace >= mtp_full_attn_bwd_workspace_bytes().
  * ------------------------------------------------------------------------------------------------------------- */

@@ -41,7 +41,7 @@ _SIGNATURES = {
     "mtp_gemm_set_debug_mode": [c_int],
     "mtp_layernorm_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],
     "mtp_layernorm_bwd": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                          c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+                          c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_scale_cast_bf16": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "mtp_colsum_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "mtp_cast_f32_bf16": [c_void_p, c_void_p, c_size_t, c_void_p],

@@ -574,7 +574,7 @@ extern "C" int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, 
                                      float* dw_angle, float* db_angle, void* dyn_bf16, void* workspace, int B, int h, int w, int C,
                                      int nH, mtp_stream_t stream) {
   MTP_REQUIRE(dparams && pooled && w_off && w_scale && w_angle && dw_off && db_off && dw_scale && db_scale && dw_angle && db_angle &&
-                  dyn_bf16 && workspace, "mtp_rvsa_sampling_bwd: null pointer");
+                  workspace, "mtp_rvsa_sampling_bwd: null pointer");
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && nH <= 64, "mtp_rvsa_sampling_bwd: unsupported geometry");
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -587,7 +587,7 @@ extern "C" int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, 
   (void)launch_k(rvsa_sampling_wgrad_kernel, dim3(ceil_div(C, 256), 5 * nH), 256, 0, st, g_out, pooled, dw_off, db_off, dw_scale, db_scale, dw_angle,
                                                                              db_angle, n_bw, nH, C);
   rc = check_launch("rvsa_sampling_wgrad_kernel");
-  if (rc) return rc;
+  if (rc || dyn_bf16 == nullptr) return rc;      // no dyn: the caller hands dpooled (workspace + n_bw*5*nH floats) to mtp_layernorm_bwd
   const size_t total = (size_t)B * h * w * (C / 4);
   const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 8);
   (void)launch_k(rvsa_pool_bwd_add_kernel, grid, 256, 0, st, dpooled, reinterpret_cast<__nv_bfloat16*>(dyn_bf16), g);

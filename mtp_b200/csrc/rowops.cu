@@ -4,6 +4,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "rvsa_geom.cuh"
 
 namespace mtp {
 
@@ -92,7 +93,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, c
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
               const float* __restrict__ dres, TDx* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
               const float* __restrict__ row_scale, int rows_per_group, __nv_bfloat16* __restrict__ g16, float* __restrict__ colsum16,
-              int rows, int rows_per_cta) {
+              const float* __restrict__ pool_add, const RvsaGeom pg, int rows, int rows_per_cta) {
   constexpr int C = NV * 128;
   extern __shared__ float red[];          // [warps][C]
   MTP_PDL_ENTRY();
@@ -108,13 +109,28 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, c
     const float mu = mean[row], rs = rstd[row];
     const TIn* xr = x + (size_t)row * C;
     const __nv_bfloat16* dyr = dy + (size_t)row * C;
-    float4 xh[NV], g[NV];
+    // AvgPool backward of the RVSA sampling heads: every real token of a window receives dpooled[window] / 49 on top of dy
+    const float* pa = nullptr;
+    if (pool_add != nullptr) {
+      const int xw = row % pg.w, yh = (row / pg.w) % pg.h, b = row / (pg.w * pg.h);
+      pa = pool_add + (size_t)((b * pg.nh + (yh + pg.pt) / WS) * pg.nw + (xw + pg.pl) / WS) * C;
+    }
+    float4 xh[NV], g[NV], rres[NV];
     float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {             // the residual-path cotangent is fetched with the other operands (one latency round)
+      if (dres != nullptr) rres[i] = *reinterpret_cast<const float4*>(dres + (size_t)row * C + (i * 32 + lane) * 4);
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       const float4 xv = Vec4<TIn>::load(xr + c);
       float4 d = Vec4<__nv_bfloat16>::load(dyr + c);
+      if (pa != nullptr) {
+        const float4 pv = *reinterpret_cast<const float4*>(pa + c);
+        const float inv = 1.0f / (WS * WS);
+        d.x += pv.x * inv; d.y += pv.y * inv; d.z += pv.z * inv; d.w += pv.w * inv;
+      }
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       if (GELU) {
@@ -143,7 +159,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, c
       o.z = rs * (g[i].z - s1 - xh[i].z * s2);
       o.w = rs * (g[i].w - s1 - xh[i].w * s2);
       if (dres != nullptr) {
-        const float4 r = *reinterpret_cast<const float4*>(dres + (size_t)row * C + c);
+        const float4 r = rres[i];
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       Vec4<TDx>::store(dxr + c, o);
@@ -249,7 +265,7 @@ static int ln_fwd_dispatch(const void* x, const float* g, const float* b, void* 
 template <typename TIn, typename TDx, bool GELU, bool CAST>
 static int ln_bwd_dispatch(const void* dy, const void* x, const float* mean, const float* rstd, const float* g, const float* b,
                            const float* dres, void* dx, float* dgamma, float* dbeta, const float* row_scale, int rows_per_group,
-                           void* g16, float* colsum16, int rows, int C, cudaStream_t st) {
+                           void* g16, float* colsum16, const float* pool_add, const RvsaGeom& pg, int rows, int C, cudaStream_t st) {
   // one wave: every SM gets one CTA whose warps take one row each (rows <= 12 * SMs); beyond that CTAs loop over rows
   const int per_sm = ceil_div(rows, num_sms());
   const int warps = std::max(4, std::min(per_sm, LN_BWD_MAX_WARPS));
@@ -272,7 +288,7 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* mean, con
       attr = true;                                                                                                         \
     }                                                                                                                      \
     e = launch_k(kern, grid, block, smem, st, dyp, xp, mean, rstd, g, b, dres, dxp, dgamma, dbeta, row_scale,              \
-                 rows_per_group, g16p, colsum16, rows, rows_per_cta);                                                      \
+                 rows_per_group, g16p, colsum16, pool_add, pg, rows, rows_per_cta);                                        \
   } break;
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
 #undef LN_CASE
@@ -302,24 +318,30 @@ extern "C" int mtp_layernorm_fwd(const void* x, int x_is_bf16, const float* gamm
 extern "C" int mtp_layernorm_bwd(const void* dy_bf16, const void* x, int x_is_bf16, const float* mean, const float* rstd,
                                  const float* gamma, const float* beta, const float* dres_f32, void* dx, int dx_is_bf16,
                                  float* dgamma, float* dbeta, const float* cast_row_scale, int cast_rows_per_group,
-                                 void* cast_out_bf16, float* cast_colsum, int rows, int C, int fused_gelu, mtp_stream_t stream) {
+                                 void* cast_out_bf16, float* cast_colsum, const float* pool_add, int pool_h, int pool_w, int rows, int C,
+                                 int fused_gelu, mtp_stream_t stream) {
   MTP_REQUIRE(dy_bf16 && x && mean && rstd && gamma && dx && dgamma && dbeta, "mtp_layernorm_bwd: null pointer");
   MTP_REQUIRE(rows > 0 && C % 128 == 0 && C <= 1024, "mtp_layernorm_bwd: rows=%d C=%d unsupported", rows, C);
   MTP_REQUIRE(!fused_gelu || beta, "mtp_layernorm_bwd: GELU variant needs beta");
   MTP_REQUIRE(!cast_row_scale || cast_rows_per_group > 0, "mtp_layernorm_bwd: cast_rows_per_group");
   MTP_REQUIRE(cast_out_bf16 || !cast_colsum, "mtp_layernorm_bwd: cast_colsum needs cast_out_bf16");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  RvsaGeom pg = make_rvsa_geom(1, WS, WS, C, 1);
+  if (pool_add != nullptr) {
+    MTP_REQUIRE(pool_h >= WS && pool_w >= WS && rows % (pool_h * pool_w) == 0, "mtp_layernorm_bwd: pool_add needs rows = B * pool_h * pool_w");
+    pg = make_rvsa_geom(rows / (pool_h * pool_w), pool_h, pool_w, C, 1);
+  }
   if (!x_is_bf16 && !dx_is_bf16 && !fused_gelu) {
     if (cast_out_bf16)
       return ln_bwd_dispatch<float, float, false, true>(dy_bf16, x, mean, rstd, gamma, beta, dres_f32, dx, dgamma, dbeta, cast_row_scale,
-                                                        cast_rows_per_group, cast_out_bf16, cast_colsum, rows, C, st);
+                                                        cast_rows_per_group, cast_out_bf16, cast_colsum, pool_add, pg, rows, C, st);
     return ln_bwd_dispatch<float, float, false, false>(dy_bf16, x, mean, rstd, gamma, beta, dres_f32, dx, dgamma, dbeta, nullptr, 0,
-                                                       nullptr, nullptr, rows, C, st);
+                                                       nullptr, nullptr, pool_add, pg, rows, C, st);
   }
-  MTP_REQUIRE(!cast_out_bf16, "mtp_layernorm_bwd: the fused cast is only available for the (f32 x, f32 dx, no gelu) variant");
+  MTP_REQUIRE(!cast_out_bf16 && !pool_add, "mtp_layernorm_bwd: the fused cast / pool_add are only available for the (f32 x, f32 dx, no gelu) variant");
   if (x_is_bf16 && dx_is_bf16 && fused_gelu)
     return ln_bwd_dispatch<__nv_bfloat16, __nv_bfloat16, true, false>(dy_bf16, x, mean, rstd, gamma, beta, dres_f32, dx, dgamma, dbeta,
-                                                                      nullptr, 0, nullptr, nullptr, rows, C, st);
+                                                                      nullptr, 0, nullptr, nullptr, nullptr, pg, rows, C, st);
   return set_error(MTP_ERR_INVALID, "mtp_layernorm_bwd: unsupported variant (x_bf16=%d dx_bf16=%d gelu=%d)", x_is_bf16, dx_is_bf16, fused_gelu);
 }
 

@@ -11,12 +11,15 @@ accumulates straight into the residual-stream gradient).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
 from . import engine, ops
 
 BF16, F32 = torch.bfloat16, torch.float32
+_POOL_FUSE = os.environ.get("MTP_POOL_FUSE", "1") != "0"      # A/B switch: 0 = separate rvsa_pool_bwd_add kernel
 
 
 class GradStore:
@@ -87,16 +90,20 @@ def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
                                  G.g(pre + "attn.full_attn_rel_pos_w") if has_rel else None, B, gh, gw, nH)
         ops.colsum_bf16(dqkv, G.g(pre + "attn.qkv.bias"))
     dy1 = _linear_bwd(dqkv, s["y1"], d["qkv_w"], G.g(pre + "attn.qkv.weight"), T, 3 * C, C, sumsq=G.sumsq)
-    if d["window"]:
+    pool = None
+    if d["window"]:                       # the pooled (AvgPool) path of the sampling heads joins dy1 inside the LayerNorm backward
         a = pre + "attn.sampling_"
-        ops.rvsa_sampling_bwd(dparams, s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],
-                              G.g(a + "offsets.2.weight"), G.g(a + "offsets.2.bias"), G.g(a + "scales.2.weight"), G.g(a + "scales.2.bias"),
-                              G.g(a + "angles.2.weight"), G.g(a + "angles.2.bias"), dy1, B, gh, gw, nH)
+        dpooled = ops.rvsa_sampling_bwd(dparams, s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],
+                                        G.g(a + "offsets.2.weight"), G.g(a + "offsets.2.bias"), G.g(a + "scales.2.weight"),
+                                        G.g(a + "scales.2.bias"), G.g(a + "angles.2.weight"), G.g(a + "angles.2.bias"),
+                                        None if _POOL_FUSE else dy1, B, gh, gw, nH)
+        pool = (dpooled, gh, gw) if _POOL_FUSE else None
     if nxt is None:
-        dx0 = ops.layernorm_bwd(dy1, s["x0"], s["mean1"], s["rstd1"], d["norm1_w"], None, dx1, G.g(pre + "norm1.weight"), G.g(pre + "norm1.bias"))
+        dx0 = ops.layernorm_bwd(dy1, s["x0"], s["mean1"], s["rstd1"], d["norm1_w"], None, dx1, G.g(pre + "norm1.weight"), G.g(pre + "norm1.bias"),
+                                pool_add=pool)
         return dx0, None
     return ops.layernorm_bwd(dy1, s["x0"], s["mean1"], s["rstd1"], d["norm1_w"], None, dx1, G.g(pre + "norm1.weight"),
-                             G.g(pre + "norm1.bias"), cast=(nxt[0], N, nxt[1]))
+                             G.g(pre + "norm1.bias"), cast=(nxt[0], N, nxt[1]), pool_add=pool)
 
 
 def _convt_grads(G, wname, bname, dWp, colsum4):

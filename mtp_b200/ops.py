@@ -75,8 +75,9 @@ def layernorm_fwd(x, gamma, beta, eps=1e-6, gelu=False, save_stats=True):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, beta, dres, dgamma, dbeta, gelu=False, cast=None):
-    """``cast=(row_scale|None, rows_per_group, colsum|None)``: also return bf16(row_scale * dx) (+ its column sums into colsum)."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, beta, dres, dgamma, dbeta, gelu=False, cast=None, pool_add=None):
+    """``cast=(row_scale|None, rows_per_group, colsum|None)``: also return bf16(row_scale * dx) (+ its column sums into colsum).
+    ``pool_add=(dpooled, h, w)``: fold the AvgPool backward of the RVSA sampling heads into dy."""
     rows, C = x.shape
     dx = torch.empty(rows, C, device=x.device, dtype=x.dtype)
     g16 = None
@@ -86,7 +87,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, beta, dres, dgamma, dbeta, gelu=Fals
         g16 = torch.empty(rows, C, device=x.device, dtype=BF16)
     L.call("mtp_layernorm_bwd", dy.data_ptr(), x.data_ptr(), int(x.dtype == BF16), mean.data_ptr(), rstd.data_ptr(),
            gamma.data_ptr(), _p(beta), _p(dres), dx.data_ptr(), int(dx.dtype == BF16), dgamma.data_ptr(), dbeta.data_ptr(),
-           _p(sc), int(rpg), _p(g16), _p(cs), rows, C, int(gelu), _stream())
+           _p(sc), int(rpg), _p(g16), _p(cs), _p(pool_add[0]) if pool_add else 0, int(pool_add[1]) if pool_add else 0,
+           int(pool_add[2]) if pool_add else 0, rows, C, int(gelu), _stream())
     return dx if cast is None else (dx, g16)
 
 
@@ -197,12 +199,16 @@ def rvsa_attn_bwd(qkv, params, rel_h, rel_w, table, lse, dout, d_rel_h, d_rel_w,
 
 
 def rvsa_sampling_bwd(dparams, pooled, w_off, w_sc, w_ang, dw_off, db_off, dw_sc, db_sc, dw_ang, db_ang, dyn, B, h, w, nH):
+    """``dyn=None``: returns dpooled [B*nWin, C] (fp32) for ``layernorm_bwd(pool_add=...)`` instead of adding it into dyn."""
     C = pooled.shape[-1]
     ws = _workspace(L.load().mtp_rvsa_sampling_bwd_workspace_bytes(B, h, w, C, nH), pooled.device)
     L.call("mtp_rvsa_sampling_bwd", dparams.data_ptr(), pooled.data_ptr(), w_off.data_ptr(), w_sc.data_ptr(), w_ang.data_ptr(),
            dw_off.data_ptr(), db_off.data_ptr(), dw_sc.data_ptr(), db_sc.data_ptr(), dw_ang.data_ptr(), db_ang.data_ptr(),
-           dyn.data_ptr(), ws.data_ptr(), B, h, w, C, nH, _stream())
-    return dyn
+           _p(dyn), ws.data_ptr(), B, h, w, C, nH, _stream())
+    if dyn is not None:
+        return dyn
+    n_bw = pooled.shape[0]
+    return ws[n_bw * 5 * nH: n_bw * 5 * nH + n_bw * C].view(n_bw, C)
 
 
 def full_attn_bwd(qkv, rel_h, rel_w, lse, out, dout, d_rel_h, d_rel_w, B, gh, gw, nH):

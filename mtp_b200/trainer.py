@@ -10,6 +10,8 @@ objective the parity tests use.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Callable, List, Optional, Sequence
 
@@ -124,7 +126,7 @@ class PretrainStep:
         self.G.touched = set()
         # world size 1: the wgrad GEMM epilogues accumulate the squared norm of the weight gradients they store, so the clip
         # needs a reduction pass over the small region only (verified once against the full pass, see _forward_backward)
-        self.fused_norm = self.world == 1 and bool(self.max_norm and self.max_norm > 0)
+        self.fused_norm = self.world == 1 and bool(self.max_norm and self.max_norm > 0) and os.environ.get("MTP_FUSED_NORM", "1") != "0"
         self._norm_checked = False
         self.G.sumsq = self.state[1:2] if self.fused_norm else None
         # ---- all-reduce buckets over the big region (in backward order) + one bucket for the small region

@@ -96,3 +96,33 @@ def test_layernorm_bwd_fused_cast_matches_scale_cast(rows):
     cs3 = torch.zeros(C, device="cuda")
     _, g16b = ops.layernorm_bwd(dy, x, mean, rstd, g, None, dres, dg, db, cast=(None, 0, cs3))
     assert torch.equal(g16b, dx2.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("grid", [14, 10])
+def test_layernorm_bwd_pool_add(grid):
+    """pool_add folds dpooled[window(t)] / 49 (AvgPool backward of the RVSA sampling heads, zero-padded 7x7 windows) into dy."""
+    from mtp_b200 import ops
+    torch.manual_seed(7)
+    B, C = 2, 256
+    h = w = grid
+    rows = B * h * w
+    pad = (7 - grid % 7) % 7
+    pt = pad // 2
+    nwin = (grid + pad) // 7
+    x = torch.randn(rows, C, device="cuda")
+    g = torch.randn(C, device="cuda") * 0.2 + 1
+    _, mean, rstd = ops.layernorm_fwd(x, g, torch.zeros_like(g))
+    dy = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
+    dp = torch.randn(B * nwin * nwin, C, device="cuda")
+    t = torch.arange(rows, device="cuda")
+    xx, yy, bb = t % w, (t // w) % h, t // (w * h)
+    win = (bb * nwin + (yy + pt) // 7) * nwin + (xx + pt) // 7
+    dy_eff = dy.float() + dp[win] / 49.0
+    xr = x.clone().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (C,), gr, torch.zeros_like(g), 1e-6).backward(dy_eff)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = ops.layernorm_bwd(dy, x, mean, rstd, g, None, None, dg, db, pool_add=(dp, h, w))
+    assert (dx - xr.grad).abs().max().item() < 1e-3
+    assert (dg - gr.grad).abs().max().item() < 1e-3 * max(1.0, gr.grad.abs().max().item())
+    assert (db - dy_eff.sum(0)).abs().max().item() < 1e-3 * max(1.0, dy_eff.sum(0).abs().max().item())
