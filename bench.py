@@ -192,7 +192,16 @@ def gemm_profile(trainer, x):
     """One eager (non-graph) step with CUDA events around every GEMM launch on the launching stream."""
     from mtp_b200 import ops
     recs = []
+    abytes = [0.0]
     orig = ops.gemm
+
+    def alg_bytes(M, N, K, out, aux=None, out2=None, **_):      # operands read once + outputs written once
+        b = 2.0 * (M * K + N * K) + out.element_size() * M * N
+        if aux is not None:
+            b += aux.element_size() * M * N
+        if out2 is not None:
+            b += out2.element_size() * M * N
+        return b
 
     def timed(A, B, M, N, K, out, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -200,6 +209,7 @@ def gemm_profile(trainer, x):
         r = orig(A, B, M, N, K, out, **kw)
         e1.record()
         recs.append((e0, e1, 2.0 * M * N * K))
+        abytes[0] += alg_bytes(M, N, K, out, **kw)
         return r
     orig_dual = ops.gemm_dual
 
@@ -209,6 +219,7 @@ def gemm_profile(trainer, x):
         r = orig_dual(g0, g1, force_bn)
         e1.record()
         recs.append((e0, e1, 2.0 * (g0["M"] * g0["N"] * g0["K"] + g1["M"] * g1["N"] * g1["K"])))
+        abytes[0] += sum(alg_bytes(g["M"], g["N"], g["K"], g["out"], aux=g.get("aux"), out2=g.get("out2")) for g in (g0, g1))
         return r
     ops.gemm = timed
     ops.gemm_dual = timed_dual
@@ -220,7 +231,7 @@ def gemm_profile(trainer, x):
         ops.gemm_dual = orig_dual
     ms = sum(a.elapsed_time(b) for a, b, _ in recs)
     flops = sum(f for _, _, f in recs)
-    return len(recs), ms, flops
+    return len(recs), ms, flops, abytes[0]
 
 
 def count_launches(trainer, x):
@@ -281,7 +292,7 @@ def main():
         trainer.step(x)
     torch.cuda.synchronize()
     launches = count_launches(trainer, x)
-    n_gemm, gemm_ms, gemm_flops = gemm_profile(trainer, x)
+    n_gemm, gemm_ms, gemm_flops, gemm_alg_bytes = gemm_profile(trainer, x)
     trainer.use_cuda_graph = trainer_eager_graph
 
     # ---- device-resident timing
@@ -344,6 +355,14 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        # DRAM traffic of the GEMM launches of one step, from the committed ncu pass (profiles/: dram__bytes_read/write.sum per launch)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_dram.json")))
+            per_launch = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / max(1, tj["gemm_launches"])
+            traffic = per_launch * n_gemm      # bytes per step over all GEMM launches (same unit of work as `achieved`)
+        except Exception:
+            pass
         step_tflops = 3.0 * FWD_GFLOP_PER_IMG * (value / world) / 1e3          # per GPU, training step = 3 x forward
         gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         line = {
@@ -358,7 +377,7 @@ def main():
             "gpu_launches": launches * args.steps,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of one step)", "achieved": gemm_tflops,
                          "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": (gemm_tflops / pk["tf_burst"]) if gemm_tflops else None,
-                         "traffic": None, "peak_source": pk["src"] + " (burst cuBLAS bf16)", "gemm_launches_per_step": n_gemm,
+                         "traffic": traffic, "algorithmic_bytes_per_step": gemm_alg_bytes, "peak_source": pk["src"] + " (burst cuBLAS bf16)", "gemm_launches_per_step": n_gemm,
                          "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_step if ms_step else None,
                          "step_tflops_per_gpu": step_tflops, "step_frac_of_sustained_peak": step_tflops / pk["tf_sustained"]},
             "clocks": clocks,
