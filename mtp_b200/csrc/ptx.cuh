@@ -209,11 +209,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, 
 }
 
 // ------------------------------------------------------------------ small math helpers
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-form GELU ([V]:56-57 nn.GELU default) and its derivative.  erf(x / sqrt 2) by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7,
+// far below the bf16 rounding of every consumer): one reciprocal, one exp and five FMAs instead of libm's branchy erff -- the
+// GELU / GELU' epilogues of the fc1 / fc2-dgrad GEMMs were ALU-bound on it (128 x 256 elements per tile and 16 k-blocks of
+// mainloop to hide them behind).  exp(-x^2/2) is shared between the erf tail and the Gaussian density of the derivative.
+__device__ __forceinline__ void gelu_terms(float x, float& erf_v, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));      // MUFU.RCP (2 ulp): plenty here
+  e = __expf(-z * z);
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  erf_v = copysignf(fmaf(-poly, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float er, e;
+  gelu_terms(x, er, e);
+  return 0.5f * x * (1.0f + er);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float er, e;
+  gelu_terms(x, er, e);
+  return fmaf(x * 0.39894228040143267794f, e, 0.5f * (1.0f + er));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

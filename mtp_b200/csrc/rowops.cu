@@ -170,23 +170,27 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, c
       }
     }
   }
-  // cross-warp reduction of the column sums
+  // cross-warp reduction of the column sums: all (2 or 3) arrays go through shared memory at once ([array][warp][C]); a thread
+  // then owns 4 consecutive columns of one array and issues ONE vector atomic for them
+  constexpr int NARR = CAST ? 3 : 2;
 #pragma unroll
-  for (int pass = 0; pass < (CAST ? 3 : 2); ++pass) {
-    float* dst = pass == 0 ? dgamma : pass == 1 ? dbeta : colsum16;
-    if (dst == nullptr) continue;          // uniform
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      *reinterpret_cast<float4*>(&red[warp * C + c]) = pass == 0 ? ag[i] : pass == 1 ? ab[i] : ac[CAST ? i : 0];
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    *reinterpret_cast<float4*>(&red[(0 * n_warps + warp) * C + c]) = ag[i];
+    *reinterpret_cast<float4*>(&red[(1 * n_warps + warp) * C + c]) = ab[i];
+    if (CAST) *reinterpret_cast<float4*>(&red[(2 * n_warps + warp) * C + c]) = ac[CAST ? i : 0];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NARR * (C / 4); e += blockDim.x) {
+    const int arr = e / (C / 4), c = (e % (C / 4)) * 4;
+    float* dst = arr == 0 ? dgamma : arr == 1 ? dbeta : colsum16;
+    if (dst == nullptr) continue;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < n_warps; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(&red[(arr * n_warps + w) * C + c]);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float t = 0.f;
-      for (int w = 0; w < n_warps; ++w) t += red[w * C + c];
-      atomicAdd(dst + c, t);
-    }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
   }
 }
 
@@ -208,10 +212,8 @@ scale_cast_kernel(const float* __restrict__ in, const float* __restrict__ row_sc
     Vec4<__nv_bfloat16>::store(out + (size_t)r * C + c, v);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  if (colsum) {
-    atomicAdd(colsum + c, acc.x); atomicAdd(colsum + c + 1, acc.y);
-    atomicAdd(colsum + c + 2, acc.z); atomicAdd(colsum + c + 3, acc.w);
-  }
+  if (colsum)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + c), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
 }
 
 // colsum[c] += sum_r in_bf16[r, c]
@@ -226,8 +228,7 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ col
     const float4 v = Vec4<__nv_bfloat16>::load(in + (size_t)r * ld + c);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  atomicAdd(colsum + c, acc.x); atomicAdd(colsum + c + 1, acc.y);
-  atomicAdd(colsum + c + 2, acc.z); atomicAdd(colsum + c + 3, acc.w);
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + c), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n4) {
@@ -271,7 +272,7 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* mean, con
   const int warps = std::max(4, std::min(per_sm, LN_BWD_MAX_WARPS));
   const int rows_per_cta = std::max(per_sm, warps);
   const dim3 grid(ceil_div(rows, rows_per_cta)), block(warps * 32);
-  const size_t smem = (size_t)warps * C * sizeof(float);
+  const size_t smem = (size_t)(CAST ? 3 : 2) * warps * C * sizeof(float);
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
   const TIn* xp = reinterpret_cast<const TIn*>(x);
   TDx* dxp = reinterpret_cast<TDx*>(dx);
@@ -283,7 +284,7 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* mean, con
     auto kern = ln_bwd_kernel<TIn, TDx, NV, GELU, CAST>;                                                                   \
     static bool attr = false;                                                                                              \
     if (!attr && smem > 48 * 1024) {                                                                                       \
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_BWD_MAX_WARPS * NV * 128 * 4);        \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LN_BWD_MAX_WARPS * NV * 128 * 4);    \
       if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "ln_bwd smem attr: %s", cudaGetErrorString(e));                 \
       attr = true;                                                                                                         \
     }                                                                                                                      \
