@@ -465,7 +465,7 @@ rvsa_sampling_wgrad_kernel(const float* __restrict__ g_out, const float* __restr
   else { dw = dw_ang; db = db_ang; oo = o - 4 * nH; }
   if (c < C) {
     float s = 0.f;
-#pragma unroll 8
+#pragma unroll 4
     for (int bw = 0; bw < n_bw; ++bw) {
       const float p = pooled[(size_t)bw * C + c];
       s += g_out[(size_t)bw * 5 * nH + o] * (p >= 0.f ? p : 0.01f * p);
