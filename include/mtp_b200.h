@@ -98,6 +98,11 @@ typedef struct mtp_gemm_desc {
   const mtp_epilogue* ep;
 } mtp_gemm_desc;
 int mtp_gemm_bf16_dual(const mtp_gemm_desc* g0, const mtp_gemm_desc* g1, int force_bn, mtp_stream_t stream);
+/* Host-only planning (no CUDA call, works without a GPU): the tile configuration (width + 1000 for pairs), CTA count and modelled
+ * makespan in SM cycles the scheduler picks for one problem (M1 = 0) or a grouped pair, after checking that its work schedule
+ * assigns every tile exactly once. */
+int mtp_gemm_plan(int M0, int N0, int K0, int b0_mn_major, int M1, int N1, int K1, int b1_mn_major, int force_bn, int* out_config,
+                  int* out_ctas, double* out_cycles);
 /* Tile configuration the heuristic (or force_bn) selected for the most recent GEMM launch: width + 1000 for cta_group::2 pairs. */
 int mtp_gemm_last_config(void);
 /* Tuning aid: device buffer [grid][8] of int64 that receives per-CTA globaltimer stamps of the pipeline phases (NULL = off). */

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "mtp_set_pdl": [c_int],
     "mtp_set_sm_limit": [c_int],
     "mtp_gemm_last_config": [],
+    "mtp_gemm_plan": [c_int] * 9 + [ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double)],
     "mtp_gemm_set_debug": [c_void_p],
     "mtp_gemm_set_debug_mode": [c_int],
     "mtp_layernorm_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],

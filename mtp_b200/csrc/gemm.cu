@@ -799,9 +799,65 @@ static int run_grouped(const HostProblem* pr, int np, int force_bn, cudaStream_t
   return set_error(MTP_ERR_INVALID, "mtp_gemm_bf16: unsupported tile width %d", cfg->bn);
 }
 
+// Host-only planning (no CUDA call): the tile configuration the heuristic picks and a self-check of the work schedule --
+// every tile of every problem is assigned to exactly one slot, no slot exceeds the by-value list.
+static int plan_grouped(const HostProblem* pr, int np, int force_bn, int* out_config, int* out_ctas, double* out_cycles) {
+  for (int p = 0; p < np; ++p) {
+    int rc = validate_problem(pr[p]);
+    if (rc) return rc;
+  }
+  const Config* cfg = get_config(pr, np, force_bn);
+  if (cfg == nullptr) return set_error(MTP_ERR_INVALID, "mtp_gemm_plan: no valid tile configuration (force_bn=%d)", force_bn);
+  const int slots = cfg->cl2 ? num_sms() / 2 : num_sms();
+  int total = 0;
+  for (int p = 0; p < np; ++p) {
+    const int tiles_m = ceil_div(pr[p].M, BM), tiles_n = ceil_div(pr[p].N, cfg->bn);
+    total += (cfg->cl2 ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
+  }
+  std::vector<int> seen(total, 0);
+  int used = 0;
+  const Sched& sc = cfg->sched;
+  if (sc.strided_total > 0) {
+    MTP_REQUIRE(sc.strided_total == total, "mtp_gemm_plan: strided schedule covers %d of %d items", sc.strided_total, total);
+    for (int s = 0; s < slots; ++s)
+      for (int i = s; i < total; i += slots) ++seen[i];
+    used = std::min(slots, total);
+  } else {
+    for (int s = 0; s < slots; ++s) {
+      MTP_REQUIRE(sc.count[s] <= MAX_ITEMS, "mtp_gemm_plan: slot %d holds %d items", s, (int)sc.count[s]);
+      for (int i = 0; i < sc.count[s]; ++i) {
+        MTP_REQUIRE(sc.item[s][i] < total, "mtp_gemm_plan: item id %d out of range", (int)sc.item[s][i]);
+        ++seen[sc.item[s][i]];
+      }
+      if (sc.count[s] > 0) used = s + 1;
+    }
+  }
+  for (int i = 0; i < total; ++i) MTP_REQUIRE(seen[i] == 1, "mtp_gemm_plan: item %d scheduled %d times", i, seen[i]);
+  if (out_config) *out_config = cfg->bn + (cfg->cl2 ? 1000 : 0);
+  if (out_ctas) *out_ctas = cfg->cl2 ? 2 * used : used;
+  if (out_cycles) *out_cycles = build_schedule(pr, np, cfg->bn, cfg->cl2, nullptr) + (cfg->cl2 ? kClusterLaunchCycles : 0.0);
+  return MTP_OK;
+}
+
 }  // namespace mtp
 
 using namespace mtp;
+
+static EpiParams plan_epi(int n) {      // a valid epilogue for planning (never dereferenced)
+  EpiParams e;
+  memset(&e, 0, sizeof(e));
+  e.mode = MTP_EPI_BF16;
+  e.ldo = (n + 7) / 8 * 8;
+  e.out = reinterpret_cast<void*>(uintptr_t(16));
+  return e;
+}
+
+extern "C" int mtp_gemm_plan(int M0, int N0, int K0, int b0_mn_major, int M1, int N1, int K1, int b1_mn_major, int force_bn,
+                             int* out_config, int* out_ctas, double* out_cycles) {
+  void* dummy = reinterpret_cast<void*>(uintptr_t(16));
+  HostProblem h[2] = {{dummy, 8, 0, dummy, 8, b0_mn_major, M0, N0, K0, plan_epi(N0)}, {dummy, 8, 0, dummy, 8, b1_mn_major, M1, N1, K1, plan_epi(N1)}};
+  return plan_grouped(h, M1 > 0 ? 2 : 1, force_bn, out_config, out_ctas, out_cycles);
+}
 
 extern "C" int mtp_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N,
                              int K, const mtp_epilogue* ep, int force_bn, mtp_stream_t stream_) {

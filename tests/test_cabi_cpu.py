@@ -35,3 +35,42 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.MtpError):
         _lib.load()
+
+
+def _plan(M0, N0, K0, b0=0, M1=0, N1=0, K1=0, b1=0, force=0):
+    import ctypes
+    from mtp_b200 import _lib
+    c, n, cy = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    _lib.call("mtp_gemm_plan", M0, N0, K0, b0, M1, N1, K1, b1, force, ctypes.byref(c), ctypes.byref(n), ctypes.byref(cy))
+    return c.value, n.value, cy.value
+
+
+def test_gemm_scheduler_covers_every_tile_once():
+    """Host logic of the GEMM (tile heuristic + LPT / strided work schedule) runs without a GPU: mtp_gemm_plan self-checks that every
+    tile of every problem is assigned to exactly one CTA slot."""
+    T, C = 1568, 1024
+    singles = [(T, 3 * C, C), (T, C, C), (T, 4 * C, C), (T, C, 4 * C), (8, 8, 16), (392, 320, 456), (6272, 4096, 1024), (8192, 8192, 8192)]
+    for shape in singles:
+        for force in (0, 64, 128, 192, 256, 1064, 1128, 1192, 1256):
+            if force >= 1000 and shape[0] <= 128:
+                continue                       # a cta_group::2 pair needs two row tiles
+            cfg, ctas, cycles = _plan(*shape, force=force)
+            assert ctas >= 1 and cycles > 0
+            if force:
+                assert cfg == force
+    # grouped dgrad + wgrad launches of the four Linears of a ViT-L block (B operands MN-major)
+    for n_out, n_in in ((C, 4 * C), (4 * C, C), (C, C), (3 * C, C)):
+        for force in (0, 128, 256, 1128, 1256):
+            cfg, ctas, cycles = _plan(T, n_in, n_out, 1, n_out, n_in, T, 1, force=force)
+            assert 1 <= ctas <= 148 and cycles > 0
+    # the heuristic prefers a config whose modelled makespan is minimal among the forced ones
+    best = min(_plan(T, 3 * C, C, force=f)[2] for f in (64, 128, 192, 256))
+    assert _plan(T, 3 * C, C)[2] <= best + 1e-6
+
+
+def test_gemm_plan_rejects_bad_shapes():
+    from mtp_b200 import _lib
+    with pytest.raises(_lib.MtpError):
+        _plan(128, 12, 64)                     # N not a multiple of 8
+    with pytest.raises(_lib.MtpError):
+        _plan(128, 128, 64, 1, 0, 0, 0, 0, force=1192)     # pairs with MN-major B need 128 / 256 wide tiles
