@@ -99,6 +99,10 @@ class ClockSampler:
                 "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm)}
 
 
+METRIC = "images/sec ViT-L+RVSA MTP step @224^2 bf16"
+WORKLOAD = "ViT-L+RVSA backbone pretrain step @224^2: fwd + synthetic heads + bwd + grad all-reduce + clip + AdamW"
+
+
 # ------------------------------------------------------------------------------------------------------ CPU reference arm
 def usable_threads():
     """Thread count that actually maximises CPU throughput on this host.  Containers often expose every logical CPU of the
@@ -163,10 +167,10 @@ def run_reference(args, rank):
     rate, threads, total = cpu_reference_rate(args.cpu_batch, args.steps, args.warmup)
     ms = 1000.0 * args.cpu_batch / rate
     sample = f"{args.cpu_batch} image(s) per step, ViT-L+RVSA @224 fwd+bwd+AdamW, fp32, {threads} threads"
-    line = {"impl": "reference", "metric": "images/sec ViT-L+RVSA MTP step @224^2", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "ViT-L+RVSA backbone pretrain step @224^2 (oracle port of the reference on host cores)",
+            "config": {"workload": WORKLOAD, "implementation": "oracle port of the reference ([V]) on the host cores, fp32",
                        "per_step_batch": args.cpu_batch},
             "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -366,10 +370,10 @@ def main():
         step_tflops = 3.0 * FWD_GFLOP_PER_IMG * (value / world) / 1e3          # per GPU, training step = 3 x forward
         gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         line = {
-            "metric": "images/sec ViT-L+RVSA MTP step @224^2 bf16", "value": value, "unit": "images/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ViT-L+RVSA backbone pretrain step @224^2: fwd + synthetic heads + bwd + grad all-reduce + clip + AdamW",
+            "config": {"workload": WORKLOAD,
                        "per_gpu_batch": B, "global_batch": B * world, "tokens_per_gpu": B * 196, "parallelism": f"dp{world}",
                        "cuda_graph": bool(args.graph), "l2": "per-step working set (~5 GB of weights, activations, gradients) >> 126 MB L2; no explicit flush",
                        "loss": final_loss},
