@@ -68,7 +68,7 @@ enum mtp_epilogue_mode {
 typedef struct mtp_epilogue {
   int mode;
   int ldo;                /* leading dimension (elements) of out / out2 / aux (when aux is [M, ldo]-shaped) */
-  const float* bias;      /* [N] (PIXSHUF: [ps_cout]) or NULL */
+  const float* bias;      /* [N], or [ps_cout] applied with period ps_cout when ps_cout > 0 (any mode), or NULL */
   void* out;
   void* out2;             /* GELU mode: optional pre-activation copy */
   const void* aux;
@@ -76,7 +76,8 @@ typedef struct mtp_epilogue {
   int rows_per_group;     /* RESID: tokens per image */
   int pos_rows;           /* POS: rows of the positional table */
   int accumulate;         /* F32: add into out */
-  int ps_h, ps_w, ps_cout;
+  int ps_h, ps_w, ps_cout; /* PIXSHUF geometry; ps_cout > 0 alone (other modes): bias[n % ps_cout] -- the ConvTranspose2d GEMM whose
+                             output row holds the 4 sub-pixels side by side shares one [Cout] bias across them */
   float* colsum;          /* BF16 / BF16_DGELU: optional [N] fp32, += column sums of the stored values (the bias gradient of the
                              Linear whose cotangent this GEMM produces); 16-byte aligned */
   float* sumsq;           /* F32: optional scalar, += sum of squares of the stored outputs (gradient-norm clipping without a

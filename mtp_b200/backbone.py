@@ -172,6 +172,19 @@ class ViT_Win_RVSA_V3_WSZ7(nn.Module):
         self.return_tuple = return_tuple
         self.frozen_stages = frozen_stages
         self._engine_state = _engine.EngineState()
+        # weights replaced wholesale: drop cached bf16 copies / refresh always-current mirrors (engine.EngineState.invalidate)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._engine_state.invalidate())
+
+    def invalidate_weight_cache(self):
+        """Call after editing parameters through ``p.data`` (EMA / weight averaging / manual rescale): such writes do not bump the
+        autograd version counter the bf16 weight cache is keyed on."""
+        self._engine_state.invalidate()
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)           # .to() / .cuda() / .float(): storages move
+        if hasattr(self, "_engine_state"):
+            self._engine_state.invalidate()
+        return out
 
     # ---- init (mirrors [V]:676-691) -------------------------------------------------------------------------
     def fix_init_weight(self):

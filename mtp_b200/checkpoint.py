@@ -77,12 +77,12 @@ def init_weights(model, pretrained=None, variant="pretrain", verbose=False):
         ckpt = torch.load(pretrained, map_location="cpu")
         sd = convert_state_dict(model, ckpt, variant, verbose)
         msg = model.load_state_dict(sd, strict=False)
-        model._engine_state.clear()
+        model._engine_state.invalidate()
         if verbose:
             print(msg)
         return msg
     if pretrained is None:
         model.apply(_reinit)
-        model._engine_state.clear()
+        model._engine_state.invalidate()
         return None
     raise TypeError("pretrained must be a str or None")

@@ -23,11 +23,13 @@ static int g_sm_limit = 0;
 void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
 
 int num_sms() {
-  static int cached = 0;
+  static int cached_dev[64] = {};      // per device (a process may drive several)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return g_sm_limit > 0 ? std::min(148, g_sm_limit) : 148;      // no device: planning only
+  int& cached = cached_dev[dev & 63];
   if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
       cached = n;
     else
       return g_sm_limit > 0 ? std::min(148, g_sm_limit) : 148;

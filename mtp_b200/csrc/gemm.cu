@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <queue>
 #include <vector>
 
@@ -487,7 +488,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       if (ep.bias != nullptr) {             // stage this tile's bias slice once (zeros beyond N)
         for (int i = et; i < BN; i += EPI_THREADS) {
           const int n = n0 + i;
-          bsm[i] = n < N ? __ldg(ep.bias + (ep.mode == MTP_EPI_BF16_PIXSHUF ? n % ep.ps_cout : n)) : 0.f;
+          bsm[i] = n < N ? __ldg(ep.bias + (ep.ps_cout > 0 ? n % ep.ps_cout : n)) : 0.f;      // ps_cout: period of the bias vector
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      // bias visible; also keeps the 8 warps on the same item
@@ -652,7 +653,9 @@ static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sc
 struct Config { int bn; bool cl2; Sched sched; };
 
 static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
-  static std::map<std::vector<int>, Config> cache;
+  static std::map<std::vector<int>, Config> cache;      // node-based: returned pointers stay valid
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   std::vector<int> key = {force_bn, np, num_sms()};
   for (int p = 0; p < np; ++p) { key.push_back(pr[p].M); key.push_back(pr[p].N); key.push_back(pr[p].K); key.push_back(pr[p].b_mn); }
   auto it = cache.find(key);
@@ -702,7 +705,10 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
     gp[p].tiles_m = ceil_div(h.M, BM); gp[p].tiles_n = ceil_div(h.N, BN);
     gp[p].a_mn = h.a_mn; gp[p].b_mn = h.b_mn;
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};      // the attribute is per device (function handles are per context)
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
   auto kern = gemm_bf16_kernel<BN, CL2>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);

@@ -28,6 +28,7 @@ class EngineState:
         self.cache: Dict[str, tuple] = {}
         self.pinned: Dict[str, torch.Tensor] = {}      # always-current bf16 views maintained by the fused optimizer
         self.consts: Dict[tuple, torch.Tensor] = {}    # small device constants (DropPath keep probabilities)
+        self.listeners: List = []                      # callbacks run by invalidate() (PretrainStep.refresh_mirror)
 
     def get(self, key, param, fn):
         pin = self.pinned.get(key)
@@ -43,6 +44,13 @@ class EngineState:
 
     def clear(self):
         self.cache.clear()
+
+    def invalidate(self):
+        """Weights were changed behind autograd's back (``p.data`` writes, ``load_state_dict``, checkpoint loading): drop the cached
+        bf16 copies and let the owners of always-current mirrors (the fused-optimizer trainer) refresh theirs."""
+        self.cache.clear()
+        for fn in list(self.listeners):
+            fn()
 
 
 def _as_bf16(w):
@@ -104,7 +112,7 @@ class _W:
             self.fpn = {}
             for key, conv in (("fpn1_0", m.fpn1[0]), ("fpn1_3", m.fpn1[3]), ("fpn2_0", m.fpn2[0])):
                 self.fpn[key + "_w"] = st.get(key, conv.weight, _pack_convt)
-                self.fpn[key + "_b"] = st.get(key + "_b4", conv.bias, lambda b: b.repeat(4).contiguous())
+                self.fpn[key + "_b"] = _f32(conv.bias, key + ".bias")      # [Cout]; the GEMM epilogue applies it with period Cout
             self.fpn["ln_w"], self.fpn["ln_b"] = _f32(m.fpn1[1].ln.weight, "fpn1.1.ln"), _f32(m.fpn1[1].ln.bias, "fpn1.1.ln")
 
 
@@ -152,15 +160,15 @@ def _fpn_forward(m, W, feats, B, gh, gw, out_dtype, save):
     # fpn1: ConvT -> Norm2d(LN over C) -> GELU -> ConvT ; rows of u1 viewed as [4T, C] are the 2x-upsampled pixels
     a0 = feats[0] if feats[0].dtype == BF16 else ops.cast_f32_bf16(feats[0])
     u1 = torch.empty(T, 4 * C, device=a0.device, dtype=BF16)
-    ops.gemm(a0, F_["fpn1_0_w"], T, 4 * C, C, u1, bias=F_["fpn1_0_b"], b_static=True)
+    ops.gemm(a0, F_["fpn1_0_w"], T, 4 * C, C, u1, bias=F_["fpn1_0_b"], ps=(0, 0, C), b_static=True)
     z, mean, rstd = ops.layernorm_fwd(u1.view(4 * T, C), F_["ln_w"], F_["ln_b"], gelu=True, save_stats=save)
     u2 = torch.empty(4 * T, 4 * C, device=a0.device, dtype=BF16)
-    ops.gemm(z, F_["fpn1_3_w"], 4 * T, 4 * C, C, u2, bias=F_["fpn1_3_b"], b_static=True)
+    ops.gemm(z, F_["fpn1_3_w"], 4 * T, 4 * C, C, u2, bias=F_["fpn1_3_b"], ps=(0, 0, C), b_static=True)
     outs.append(ops.tok_to_nchw(u2, B, gh, gw, C, 2, out_dtype))
     # fpn2: ConvT
     a1 = feats[1] if feats[1].dtype == BF16 else ops.cast_f32_bf16(feats[1])
     v1 = torch.empty(T, 4 * C, device=a0.device, dtype=BF16)
-    ops.gemm(a1, F_["fpn2_0_w"], T, 4 * C, C, v1, bias=F_["fpn2_0_b"], b_static=True)
+    ops.gemm(a1, F_["fpn2_0_w"], T, 4 * C, C, v1, bias=F_["fpn2_0_b"], ps=(0, 0, C), b_static=True)
     outs.append(ops.tok_to_nchw(v1, B, gh, gw, C, 1, out_dtype))
     # fpn3: identity
     outs.append(ops.tok_to_nchw(feats[2], B, gh, gw, C, 0, out_dtype))
@@ -176,6 +184,9 @@ def _fpn_forward(m, W, feats, B, gh, gw, out_dtype, save):
 def _check_input(m, x):
     if not x.is_cuda:
         raise RuntimeError("mtp_b200: the backbone runs only on a CUDA (sm_100a) device; there is no CPU fallback")
+    if x.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"mtp_b200: input lives on {x.device} but the current CUDA device is cuda:{torch.cuda.current_device()} "
+                           "(kernels are enqueued on the current device's stream): wrap the call in torch.cuda.device(x.device)")
     if x.dim() != 4 or x.shape[1] != m.in_chans:
         raise ValueError(f"expected (B, {m.in_chans}, H, W), got {tuple(x.shape)}")
     gh, gw = m.patch_embed.patch_shape

@@ -37,7 +37,9 @@ class GradStore:
             self.names.append(name)
             self.views[name] = self.flat[o:o + p.numel()].view(p.shape)
         self.touched = set()
+        self.packed = {}
 
+    packed = {}        # ConvTranspose2d weights: name -> [4*Cout, Cin] fp32 tensor ALIASING the gradient in GEMM layout (trainer)
     sumsq = None       # optional fp32 scalar: the wgrad GEMMs add the sum of squares of the weight gradients they store (trainer)
 
     def g(self, name):
@@ -106,11 +108,20 @@ def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
                              G.g(pre + "norm1.bias"), cast=(nxt[0], N, nxt[1]), pool_add=pool)
 
 
-def _convt_grads(G, wname, bname, dWp, colsum4):
-    """Unpack the GEMM-layout gradients of a ConvTranspose2d(k2,s2): dWp [4*Cout, Cin] -> (Cin, Cout, 2, 2); bias = sum of 4 groups."""
-    cout = dWp.shape[0] // 4
-    G.g(wname).copy_(dWp.view(2, 2, cout, dWp.shape[1]).permute(3, 2, 0, 1))
-    G.g(bname).copy_(colsum4.view(4, cout).sum(0))
+def _convt_wgrad(G, wname, bname, dy, x_in, T, C):
+    """Gradients of a ConvTranspose2d(k2,s2) run as the GEMM y[T, 4*Cout] = x[T, Cin] Wp^T, Wp [4*Cout, Cin] (row = (dy*2+dx)*Cout + co):
+    dWp = dy^T x straight into the gradient storage when it is kept in GEMM layout (trainer), else via a temporary and one permuted copy
+    to (Cin, Cout, 2, 2); the bias gradient is the column sum over the [4T, Cout] view of dy (the 4 sub-pixels share one bias)."""
+    dWp = G.packed.get(wname)
+    tmp = dWp is None
+    if tmp:
+        dWp = torch.empty(4 * C, C, device=dy.device, dtype=F32)
+    else:
+        G.touched.add(wname)
+    ops.gemm(dy, x_in, 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C, sumsq=G.sumsq)
+    if tmp:
+        G.g(wname).copy_(dWp.view(2, 2, C, C).permute(3, 2, 0, 1))
+    ops.colsum_bf16(dy.view(-1, C), G.g(bname))
 
 
 def _fpn_tap_backward(m, W, S, k, grad, dx, G, B, gh, gw):
@@ -132,30 +143,18 @@ def _fpn_tap_backward(m, W, S, k, grad, dx, G, B, gh, gw):
     if k == 1:
         dv1 = torch.empty(T, 4 * C, device=dev, dtype=BF16)
         ops.nchw_to_tok(grad, dv1, B, gh, gw, C, 1)
-        cs = torch.zeros(4 * C, device=dev, dtype=F32)
-        ops.colsum_bf16(dv1, cs)
-        dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
-        ops.gemm(dv1, sv["a1"], 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C, sumsq=G.sumsq)
-        _convt_grads(G, "fpn2.0.weight", "fpn2.0.bias", dWp, cs)
+        _convt_wgrad(G, "fpn2.0.weight", "fpn2.0.bias", dv1, sv["a1"], T, C)
         ops.gemm(dv1, F_["fpn2_0_w"], T, C, 4 * C, dx, b_mn=True, mode=L.EPI_F32, accumulate=True, lda=4 * C, ldb=C)
         return
     # k == 0: ConvT -> LN -> GELU -> ConvT
     du2 = torch.empty(4 * T, 4 * C, device=dev, dtype=BF16)
     ops.nchw_to_tok(grad, du2, B, gh, gw, C, 2)
-    cs = torch.zeros(4 * C, device=dev, dtype=F32)
-    ops.colsum_bf16(du2, cs)
-    dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
-    ops.gemm(du2, sv["z"], 4 * C, C, 4 * T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C, sumsq=G.sumsq)
-    _convt_grads(G, "fpn1.3.weight", "fpn1.3.bias", dWp, cs)
+    _convt_wgrad(G, "fpn1.3.weight", "fpn1.3.bias", du2, sv["z"], 4 * T, C)
     dz = torch.empty(4 * T, C, device=dev, dtype=BF16)
     ops.gemm(du2, F_["fpn1_3_w"], 4 * T, C, 4 * C, dz, b_mn=True, lda=4 * C, ldb=C)
     du1 = ops.layernorm_bwd(dz, sv["u1"].view(4 * T, C), sv["mean"], sv["rstd"], F_["ln_w"], F_["ln_b"], None,
                             G.g("fpn1.1.ln.weight"), G.g("fpn1.1.ln.bias"), gelu=True).view(T, 4 * C)
-    cs = torch.zeros(4 * C, device=dev, dtype=F32)
-    ops.colsum_bf16(du1, cs)
-    dWp = torch.empty(4 * C, C, device=dev, dtype=F32)
-    ops.gemm(du1, sv["a0"], 4 * C, C, T, dWp, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=4 * C, ldb=C, sumsq=G.sumsq)
-    _convt_grads(G, "fpn1.0.weight", "fpn1.0.bias", dWp, cs)
+    _convt_wgrad(G, "fpn1.0.weight", "fpn1.0.bias", du1, sv["a0"], T, C)
     ops.gemm(du1, F_["fpn1_0_w"], T, C, 4 * C, dx, b_mn=True, mode=L.EPI_F32, accumulate=True, lda=4 * C, ldb=C)
 
 

@@ -89,10 +89,19 @@ class PretrainStep:
         self.flat_v = torch.zeros(total, device=dev, dtype=F32)
         num_layers = len(model.blocks) + 2
         groups, chunk_group = {}, torch.zeros(total // 64, dtype=torch.uint8)
+        self._convt = {"fpn1.0.weight": "fpn1_0", "fpn1.3.weight": "fpn1_3", "fpn2.0.weight": "fpn2_0"}
         for n, p in order:
             o = self.offsets[n]
-            self.flat_p[o:o + p.numel()].copy_(p.data.reshape(-1))
-            p.data = self.flat_p[o:o + p.numel()].view(p.shape)
+            if n in self._convt:
+                # ConvTranspose2d(k2,s2) weights live in the flat buffers in GEMM layout [4*Cout, Cin] (row = (dy*2+dx)*Cout + co): the
+                # bf16 mirror slice IS the GEMM operand and the wgrad GEMM writes the flat gradient in place.  The nn.Parameter keeps
+                # its (Cin, Cout, 2, 2) shape as a permuted (non-contiguous) view, so state_dict / load_state_dict are unchanged.
+                cin, cout = p.shape[0], p.shape[1]
+                self.flat_p[o:o + p.numel()].copy_(p.data.permute(2, 3, 1, 0).reshape(-1))
+                p.data = self.flat_p[o:o + p.numel()].view(2, 2, cout, cin).permute(3, 2, 0, 1)
+            else:
+                self.flat_p[o:o + p.numel()].copy_(p.data.reshape(-1))
+                p.data = self.flat_p[o:o + p.numel()].view(p.shape)
             lid, nodecay = layer_decay_group(n, p.shape, num_layers, name_prefix)
             key = (layer_decay_rate ** (num_layers - lid - 1), 0.0 if nodecay else weight_decay)
             gid = groups.setdefault(key, len(groups))
@@ -113,16 +122,25 @@ class PretrainStep:
             v16 = self.flat_p16[o:o + p.numel()]
             if n == "patch_embed.proj.weight":
                 st.pinned["pe_w"] = v16.view(C, -1)
+            elif n in self._convt:
+                st.pinned[self._convt[n]] = v16.view(4 * p.shape[1], p.shape[0])
             elif n.startswith("blocks."):
                 i = int(n.split(".")[1])
                 nm = n.split(".")[-2]
                 st.pinned[f"b{i}.{nm}"] = v16.view(p.shape)
-        self._convt_keys = ("fpn1_0", "fpn1_3", "fpn2_0")
+        st.listeners.append(self.refresh_mirror)       # checkpoint loading / load_state_dict / manual p.data edits: engine invalidate()
         # ---- gradient store bound to the flat gradient buffer (same layout)
         self.G = engine_bwd.GradStore.__new__(engine_bwd.GradStore)
         self.G.names = [n for n, _ in named]
         self.G.flat = self.flat_g
-        self.G.views = {n: self.flat_g[self.offsets[n]:self.offsets[n] + p.numel()].view(p.shape) for n, p in named}
+        self.G.views, self.G.packed = {}, {}
+        for n, p in named:
+            gslice = self.flat_g[self.offsets[n]:self.offsets[n] + p.numel()]
+            if n in self._convt:
+                self.G.packed[n] = gslice.view(4 * p.shape[1], p.shape[0])
+                self.G.views[n] = gslice.view(2, 2, p.shape[1], p.shape[0]).permute(3, 2, 0, 1)
+            else:
+                self.G.views[n] = gslice.view(p.shape)
         self.G.touched = set()
         # world size 1: the wgrad GEMM epilogues accumulate the squared norm of the weight gradients they store, so the clip
         # needs a reduction pass over the small region only (verified once against the full pass, see _forward_backward)
@@ -152,9 +170,6 @@ class PretrainStep:
     def _forward_backward(self, x, on_bucket):
         """forward + heads + backward; ``on_bucket(ranges)`` is called when flat-gradient ranges have become final."""
         m = self.model
-        st = m._engine_state
-        for k in self._convt_keys:                 # packed ConvTranspose weights are re-derived from the fp32 masters
-            st.cache.pop(k, None)
         keep = engine._draw_keep(m, x.shape[0], x.device)
         outs, ctx = engine._forward_impl(m, x, keep, save=True)
         loss, douts = self.heads(outs)
@@ -196,6 +211,40 @@ class PretrainStep:
                self.flat_p16.data_ptr(), self.chunk_group.data_ptr(), self.group_lr.data_ptr(), self.group_wd.data_ptr(),
                self.state.data_ptr(), self.total, float(self.lr), float(self.eta_min), int(self.t_max), float(self.betas[0]),
                float(self.betas[1]), float(self.eps), float(self.max_norm or 0.0), 1.0 / self.world, stream)
+
+    # ---- training-state checkpointing (the reference saves optimizer + scheduler state: main_pretrain.py:825-832) --------------
+    def refresh_mirror(self):
+        """Re-derive the bf16 weight mirror from the fp32 masters (after weights were loaded / edited outside the optimizer) and
+        invalidate captured graphs' assumptions about nothing (they read the same buffers)."""
+        L.call("mtp_cast_f32_bf16", self.flat_p.data_ptr(), self.flat_p16.data_ptr(), self.total, ops._stream())
+        self.model._engine_state.cache.clear()
+
+    def state_dict(self):
+        """Optimizer + schedule state keyed by parameter name (layout independent): exp_avg / exp_avg_sq per parameter in the
+        parameter's own shape, the step counter that drives the bias correction and the cosine schedule."""
+        out = {"step": float(self.state[0].item()), "exp_avg": {}, "exp_avg_sq": {}}
+        for n, p in self.model.named_parameters():
+            o = self.offsets[n]
+            for key, flat in (("exp_avg", self.flat_m), ("exp_avg_sq", self.flat_v)):
+                v = flat[o:o + p.numel()]
+                if n in self._convt:
+                    v = v.view(2, 2, p.shape[1], p.shape[0]).permute(3, 2, 0, 1)
+                else:
+                    v = v.view(p.shape)
+                out[key][n] = v.detach().clone().contiguous()
+        return out
+
+    def load_state_dict(self, sd):
+        with torch.no_grad():
+            for n, p in self.model.named_parameters():
+                o = self.offsets[n]
+                for key, flat in (("exp_avg", self.flat_m), ("exp_avg_sq", self.flat_v)):
+                    src = sd[key][n].to(self.dev, F32)
+                    if n in self._convt:
+                        src = src.permute(2, 3, 1, 0)
+                    flat[o:o + p.numel()].copy_(src.reshape(-1))
+            self.state[0] = float(sd["step"])
+        self.refresh_mirror()
 
     def _reduce(self, ranges):
         for lo, hi in ranges:

@@ -48,6 +48,11 @@ class OracleConfig:
     # CUDA path stores bf16 (GEMM operands: weights, LN outputs, qkv, attention output, GELU output, fpn intermediates).
     # With it the oracle predicts the CUDA path's forward to ~1e-3 and shares its bilinear-tap cell decisions.
     emulate_bf16: bool = False
+    # Test aid: additionally round the COTANGENTS to bf16 where the CUDA backward stores them as bf16 GEMM operands (branch
+    # cotangents, dh, dy, dO, dS / P of the attention backward, dqkv, the pyramid intermediates) and differentiate GELU at the
+    # bf16-rounded pre-activation the CUDA path keeps.  Makes the oracle's backward carry the same rounding-noise SOURCES as the CUDA
+    # backward (it cannot reproduce the individual rounding decisions at depth: see tests/test_rounding_chaos_cpu.py).
+    emulate_bf16_grad: bool = False
 
     @property
     def grid(self) -> int:
@@ -78,6 +83,72 @@ def _ste_bf16(t: torch.Tensor) -> torch.Tensor:
 
 def _ident(t: torch.Tensor) -> torch.Tensor:
     return t
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _RoundGrad(torch.autograd.Function):
+    """Identity in the forward pass; rounds the cotangent to bf16 in the backward pass."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+def _round_grad(t: torch.Tensor) -> torch.Tensor:
+    return _RoundGrad.apply(t)
+
+
+class _GeluSavedBf16(torch.autograd.Function):
+    """erf-GELU of the fp32 pre-activation; the derivative is evaluated at the bf16 copy the CUDA path saves (fc1 epilogue out2)."""
+
+    @staticmethod
+    def forward(ctx, h):
+        ctx.save_for_backward(_bf16(h))
+        return gelu_erf(h)
+
+    @staticmethod
+    def backward(ctx, g):
+        (hb,) = ctx.saved_tensors
+        cdf = 0.5 * (1.0 + torch.erf(hb * (1.0 / math.sqrt(2.0))))
+        pdf = torch.exp(-0.5 * hb * hb) * (1.0 / math.sqrt(2.0 * math.pi))
+        return g * (cdf + hb * pdf)
+
+
+class _AttnCoreBf16(torch.autograd.Function):
+    """softmax(S) @ v with the bf16 staging of the tensor-core attention kernels, forward AND backward.
+    ``normalized``: P is normalised before it is rounded (RVSA kernel) or rounded as exp(S - max) and O divided by the fp32 row sum
+    (dense kernel).  Backward: dV = bf16(P)^T dO, dP = dO v^T, dS = bf16(P (dP - D))."""
+
+    @staticmethod
+    def forward(ctx, S, v, normalized):
+        e = torch.exp(S - S.amax(-1, keepdim=True))
+        ssum = e.sum(-1, keepdim=True)
+        if normalized:
+            O = _bf16(e / ssum) @ v
+        else:
+            O = (_bf16(e) @ v) / ssum
+        ctx.save_for_backward(S, v, O)
+        ctx.normalized = normalized
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        S, v, O = ctx.saved_tensors
+        P = torch.softmax(S, dim=-1)
+        dV = _bf16(P).transpose(-1, -2) @ dO
+        dP = dO @ v.transpose(-1, -2)
+        if ctx.normalized:
+            D = (P * dP).sum(-1, keepdim=True)
+        else:
+            D = (dO * _bf16(O)).sum(-1, keepdim=True)
+        return _bf16(P * (dP - D)), dV, None
 
 
 def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
@@ -182,9 +253,11 @@ def rvsa_coords(ox, oy, sx, sy, th, Hq: int, Wq: int):
     return px, py
 
 
-def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: int, w: int, nH: int, r=_ident) -> torch.Tensor:
+def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: int, w: int, nH: int, r=_ident, gr=None) -> torch.Tensor:
     """RotatedVariedSizeWindowAttention.forward, [V]:287-433 / SURVEY.md A.1.  xn: LN'd (B, N, C).
-    ``r`` is the identity (reference arithmetic) or the bf16 straight-through rounding of ``emulate_bf16``."""
+    ``r`` is the identity (reference arithmetic) or the bf16 straight-through rounding of ``emulate_bf16``; ``gr`` (optional) rounds
+    cotangents (``emulate_bf16_grad``)."""
+    g_ = gr if gr is not None else _ident
     B, N, C = xn.shape
     hd = C // nH
     scale = hd ** -0.5
@@ -196,7 +269,8 @@ def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: in
     ox, oy, sx, sy, th = sampling_params(xg, P, pre, nH, h, w)
     px, py = rvsa_coords(ox, oy, sx, sy, th, Hq, Wq)                           # (B,nH,nh,7,nw,7)
 
-    qkv = r(xn @ r(P[pre + "qkv.weight"]).t() + P[pre + "qkv.bias"])         # [V]:390
+    # (the pooled sampling-head path above keeps an fp32 cotangent; the qkv GEMM's input cotangent dy1 is a bf16 tensor)
+    qkv = g_(r(g_(xn) @ r(P[pre + "qkv.weight"]).t() + P[pre + "qkv.bias"]))         # [V]:390
     qkv = qkv.reshape(B, h, w, 3, nH, hd)
     qkv = F.pad(qkv, (0, 0, 0, 0, 0, 0, pl, pr, pt, pb))                        # zero pad AFTER bias [V]:392
     q, k, v = (qkv[:, :, :, i].permute(0, 3, 1, 2, 4) for i in range(3))        # (B,nH,Hq,Wq,hd)
@@ -227,20 +301,24 @@ def rvsa_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: in
     idx = (iy[:, None] - iy[None, :] + WS - 1) * (2 * WS - 1) + (ix[:, None] - ix[None, :] + WS - 1)
     bias = P[pre + "relative_position_bias_table"][idx.reshape(-1)].reshape(WS * WS, WS * WS, nH).permute(2, 0, 1)
     S = S + bias
-    A = r(torch.softmax(S, dim=-1))
-    O = A @ vw                                                                  # (B,nh,nw,nH,49,hd)
+    if gr is not None:
+        O = _AttnCoreBf16.apply(S, vw, True)
+    else:
+        A = r(torch.softmax(S, dim=-1))
+        O = A @ vw                                                              # (B,nh,nw,nH,49,hd)
     O = O.reshape(B, nh, nw, nH, WS, WS, hd).permute(0, 1, 4, 2, 5, 3, 6).reshape(B, Hq, Wq, C)
-    O = r(O[:, pt:pt + h, pl:pl + w].reshape(B, N, C))                          # crop  [V]:426
-    return O @ r(P[pre + "proj.weight"]).t() + P[pre + "proj.bias"]
+    O = g_(r(O[:, pt:pt + h, pl:pl + w].reshape(B, N, C)))                      # crop  [V]:426
+    return g_(O @ r(P[pre + "proj.weight"]).t() + P[pre + "proj.bias"])
 
 
 def full_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: int, w: int, nH: int,
-                   use_rel_pos: bool = True, r=_ident) -> torch.Tensor:
+                   use_rel_pos: bool = True, r=_ident, gr=None) -> torch.Tensor:
     """Attention.forward + calc_rel_pos_spatial, [V]:90-111,142-193 / SURVEY.md A.2."""
+    g_ = gr if gr is not None else _ident
     B, N, C = xn.shape
     hd = C // nH
     scale = hd ** -0.5
-    qkv = r(xn @ r(P[pre + "qkv.weight"]).t() + P[pre + "qkv.bias"])
+    qkv = g_(r(g_(xn) @ r(P[pre + "qkv.weight"]).t() + P[pre + "qkv.bias"]))
     qkv = qkv.reshape(B, N, 3, nH, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0] * scale, qkv[1], qkv[2]                                     # q scaled first [V]:100
     S = q @ k.transpose(-1, -2)
@@ -252,15 +330,26 @@ def full_attention(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, h: in
         rel_h = torch.einsum("bnqc,qkc->bnqk", q, Rh)
         rel_w = torch.einsum("bnqc,qkc->bnqk", q, Rw)
         S = S + rel_h[..., :, ty] + rel_w[..., :, tx]
-    A = torch.softmax(S, dim=-1)
-    O = r((A @ v).transpose(1, 2).reshape(B, N, C))
-    return O @ r(P[pre + "proj.weight"]).t() + P[pre + "proj.bias"]
+    if gr is not None:
+        O = _AttnCoreBf16.apply(S, v, False)
+    elif r is not _ident:
+        # the dense tensor-core kernel stages exp(S - max) as a bf16 MMA operand and divides O by the fp32 row sum
+        e = torch.exp(S - S.amax(-1, keepdim=True))
+        O = (r(e) @ v) / e.sum(-1, keepdim=True)
+    else:
+        O = torch.softmax(S, dim=-1) @ v
+    O = g_(r(O.transpose(1, 2).reshape(B, N, C)))
+    return g_(O @ r(P[pre + "proj.weight"]).t() + P[pre + "proj.bias"])
 
 
-def mlp(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, r=_ident) -> torch.Tensor:
+def mlp(xn: torch.Tensor, P: Dict[str, torch.Tensor], pre: str, r=_ident, gr=None) -> torch.Tensor:
     """Mlp.forward, [V]:55-62."""
-    hdn = r(gelu_erf(xn @ r(P[pre + "fc1.weight"]).t() + P[pre + "fc1.bias"]))
-    return hdn @ r(P[pre + "fc2.weight"]).t() + P[pre + "fc2.bias"]
+    if gr is None:
+        hdn = r(gelu_erf(xn @ r(P[pre + "fc1.weight"]).t() + P[pre + "fc1.bias"]))
+        return hdn @ r(P[pre + "fc2.weight"]).t() + P[pre + "fc2.bias"]
+    hpre = gr(gr(xn) @ r(P[pre + "fc1.weight"]).t() + P[pre + "fc1.bias"])
+    hdn = r(_GeluSavedBf16.apply(hpre))
+    return gr(hdn @ r(P[pre + "fc2.weight"]).t() + P[pre + "fc2.bias"])
 
 
 def conv_transpose_2x2(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -271,12 +360,13 @@ def conv_transpose_2x2(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> tor
     return o + b[None, :, None, None]
 
 
-def fpn_tail(feats: List[torch.Tensor], P: Dict[str, torch.Tensor], eps: float, r=_ident) -> List[torch.Tensor]:
+def fpn_tail(feats: List[torch.Tensor], P: Dict[str, torch.Tensor], eps: float, r=_ident, gr=None) -> List[torch.Tensor]:
     """fpn1..fpn4 for patch_size 16 ([V]:640-654,807-811); Norm2d = LN over channels ([V]:576-584)."""
-    f1 = r(conv_transpose_2x2(r(feats[0]), r(P["fpn1.0.weight"]), P["fpn1.0.bias"]))
+    g_ = gr if gr is not None else _ident
+    f1 = g_(r(conv_transpose_2x2(r(feats[0]), r(P["fpn1.0.weight"]), P["fpn1.0.bias"])))
     f1 = layer_norm(f1.permute(0, 2, 3, 1), P["fpn1.1.ln.weight"], P["fpn1.1.ln.bias"], eps).permute(0, 3, 1, 2)
-    f1 = r(conv_transpose_2x2(r(gelu_erf(f1)), r(P["fpn1.3.weight"]), P["fpn1.3.bias"]))
-    f2 = r(conv_transpose_2x2(r(feats[1]), r(P["fpn2.0.weight"]), P["fpn2.0.bias"]))
+    f1 = g_(r(conv_transpose_2x2(g_(r(gelu_erf(f1))), r(P["fpn1.3.weight"]), P["fpn1.3.bias"])))
+    f2 = g_(r(conv_transpose_2x2(r(feats[1]), r(P["fpn2.0.weight"]), P["fpn2.0.bias"])))
     f3 = feats[2]
     B, C, H, W = feats[3].shape
     f4 = feats[3][:, :, :H // 2 * 2, :W // 2 * 2].reshape(B, C, H // 2, 2, W // 2, 2).amax(dim=(3, 5))
@@ -299,7 +389,9 @@ def backbone_forward(P: Dict[str, torch.Tensor], cfg: OracleConfig, x: torch.Ten
     hp = wp = None
     C, nH = cfg.embed_dim, cfg.num_heads
     r = _ste_bf16 if cfg.emulate_bf16 else _ident
-    t = patch_embed(r(x), r(P["patch_embed.proj.weight"]), P["patch_embed.proj.bias"], cfg.patch_size)
+    gr = _round_grad if (cfg.emulate_bf16 and cfg.emulate_bf16_grad) else None
+    g_ = gr if gr is not None else _ident
+    t = g_(patch_embed(r(x), r(P["patch_embed.proj.weight"]), P["patch_embed.proj.bias"], cfg.patch_size))
     hp, wp = x.shape[2] // cfg.patch_size, x.shape[3] // cfg.patch_size
     if "pos_embed" in P:
         t = t + P["pos_embed"]                                                   # [V]:793-794
@@ -308,14 +400,14 @@ def backbone_forward(P: Dict[str, torch.Tensor], cfg: OracleConfig, x: torch.Ten
         pre = f"blocks.{i}."
         xn = r(layer_norm(t, P[pre + "norm1.weight"], P[pre + "norm1.bias"], cfg.ln_eps))
         if cfg.is_window_block(i):
-            a = rvsa_attention(xn, P, pre + "attn.", hp, wp, nH, r)
+            a = rvsa_attention(xn, P, pre + "attn.", hp, wp, nH, r, gr)
         else:
-            a = full_attention(xn, P, pre + "attn.", hp, wp, nH, cfg.full_attn_rel_pos, r)
+            a = full_attention(xn, P, pre + "attn.", hp, wp, nH, cfg.full_attn_rel_pos, r, gr)
         if keep is not None:
             a = a * keep[i, 0].reshape(B, 1, 1)
         t = t + a                                                                # [V]:508
         xn = r(layer_norm(t, P[pre + "norm2.weight"], P[pre + "norm2.bias"], cfg.ln_eps))
-        m = mlp(xn, P, pre + "mlp.", r)
+        m = mlp(xn, P, pre + "mlp.", r, gr)
         if keep is not None:
             m = m * keep[i, 1].reshape(B, 1, 1)
         t = t + m                                                                # [V]:509
@@ -326,7 +418,7 @@ def backbone_forward(P: Dict[str, torch.Tensor], cfg: OracleConfig, x: torch.Ten
         feats = [last, last, last, last]
     feats = [f.permute(0, 2, 1).reshape(B, C, hp, wp) for f in feats]            # [V]:807
     if cfg.apply_fpn:
-        return fpn_tail(feats, P, cfg.ln_eps, r)
+        return fpn_tail(feats, P, cfg.ln_eps, r, gr)
     return [f.contiguous() for f in feats]
 
 

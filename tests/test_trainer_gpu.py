@@ -86,3 +86,84 @@ def test_fused_gradient_norm_matches_full_pass():
     L.call("mtp_sumsq_f32", tr.flat_g.data_ptr(), tr.small_end, tr.state.data_ptr() + 4, ops._stream())
     full = float((tr.flat_g.double() ** 2).sum().item())
     assert abs(float(tr.state[1].item()) - full) <= 1e-4 * full
+
+
+def _reference_steps(m, x, lr, wd, max_norm, steps):
+    decay, no_decay = [], []
+    for n, p in m.named_parameters():
+        (no_decay if (p.dim() == 1 or n.endswith(".bias") or "pos_embed" in n) else decay).append(p)
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": wd}, {"params": no_decay, "weight_decay": 0.0}], lr=lr, betas=(0.9, 0.999), eps=1e-8)
+    losses = []
+    for _ in range(steps):
+        opt.zero_grad(set_to_none=True)
+        loss = O.synthetic_loss(m(x))
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in m.parameters() if p.grad is not None], max_norm)
+        opt.step()
+        losses.append(loss.item())
+    return losses
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_three_steps_track_torch_adamw(graph):
+    """Every forward after step 1 must see the UPDATED weights and biases (incl. the ConvTranspose2d weights / biases of the pyramid,
+    which the GEMM reads in a re-packed layout): losses of steps 2 and 3 and the final feature maps follow autograd + torch AdamW."""
+    from mtp_b200.trainer import PretrainStep
+    g = load_golden("tiny160")
+    m1 = build_module("tiny160")
+    m1.load_state_dict(g["sd"])
+    m1 = m1.cuda().eval()
+    m2 = copy.deepcopy(m1)
+    p0 = {n: p.detach().clone() for n, p in m1.named_parameters()}
+    x = g["x"].cuda()
+    lr, wd, max_norm = 2e-3, 0.05, 1.0        # a large lr so three steps move the loss visibly
+    ref_losses = _reference_steps(m2, x, lr, wd, max_norm, 3)
+    tr = PretrainStep(m1, lr=lr, weight_decay=wd, max_norm=max_norm, use_cuda_graph=graph)
+    losses = []
+    for _ in range(3):
+        l = tr.step(x)
+        torch.cuda.synchronize()
+        losses.append(l.item())
+    print("losses", losses, "reference", ref_losses)
+    assert abs(ref_losses[2] - ref_losses[0]) > 20 * 2e-3 * abs(ref_losses[0]), "the reference loss must move for this test to mean anything"
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-3 * abs(b), (losses, ref_losses)
+    for n in ("fpn1.0.bias", "fpn1.3.bias", "fpn2.0.bias", "fpn1.0.weight", "fpn2.0.weight", "blocks.0.mlp.fc1.weight", "pos_embed"):
+        d1 = dict(m1.named_parameters())[n].detach() - p0[n]
+        d2 = dict(m2.named_parameters())[n].detach() - p0[n]
+        assert d2.abs().max().item() > 0
+        assert ((d1 - d2).norm() / d2.norm()).item() < 0.08, n
+    with torch.no_grad():
+        o1, o2 = m1(x), m2(x)
+    for a, b in zip(o1, o2):
+        assert ((a - b).norm() / b.norm()).item() < 5e-3
+
+
+def test_trainer_state_dict_round_trip_and_weight_reload():
+    """Optimizer state survives state_dict()/load_state_dict(); loading model weights AFTER the trainer exists refreshes the bf16
+    mirror the kernels read."""
+    from mtp_b200.trainer import PretrainStep
+    g = load_golden("tiny160")
+    x = g["x"].cuda()
+
+    def fresh():
+        m = build_module("tiny160")
+        m.load_state_dict(g["sd"])
+        return m.cuda().eval()
+    ma = fresh()
+    ta = PretrainStep(ma, lr=1e-3, max_norm=1.0)
+    for _ in range(2):
+        ta.step(x)
+    opt_sd = {k: (v if not isinstance(v, dict) else {n: t.clone() for n, t in v.items()}) for k, v in ta.state_dict().items()}
+    model_sd = {k: v.detach().clone() for k, v in ma.state_dict().items()}
+    la = ta.step(x).item()
+    # resume in a new trainer built on a freshly initialised module
+    mb = fresh()
+    tb = PretrainStep(mb, lr=1e-3, max_norm=1.0)
+    mb.load_state_dict(model_sd)                       # goes through the parameters' .data views -> flat_p; mirror refreshed by the hook
+    assert torch.equal(tb.flat_p16, tb.flat_p.to(torch.bfloat16))
+    tb.load_state_dict(opt_sd)
+    lb = tb.step(x).item()
+    assert abs(la - lb) <= 1e-5 * abs(la), (la, lb)
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=0, atol=1e-6), n

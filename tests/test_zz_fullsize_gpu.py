@@ -1,9 +1,22 @@
-"""Parity at the sizes BASELINE.json quotes (the tiny golden configs cover the edge cases; this file covers the real widths):
-config 1 = ViT-B + RVSA, 1 x 3 x 224 x 224 (the reference's own CPU-runnable case) forward AND backward, and the ViT-L forward of
-the headline configuration.  The checker is the CPU oracle (fp32, and with bf16 rounding at the CUDA path's storage points); it needs
-about a second per pass at these sizes.  Runs last (file name) because it is the slowest GPU test."""
-import dataclasses
+"""Parity at the sizes BASELINE.json quotes (the tiny golden configs cover the edge cases; this file covers the real widths and
+depths): config 1 = ViT-B + RVSA, 1 x 3 x 224 x 224 forward AND backward; the ViT-L headline configuration forward AND backward at
+the bench operating point (8 images, train mode, fixed DropPath masks).  The checker is the CPU oracle.  Runs last (file name).
 
+How the thresholds are set (tests/test_rounding_chaos_cpu.py): the CUDA path stores its GEMM operands and
+activation cotangents as bf16.  Two correct bf16 implementations of the same network that differ by 1e-6 before any rounding do NOT
+stay together: every rounding turns a perturbation d << ulp into an rms change sqrt(d * ulp), so after a few layers the two are as
+far from each other as each is from the fp32 result.  A fixed "bf16-faithful" reference therefore cannot predict the CUDA path
+element by element at depth 12 / 24; what it CAN predict is the SIZE of the bf16 error of every output map and every parameter
+gradient.  The criterion here is self-calibrating: for each tensor
+
+        || cuda - fp32 oracle ||   <=   RATIO * || bf16-emulating oracle - fp32 oracle ||  (+ a small floor)
+
+with the oracle rounding at the CUDA path's storage points in the forward AND the backward pass (OracleConfig.emulate_bf16 +
+emulate_bf16_grad).  Measured on the CPU with an independently perturbed second emulation standing in for the CUDA path, the ratio
+is 0.45 .. 1.4 per tensor (median 0.97), so RATIO = 2 leaves room for the approximations the kernels add (ex2-based softmax,
+A&S erf) and none for a wrong kernel: a logic error moves a gradient by O(1), i.e. 25 .. 1000 x the bf16 error level.
+Kernel logic at these widths is additionally pinned on identical inputs, where no decorrelation occurs (tests/test_attention_gpu.py,
+test_gemm_gpu.py, test_rowops_gpu.py, test_block_fullwidth_gpu.py)."""
 import pytest
 import torch
 
@@ -11,29 +24,7 @@ from oracle import rvsa_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-# Expected size of the bf16 operand-rounding error at these depths (bf16-faithful oracle vs fp32 oracle, measured on the CPU):
-# forward 2.8e-3 .. 5.6e-3 rel-L2 per map, GEMM-weight gradients <= 2.7e-2.  The CUDA path follows the bf16-faithful oracle much
-# more closely (tiny configs: <= 1.2e-3 forward, <= 6e-3 per gradient).
-FWD_VS_FP32 = 1.5e-2
-FWD_VS_FAITHFUL = 6e-3
-GRAD_VS_FAITHFUL = 3e-2
-
-
-def _build(embed_dim, depth, num_heads, interval, out_indices, seed):
-    from mtp_b200 import ViT_Win_RVSA_V3_WSZ7
-    torch.manual_seed(seed)
-    m = ViT_Win_RVSA_V3_WSZ7(img_size=224, patch_size=16, embed_dim=embed_dim, depth=depth, num_heads=num_heads, mlp_ratio=4, qkv_bias=True,
-                             use_abs_pos_emb=True, interval=interval, out_indices=out_indices, drop_path_rate=0.1, use_rel_pos_bias=True)
-    with torch.no_grad():
-        for n, p in m.named_parameters():
-            if "rel_pos" in n:                   # the reference initialises these tables to zero; make them count
-                p.normal_(0, 0.02)
-    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    return m, sd
-
-
-def _rel(a, b):
-    return float((a.detach().float().cpu() - b.detach()).norm() / b.detach().norm().clamp_min(1e-30))
+from tests.helpers import build_backbone as _build, parity_check as _check
 
 
 def test_vit_b_config1_forward_backward_vs_oracle():
@@ -45,37 +36,35 @@ def test_vit_b_config1_forward_backward_vs_oracle():
     assert [tuple(o.shape) for o in outs] == [(1, 768, 56, 56), (1, 768, 28, 28), (1, 768, 14, 14), (1, 768, 7, 7)]
     O.synthetic_loss(outs).backward()
     torch.cuda.synchronize()
-    with torch.no_grad():
-        ref32 = O.backbone_forward(sd, cfg, x)
-    e32 = [_rel(o, r) for o, r in zip(outs, ref32)]
-    print("ViT-B forward vs fp32 oracle:", ["%.2e" % e for e in e32])
-    assert max(e32) < FWD_VS_FP32, e32
-    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
-    ref16 = O.backbone_forward(P, dataclasses.replace(cfg, emulate_bf16=True), x)
-    O.synthetic_loss(ref16).backward()
-    e16 = [_rel(o, r) for o, r in zip(outs, ref16)]
-    print("ViT-B forward vs bf16-faithful oracle:", ["%.2e" % e for e in e16])
-    assert max(e16) < FWD_VS_FAITHFUL, e16
-    errs = {}
-    for k, p in m.named_parameters():
-        if P[k].grad is None or "sampling_" in k:      # coordinate-sensitive (piecewise-constant) gradients: covered at the tiny configs
-            continue
-        assert p.grad is not None, k
-        errs[k] = _rel(p.grad, P[k].grad)
-    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
-    print("ViT-B gradients vs bf16-faithful oracle, worst:", [(k, "%.2e" % v) for k, v in worst])
-    assert worst[0][1] < GRAD_VS_FAITHFUL, worst
+    _check("ViT-B 1x224", m, outs, sd, cfg, x, None)
 
 
-def test_vit_l_headline_forward_vs_oracle():
+def test_vit_l_headline_forward_bf16_input():
+    """The bench's input dtype: bf16 images in, bf16 maps out."""
     m, sd = _build(1024, 24, 16, 6, [7, 11, 15, 23], seed=1)
     cfg = O.vit_l_config(224)
-    x = torch.randn(2, 3, 224, 224)
+    x = torch.randn(2, 3, 224, 224).to(torch.bfloat16)
     m = m.cuda().eval()
     with torch.no_grad():
-        outs = m(x.cuda().to(torch.bfloat16))
-        ref32 = O.backbone_forward(sd, cfg, x.to(torch.bfloat16).float())
+        outs = m(x.cuda())
     assert all(o.dtype == torch.bfloat16 for o in outs)
-    e32 = [_rel(o, r) for o, r in zip(outs, ref32)]
-    print("ViT-L forward vs fp32 oracle:", ["%.2e" % e for e in e32])
-    assert max(e32) < FWD_VS_FP32 * 1.5, e32          # bf16 output rounding on top
+    _check("ViT-L 2x224 (bf16 in/out)", m, outs, sd, cfg, x.float(), None, backward=False)
+
+
+def test_vit_l_bench_operating_point_forward_backward():
+    """ViT-L + RVSA, 8 images, train mode with fixed DropPath masks: the step bench.py times (forward + backward)."""
+    from mtp_b200 import engine
+    m, sd = _build(1024, 24, 16, 6, [7, 11, 15, 23], seed=2)
+    cfg = O.vit_l_config(224)
+    B = 8
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 3, 224, 224, generator=g)
+    probs = torch.tensor([blk.drop_path_prob for blk in m.blocks])
+    kp = (1.0 - probs).view(-1, 1, 1).expand(cfg.depth, 2, B)
+    keep = torch.bernoulli(kp, generator=g) / kp
+    assert float(keep.min()) == 0.0, "the fixed masks must drop at least one branch"
+    m = m.cuda().train()
+    outs = engine.backbone_apply(m, x.cuda(), keep=keep.cuda().contiguous())
+    O.synthetic_loss(outs).backward()
+    torch.cuda.synchronize()
+    _check("ViT-L 8x224 train", m, outs, sd, cfg, x, keep)
