@@ -173,6 +173,13 @@ int mtp_full_attn_fwd(const void* qkv_bf16, const float* rel_pos_h, const float*
  * (0: ld >= C; 1, 2: ld >= 4C).  mtp_maxpool2_tok_*: fpn4 = MaxPool2d(2,2) on the token grid ([V]:654).
  * ------------------------------------------------------------------------------------------------------------- */
 int mtp_patchify(const void* img, int img_is_bf16, void* out_bf16, int B, int cin, int H, int W, mtp_stream_t stream);
+
+/* f2: MTP_DataPreprocessor folded into the patch gather -- replaces Multi-Task_Pretrain/preprocessing.py:145-187
+ * (mmengine ImgDataPreprocessor.forward: `_batch_input[[2,1,0]]` when bgr_to_rgb, `.float()`, `(x - mean) / std`; padding is the identity
+ * at H,W == img_size) + PatchEmbed's im2col ([V]:536-539).  img_u8: uint8 [B, cin, H, W] (hwc = 0) or [B, H, W, cin] (hwc = 1);
+ * mean / stdv: HOST arrays of cin floats in OUTPUT channel order (models.py:38-39); flip_channels = bgr_to_rgb | rgb_to_bgr. */
+int mtp_patchify_u8(const void* img_u8, int hwc, int flip_channels, const float* mean, const float* stdv, void* out_bf16, int B, int cin,
+                    int H, int W, mtp_stream_t stream);
 int mtp_tok_to_nchw(const void* tok, int tok_is_bf16, int ld, void* out, int out_is_bf16, int B, int h, int w, int C, int level,
                     mtp_stream_t stream);
 int mtp_nchw_to_tok(const void* in, int in_is_bf16, void* tok, int tok_is_bf16, int ld, int accumulate, int B, int h, int w, int C,
@@ -182,6 +189,8 @@ int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, int B, int 
 /* Stand-in objective when no decoder heads are attached (the reference's heads are third-party code): for one bf16
  * feature map of n elements (n % 8 == 0)  *loss += 0.5 * mean(f^2)  and  grad = f / n. */
 int mtp_sqloss_fwd_bwd(const void* feat_bf16, void* grad_bf16, float* loss, size_t n, mtp_stream_t stream);
+/* weighted: loss += weight * 0.5 * mean(f^2), grad = weight * f / n  (one stand-in head of the three-task step, models.py:327-335) */
+int mtp_sqloss_fwd_bwd_w(const void* feat_bf16, void* grad_bf16, float* loss, size_t n, float weight, mtp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Attention backward (autograd of the forward entry points above; everything is recomputed from qkv + lse).

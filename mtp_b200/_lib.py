@@ -51,11 +51,13 @@ _SIGNATURES = {
     "mtp_rvsa_attn_fwd": [c_void_p] * 7 + [c_int] * 5 + [c_void_p],
     "mtp_full_attn_fwd": [c_void_p] * 5 + [c_int] * 5 + [c_void_p],
     "mtp_patchify": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_patchify_u8": [c_void_p, c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_tok_to_nchw": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_nchw_to_tok": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_maxpool2_tok_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_maxpool2_tok_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_sqloss_fwd_bwd": [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "mtp_sqloss_fwd_bwd_w": [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p],
     "mtp_rvsa_attn_bwd": [c_void_p] * 14 + [c_int] * 6 + [c_void_p],
     "mtp_rvsa_sampling_bwd": [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
     "mtp_full_attn_bwd": [c_void_p] * 10 + [c_int] * 5 + [c_void_p],

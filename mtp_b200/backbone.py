@@ -172,6 +172,7 @@ class ViT_Win_RVSA_V3_WSZ7(nn.Module):
         self.return_tuple = return_tuple
         self.frozen_stages = frozen_stages
         self._engine_state = _engine.EngineState()
+        self.input_preprocess = None     # optional mtp_b200.preprocess.ImagePreprocess: accept uint8 images, normalise in the patch gather
         # weights replaced wholesale: drop cached bf16 copies / refresh always-current mirrors (engine.EngineState.invalidate)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._engine_state.invalidate())
 

@@ -37,6 +37,45 @@ patchify_kernel(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ out, in
   }
 }
 
+// uint8 images straight from the loader, with MTP_DataPreprocessor's arithmetic folded in (Multi-Task_Pretrain/preprocessing.py:145-187
+// -> mmengine ImgDataPreprocessor: optional BGR<->RGB channel flip, .float(), (x - mean[c]) / std[c]); the padding step is the identity
+// because the backbone requires H, W == img_size.  out[(b,py,px), c*256 + ky*16 + kx] = bf16((img[b, src(c), y, x] - mean[c]) / std[c]),
+// src(c) = cin-1-c when `flip`.  Layout CHW (what PackDetInputs hands to the preprocessor) or HWC (a decoded image as it lies in memory).
+struct PreNorm { float mean[4], stdv[4]; };
+
+template <bool HWC>
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int cin, int H, int W, int gh, int gw, int flip,
+                   const PreNorm pn) {
+  MTP_PDL_ENTRY();
+  const int chunks_per_tok = cin * 16 * 4;                 // 4-pixel chunks per token row
+  const size_t total = (size_t)B * gh * gw * chunks_per_tok;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks_per_tok);
+    const size_t tok = i / chunks_per_tok;
+    const int kx4 = ch & 3, ky = (ch >> 2) & 15, c = ch >> 6;
+    const int px = (int)(tok % gw), py = (int)((tok / gw) % gh), b = (int)(tok / ((size_t)gw * gh));
+    const int cs = flip ? cin - 1 - c : c;
+    const int y = py * 16 + ky, x = px * 16 + kx4 * 4;
+    float v[4];
+    if (HWC) {
+      const uint8_t* src = img + (((size_t)b * H + y) * W + x) * cin + cs;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (float)src[k * cin];
+    } else {
+      const uchar4 u = *reinterpret_cast<const uchar4*>(img + (((size_t)b * cin + cs) * H + y) * W + x);
+      v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+    }
+    const float m = pn.mean[c], sd = pn.stdv[c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __fdiv_rn(v[k] - m, sd);      // IEEE division: identical to the reference's fp32 (x - mean) / std
+    uint2 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(out + tok * (size_t)(cin * 256) + c * 256 + ky * 16 + kx4 * 4) = o;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- tok <-> NCHW
 struct MapGeom { int B, h, w, C, L; };      // base grid h x w, channels C, pixel-shuffle level L (0, 1, 2)
 
@@ -202,6 +241,29 @@ extern "C" int mtp_patchify(const void* img, int img_is_bf16, void* out_bf16, in
   return check_launch("patchify_kernel");
 }
 
+extern "C" int mtp_patchify_u8(const void* img_u8, int hwc, int flip_channels, const float* mean, const float* stdv, void* out_bf16, int B,
+                               int cin, int H, int W, mtp_stream_t stream) {
+  MTP_REQUIRE(img_u8 && out_bf16 && mean && stdv, "mtp_patchify_u8: null pointer");
+  MTP_REQUIRE(B > 0 && cin > 0 && cin <= 4 && H >= 16 && W >= 16 && W % 4 == 0, "mtp_patchify_u8: B=%d cin=%d H=%d W=%d unsupported", B, cin, H, W);
+  MTP_REQUIRE(hwc || ((uintptr_t)img_u8 & 3) == 0, "mtp_patchify_u8: CHW images must be 4-byte aligned");
+  PreNorm pn;
+  for (int c = 0; c < 4; ++c) {
+    pn.mean[c] = c < cin ? mean[c] : 0.f;                 // host arrays, passed by value
+    pn.stdv[c] = c < cin ? stdv[c] : 1.f;
+    MTP_REQUIRE(pn.stdv[c] != 0.f, "mtp_patchify_u8: std[%d] == 0", c);
+  }
+  const int gh = H / 16, gw = W / 16;
+  const size_t total = (size_t)B * gh * gw * cin * 64;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (hwc)
+    (void)launch_k(patchify_u8_kernel<true>, grid_for(total, 256), 256, 0, st, reinterpret_cast<const uint8_t*>(img_u8),
+                   reinterpret_cast<__nv_bfloat16*>(out_bf16), B, cin, H, W, gh, gw, flip_channels, pn);
+  else
+    (void)launch_k(patchify_u8_kernel<false>, grid_for(total, 256), 256, 0, st, reinterpret_cast<const uint8_t*>(img_u8),
+                   reinterpret_cast<__nv_bfloat16*>(out_bf16), B, cin, H, W, gh, gw, flip_channels, pn);
+  return check_launch("patchify_u8_kernel");
+}
+
 extern "C" int mtp_tok_to_nchw(const void* tok, int tok_is_bf16, int ld, void* out, int out_is_bf16, int B, int h, int w, int C,
                                int level, mtp_stream_t stream) {
   MTP_REQUIRE(tok && out, "mtp_tok_to_nchw: null pointer");
@@ -252,11 +314,16 @@ extern "C" int mtp_maxpool2_tok_bwd(const float* x, const float* dy, float* dx, 
   return check_launch("maxpool2_tok_bwd_kernel");
 }
 
-extern "C" int mtp_sqloss_fwd_bwd(const void* feat_bf16, void* grad_bf16, float* loss, size_t n, mtp_stream_t stream) {
+extern "C" int mtp_sqloss_fwd_bwd_w(const void* feat_bf16, void* grad_bf16, float* loss, size_t n, float weight, mtp_stream_t stream) {
   MTP_REQUIRE(feat_bf16 && grad_bf16 && loss && n > 0 && n % 8 == 0, "mtp_sqloss_fwd_bwd: bad args (n must be a positive multiple of 8)");
+  MTP_REQUIRE((((uintptr_t)feat_bf16 | (uintptr_t)grad_bf16) & 15) == 0, "mtp_sqloss_fwd_bwd: pointers must be 16-byte aligned");
   const size_t n8 = n / 8;
   const int grid = (int)std::min<size_t>((n8 + 255) / 256, (size_t)num_sms() * 8);
   (void)launch_k(sqloss_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(feat_bf16),
-                 reinterpret_cast<__nv_bfloat16*>(grad_bf16), loss, n8, 1.0f / (float)n);
+                 reinterpret_cast<__nv_bfloat16*>(grad_bf16), loss, n8, weight / (float)n);
   return check_launch("sqloss_kernel");
+}
+
+extern "C" int mtp_sqloss_fwd_bwd(const void* feat_bf16, void* grad_bf16, float* loss, size_t n, mtp_stream_t stream) {
+  return mtp_sqloss_fwd_bwd_w(feat_bf16, grad_bf16, loss, n, 1.0f, stream);
 }

@@ -187,13 +187,19 @@ def _check_input(m, x):
     if x.device.index != torch.cuda.current_device():
         raise RuntimeError(f"mtp_b200: input lives on {x.device} but the current CUDA device is cuda:{torch.cuda.current_device()} "
                            "(kernels are enqueued on the current device's stream): wrap the call in torch.cuda.device(x.device)")
-    if x.dim() != 4 or x.shape[1] != m.in_chans:
-        raise ValueError(f"expected (B, {m.in_chans}, H, W), got {tuple(x.shape)}")
+    pre = getattr(m, "input_preprocess", None)
+    hwc = x.dtype == torch.uint8 and pre is not None and pre.layout == "hwc"
+    cdim, hdim, wdim = (3, 1, 2) if hwc else (1, 2, 3)
+    if x.dim() != 4 or x.shape[cdim] != m.in_chans:
+        raise ValueError(f"expected {'(B, H, W, %d)' % m.in_chans if hwc else '(B, %d, H, W)' % m.in_chans}, got {tuple(x.shape)}")
     gh, gw = m.patch_embed.patch_shape
-    if x.shape[2] != gh * 16 or x.shape[3] != gw * 16:
-        raise ValueError(f"input {tuple(x.shape[2:])} must equal img_size {(gh * 16, gw * 16)} (fixed pos_embed / rel-pos tables, [V]:103,629)")
-    if x.dtype not in (F32, BF16):
-        raise TypeError("input must be float32 or bfloat16")
+    if x.shape[hdim] != gh * 16 or x.shape[wdim] != gw * 16:
+        raise ValueError(f"input {(x.shape[hdim], x.shape[wdim])} must equal img_size {(gh * 16, gw * 16)} (fixed pos_embed / rel-pos tables, [V]:103,629)")
+    if x.dtype == torch.uint8:
+        if pre is None:
+            raise TypeError("uint8 input needs module.input_preprocess = ImagePreprocess(mean, std, ...) (the fused MTP_DataPreprocessor)")
+    elif x.dtype not in (F32, BF16):
+        raise TypeError("input must be float32, bfloat16, or uint8 with input_preprocess set")
     return gh, gw
 
 
@@ -203,7 +209,13 @@ def _forward_impl(m, x, keep, save):
     B, C, nH = x.shape[0], W.C, W.nH
     T = B * gh * gw
     x = x.contiguous()
-    patches = ops.patchify(x)
+    if x.dtype == torch.uint8:          # MTP_DataPreprocessor (BGR->RGB, mean/std) folded into the patch gather
+        pre = m.input_preprocess
+        patches = ops.patchify_u8(x, pre.mean, pre.std, pre.flip_channels, pre.layout == "hwc")
+        out_dtype = pre.out_dtype
+    else:
+        patches = ops.patchify(x)
+        out_dtype = x.dtype
     xres = torch.empty(T, C, device=x.device, dtype=F32)
     K0 = patches.shape[1]
     if W.pos is not None:
@@ -231,11 +243,11 @@ def _forward_impl(m, x, keep, save):
         yl, meanl, rstdl = ops.layernorm_fwd(xres, W.norm_w, W.norm_b, save_stats=save)
         feats = [yl, yl, yl, yl]
         final = dict(x=xres, mean=meanl, rstd=rstdl)
-    outs, fpn_saved = _fpn_forward(m, W, feats, B, gh, gw, x.dtype, save)
+    outs, fpn_saved = _fpn_forward(m, W, feats, B, gh, gw, out_dtype, save)
     ctx = None
     if save:
         ctx = dict(W=W, B=B, gh=gh, gw=gw, patches=patches, blocks=blocks_saved, fpn=fpn_saved, final=final, keep=keep,
-                   feats=feats, out_dtype=x.dtype, ckpt=ckpt)
+                   feats=feats, out_dtype=out_dtype, ckpt=ckpt)
     return outs, ctx
 
 

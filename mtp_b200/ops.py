@@ -153,6 +153,21 @@ def patchify(img):
     return out
 
 
+def patchify_u8(img, mean, std, flip_channels, hwc):
+    """uint8 images (B,cin,H,W) or (B,H,W,cin) -> normalised bf16 patch rows (MTP_DataPreprocessor + im2col in one pass)."""
+    assert img.is_cuda and img.dtype == torch.uint8 and img.is_contiguous()
+    if hwc:
+        B, H, W, cin = img.shape
+    else:
+        B, cin, H, W = img.shape
+    assert len(mean) == cin and len(std) == cin
+    out = torch.empty(B * (H // 16) * (W // 16), cin * 256, device=img.device, dtype=BF16)
+    fa = (ctypes.c_float * cin)
+    L.call("mtp_patchify_u8", img.data_ptr(), int(bool(hwc)), int(bool(flip_channels)), fa(*[float(v) for v in mean]),
+           fa(*[float(v) for v in std]), out.data_ptr(), B, cin, H, W, _stream())
+    return out
+
+
 def tok_to_nchw(tok, B, h, w, C, level, out_dtype):
     out = torch.empty(B, C, h << level, w << level, device=tok.device, dtype=out_dtype)
     L.call("mtp_tok_to_nchw", tok.data_ptr(), int(tok.dtype == BF16), int(tok.shape[-1]), out.data_ptr(), int(out_dtype == BF16),

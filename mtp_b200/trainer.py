@@ -41,22 +41,61 @@ def layer_decay_group(name: str, shape, num_layers: int, prefix: str = "encoder.
     return lid, no_decay
 
 
-def synthetic_heads(feats: Sequence[torch.Tensor]):
-    """Stand-in objective: 0.5 * sum_k mean(f_k^2); returns (loss, d loss / d f_k)."""
-    if all(f.is_cuda and f.dtype == torch.bfloat16 and f.is_contiguous() and f.numel() % 8 == 0 for f in feats):
-        loss = torch.zeros((), device=feats[0].device, dtype=F32)       # one fused pass per map (mtp_sqloss_fwd_bwd)
-        grads = [torch.empty_like(f) for f in feats]
+def synthetic_heads(feats: Sequence[torch.Tensor], grads: Optional[Sequence[torch.Tensor]] = None, loss: Optional[torch.Tensor] = None,
+                    weight: float = 1.0):
+    """Stand-in objective: weight * 0.5 * sum_k mean(f_k^2); returns (loss, d loss / d f_k).  ``grads`` / ``loss``: write the
+    cotangents into the given tensors (views of a larger batch) and add into an existing loss scalar."""
+    fused = all(f.is_cuda and f.dtype == torch.bfloat16 and f.is_contiguous() and f.numel() % 8 == 0 and f.data_ptr() % 16 == 0 for f in feats)
+    if grads is not None:
+        fused = fused and all(g.is_contiguous() and g.dtype == torch.bfloat16 and g.data_ptr() % 16 == 0 for g in grads)
+    if fused:
+        if loss is None:
+            loss = torch.zeros((), device=feats[0].device, dtype=F32)       # one fused pass per map (mtp_sqloss_fwd_bwd)
+        if grads is None:
+            grads = [torch.empty_like(f) for f in feats]
         for f, g in zip(feats, grads):
-            L.call("mtp_sqloss_fwd_bwd", f.data_ptr(), g.data_ptr(), loss.data_ptr(), f.numel(), ops._stream())
+            L.call("mtp_sqloss_fwd_bwd_w", f.data_ptr(), g.data_ptr(), loss.data_ptr(), f.numel(), float(weight), ops._stream())
         return loss, grads
-    loss = None
-    grads = []
-    for f in feats:
+    out = []
+    for k, f in enumerate(feats):
         ff = f.float()
-        l = (ff * ff).mean() * 0.5
+        l = (ff * ff).mean() * (0.5 * weight)
         loss = l if loss is None else loss + l
-        grads.append((ff * (1.0 / f.numel())).to(f.dtype))
-    return loss, grads
+        g = (ff * (weight / f.numel())).to(f.dtype)
+        if grads is not None:
+            grads[k].copy_(g)
+            g = grads[k]
+        out.append(g)
+    return loss, out
+
+
+class ThreeTaskHeads:
+    """The fan-out of MTP.forward (Multi-Task_Pretrain/models.py:327-335): ONE encoder call on ``cat(x1, x2, x3)``; the four feature
+    maps are split on-device ``[:b1] | [b1:b1+b2] | [b1+b2:]`` and handed to the semantic-segmentation, rotated-detection and
+    instance-segmentation decoders, whose cotangents land in the matching batch slices of one gradient tensor per map.
+    ``heads[k](feats_k, grads_k, loss)`` must write d loss_k / d feats_k into ``grads_k`` (views) and add loss_k into ``loss``.
+    The decoders themselves are third-party (mmseg / mmrotate / mmdet, out of scope); the default stand-ins consume the same 4-map
+    contract with distinct weights so that the three slices carry different cotangents."""
+
+    def __init__(self, split: Sequence[int], heads: Optional[Sequence[Callable]] = None):
+        assert len(split) == 3 and all(b > 0 for b in split)
+        self.split = tuple(int(b) for b in split)
+        if heads is None:
+            heads = [lambda f, g, l, w=w: synthetic_heads(f, g, l, weight=w) for w in (1.0, 0.5, 2.0)]
+        assert len(heads) == 3
+        self.heads = list(heads)
+
+    def __call__(self, feats: Sequence[torch.Tensor]):
+        assert feats[0].shape[0] == sum(self.split), f"batch {feats[0].shape[0]} != split {self.split}"
+        loss = torch.zeros((), device=feats[0].device, dtype=F32)
+        grads = [torch.empty_like(f) for f in feats]
+        lo = 0
+        for b, head in zip(self.split, self.heads):
+            fk = [f[lo:lo + b] for f in feats]          # batch slices of contiguous NCHW maps are contiguous views: no copies
+            gk = [g[lo:lo + b] for g in grads]
+            head(fk, gk, loss)
+            lo += b
+        return loss, grads
 
 
 class PretrainStep:
@@ -309,7 +348,8 @@ class PretrainStep:
         if self.graph is None:
             self._capture(x)
             self.graph = True
-        self._static_x.copy_(x, non_blocking=True)
+        if x.data_ptr() != self._static_x.data_ptr():
+            self._static_x.copy_(x, non_blocking=True)
         last = len(self.graphs) - 1
         for k, g in enumerate(self.graphs):
             if k == last and self.world > 1:
@@ -318,7 +358,20 @@ class PretrainStep:
             self._reduce(self.reduce_after[k])
         return self._static_loss
 
-    def step_from_host(self, x_host_pinned: torch.Tensor) -> float:
-        """End-to-end step: host (pinned) batch -> device, step, loss back to the host."""
+    def step_from_host(self, x_host_pinned) -> float:
+        """End-to-end step: host (pinned) batch -> device, step, loss back to the host.  A tuple / list of three pinned batches
+        (the three task streams of models.py:327-329) is concatenated on the way: each stream is copied straight into its batch slice
+        of the step's input buffer (``x = torch.cat((x1, x2, x3), 0)`` without the extra device copy)."""
+        if isinstance(x_host_pinned, (tuple, list)):
+            parts = list(x_host_pinned)
+            n = sum(p.shape[0] for p in parts)
+            buf = self._static_x if (self.use_cuda_graph and self._static_x is not None and self._static_x.shape[0] == n
+                                     and self._static_x.dtype == parts[0].dtype) else \
+                torch.empty((n,) + tuple(parts[0].shape[1:]), device=self.dev, dtype=parts[0].dtype)
+            lo = 0
+            for p in parts:
+                buf[lo:lo + p.shape[0]].copy_(p, non_blocking=True)
+                lo += p.shape[0]
+            return float(self.step(buf).item())
         x = x_host_pinned.to(self.dev, non_blocking=True)
         return float(self.step(x).item())

@@ -57,3 +57,38 @@ def test_maxpool_fwd_bwd():
     dx = torch.ones(B * h * w, C, device="cuda")
     ops.maxpool2_tok_bwd(x.reshape(-1, C), dy.permute(0, 2, 3, 1).reshape(-1, C).contiguous(), dx, B, h, w, C)
     assert (dx.reshape(B, h, w, C).permute(0, 3, 1, 2) - 1 - xr.grad).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("layout,flip", [("chw", True), ("hwc", True), ("chw", False)])
+def test_patchify_u8_fused_preprocess_bit_exact(layout, flip):
+    """MTP_DataPreprocessor (BGR->RGB, mean/std, preprocessing.py:145-187 / mmengine ImgDataPreprocessor) folded into the patch gather:
+    bit-exact against the torch restatement of that arithmetic followed by the fp32 patchify."""
+    from mtp_b200 import ops
+    from mtp_b200.preprocess import ImagePreprocess
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 3, 64, 96
+    shape = (B, H, W, 3) if layout == "hwc" else (B, 3, H, W)
+    x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g).cuda()
+    pre = ImagePreprocess(bgr_to_rgb=flip, layout=layout)
+    got = ops.patchify_u8(x, pre.mean, pre.std, pre.flip_channels, layout == "hwc")
+    want = ops.patchify(pre.reference(x).contiguous())
+    assert torch.equal(got, want)
+
+
+def test_backbone_accepts_uint8_with_input_preprocess():
+    from mtp_b200.preprocess import ImagePreprocess
+    from tests.test_backbone_gpu import build_module
+    from tests.helpers import load_golden
+    g = load_golden("tiny160")
+    m = build_module("tiny160")
+    m.load_state_dict(g["sd"])
+    m = m.cuda().eval()
+    x = torch.randint(0, 256, (2, 3, 160, 160), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).cuda()
+    with pytest.raises(TypeError):
+        m(x)
+    m.input_preprocess = ImagePreprocess()
+    with torch.no_grad():
+        a = m(x)
+        b = m(m.input_preprocess.reference(x).contiguous())
+    for u, v in zip(a, b):
+        assert u.dtype == torch.float32 and torch.equal(u, v)

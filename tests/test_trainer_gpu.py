@@ -167,3 +167,39 @@ def test_trainer_state_dict_round_trip_and_weight_reload():
     assert abs(la - lb) <= 1e-5 * abs(la), (la, lb)
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert torch.allclose(pa, pb, rtol=0, atol=1e-6), n
+
+
+def test_three_task_fan_out_matches_one_head_per_slice():
+    """models.py:327-335: one encoder call on cat(x1,x2,x3), maps split b1|b2|b3, three heads, cotangents in the matching slices."""
+    from mtp_b200.trainer import ThreeTaskHeads, synthetic_heads
+    torch.manual_seed(4)
+    feats = [torch.randn(8, 64, s, s, device="cuda").to(torch.bfloat16) for s in (56, 28, 14, 7)]
+    heads = ThreeTaskHeads((3, 3, 2))
+    loss, grads = heads(feats)
+    ref = 0.0
+    lo = 0
+    for b, w in zip((3, 3, 2), (1.0, 0.5, 2.0)):
+        for f, g in zip(feats, grads):
+            fk = f[lo:lo + b].float()
+            ref = ref + (fk ** 2).mean() * 0.5 * w
+            assert torch.equal(g[lo:lo + b], (fk * (w / fk.numel())).to(torch.bfloat16))
+        lo += b
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+
+
+def test_three_stream_uint8_step_from_host():
+    """The e2e shape of the reference step: three pinned uint8 batches -> one encoder call with the fused preprocessor -> three heads."""
+    from mtp_b200.preprocess import ImagePreprocess
+    from mtp_b200.trainer import PretrainStep, ThreeTaskHeads
+    g = load_golden("tiny160")
+    m = build_module("tiny160")
+    m.load_state_dict(g["sd"])
+    m = m.cuda().train()
+    m.input_preprocess = ImagePreprocess(out_dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(9)
+    parts = [torch.randint(0, 256, (b, 3, 160, 160), dtype=torch.uint8, generator=gen).pin_memory() for b in (3, 3, 2)]
+    for graph in (False, True):
+        tr = PretrainStep(m, lr=1e-4, max_norm=5.0, heads=ThreeTaskHeads((3, 3, 2)), use_cuda_graph=graph)
+        l0 = tr.step_from_host(parts)
+        l1 = tr.step_from_host(parts)
+        assert l0 == l0 and l1 == l1 and l0 > 0 and l1 != l0

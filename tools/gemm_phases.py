@@ -5,7 +5,10 @@ import torch
 from mtp_b200 import ops, _lib as L
 
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
-CASES = [("qkv fwd", 1568, 3072, 1024, L.EPI_BF16, 192), ("qkv fwd pair", 1568, 3072, 1024, L.EPI_BF16, 1192),
+CASES = [("fc1 fwd gelu 256", 1568, 4096, 1024, L.EPI_BF16_GELU, 256), ("fc1 fwd gelu pair256", 1568, 4096, 1024, L.EPI_BF16_GELU, 1256),
+         ("fc1 fwd gelu 192", 1568, 4096, 1024, L.EPI_BF16_GELU, 192), ("fc1 fwd plain 256", 1568, 4096, 1024, L.EPI_BF16, 256),
+         ("fc1 fwd plain pair256", 1568, 4096, 1024, L.EPI_BF16, 1256),
+         ("qkv fwd", 1568, 3072, 1024, L.EPI_BF16, 192), ("qkv fwd pair", 1568, 3072, 1024, L.EPI_BF16, 1192),
          ("qkv fwd 256", 1568, 3072, 1024, L.EPI_BF16, 256), ("qkv fwd pair256", 1568, 3072, 1024, L.EPI_BF16, 1256),
          ("qkv fwd 128", 1568, 3072, 1024, L.EPI_BF16, 128), ("qkv fwd 64", 1568, 3072, 1024, L.EPI_BF16, 64),
          ("1 CTA only 192", 128, 192, 1024, L.EPI_BF16, 192), ("37 CTAs 192", 37 * 128, 192, 1024, L.EPI_BF16, 192),
