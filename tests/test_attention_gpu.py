@@ -56,7 +56,8 @@ def test_rvsa_attention_vs_oracle(grid, B, nH, big):
     torch.cuda.synchronize()
     got = out.float().cpu().reshape(B, grid * grid, C)
     err = (got - want).abs()
-    assert err.max().item() < 2e-2          # bf16 output rounding of O(1) values
+    # bf16 output rounding (2^-9 relative) on top of the bf16 K~ / V~ / P staging: bounded relative to the output scale
+    assert err.max().item() < 1e-2 * max(2.0, want.abs().max().item())
     assert (err.norm() / want.norm()).item() < 4e-3
     # sampling params against the oracle
     pt, pb, pl, pr = O.window_padding(grid, grid)
