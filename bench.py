@@ -1,18 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: ViT-L + RVSA backbone pretrain step @224^2, bf16, synthetic data (BASELINE.json metric).
+"""Benchmark of the hot path: ViT + RVSA backbone pretrain step, bf16, synthetic data (BASELINE.json metric and configs).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5
+    python bench.py --gpus 1 --steps 20 --warmup 5                      # headline: config c3 (ViT-L @224^2, 8 images per GPU)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores, same metric
+    python bench.py --impl reference ...                                # the reference's CPU path (oracle port) on the host cores
+    python bench.py --config c2|c4|c5 ...                               # the other BASELINE.json configurations (see CONFIGS)
 
-A "step" = one encoder call on an 8-image batch per GPU (global batch 64 at 8 GPUs, weak scaling) + synthetic heads +
-full backward + gradient all-reduce (N > 1) + global-norm clip + fused AdamW.  Prints ONE JSON line on rank 0.
+Headline step (c3, Multi-Task_Pretrain/models.py:306-335 + main_pretrain.py:701-832 for the encoder): three uint8 image streams
+(3 + 3 + 2 images per GPU) -> MTP_DataPreprocessor arithmetic fused into the patch gather -> ONE encoder call on the concatenated
+batch -> feature maps split 3|3|2 to three stand-in heads (the decoders are third-party, out of scope) -> full backward ->
+gradient all-reduce (N > 1) -> global-norm clip -> fused AdamW.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -22,9 +24,23 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-MODEL = dict(img_size=224, embed_dim=1024, depth=24, num_heads=16, interval=6, out_indices=[7, 11, 15, 23])
-PER_GPU_BATCH = 8
-FWD_GFLOP_PER_IMG = 130.20          # SURVEY.md Appendix C (oracle.algorithmic_gflop_per_image reproduces it)
+VIT = {"b": dict(embed_dim=768, depth=12, num_heads=12, interval=3, out_indices=[3, 5, 7, 11]),
+       "l": dict(embed_dim=1024, depth=24, num_heads=16, interval=6, out_indices=[7, 11, 15, 23])}
+# BASELINE.json `configs`: model, image side, images per GPU, what a step is
+CONFIGS = {
+    "c2": dict(model="b", img=224, batch=32, mode="fwdbwd",
+               metric="images/sec ViT-B+RVSA backbone fwd+bwd @224^2 bf16", workload="ViT-B+RVSA backbone fwd+bwd, batch 32 @224^2 (BASELINE configs[1])"),
+    "c3": dict(model="l", img=224, batch=8, mode="step",
+               metric="images/sec ViT-L+RVSA MTP step @224^2 bf16",
+               workload="ViT-L+RVSA backbone pretrain step @224^2: 3 uint8 streams (3|3|2 img) -> fused preprocess -> one encoder call -> "
+                        "3 stand-in heads -> bwd + grad all-reduce + clip + AdamW (BASELINE configs[2], 8 img/GPU)"),
+    "c4": dict(model="l", img=512, batch=2, mode="step",
+               metric="images/sec ViT-L+RVSA finetune-shaped step @512^2 bf16",
+               workload="ViT-L+RVSA backbone step @512^2 (25 windows/img, dense blocks N=1024), 2 img/GPU, stand-in head (BASELINE configs[3])"),
+    "c5": dict(model="l", img=1024, batch=1, mode="fwdbwd",
+               metric="images/sec ViT-L+RVSA backbone fwd+bwd @1024^2 bf16",
+               workload="ViT-L+RVSA backbone fwd+bwd @1024^2 (seq-len 4096, 100 windows/img), 1 img/GPU (BASELINE configs[4])"),
+}
 
 
 def parse():
@@ -33,12 +49,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (0 = the config's)")
     ap.add_argument("--graph", type=int, default=1, help="capture the step into a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gemm-share", action="store_true", help="skip the in-situ GEMM timing pass (leaves the training state intact)")
     ap.add_argument("--bucket-blocks", type=int, default=2, help="transformer blocks per gradient all-reduce bucket (N > 1)")
     ap.add_argument("--comm-sms", type=int, default=16, help="SMs left to NCCL while the backward runs (N > 1)")
-    ap.add_argument("--cpu-batch", type=int, default=1, help="images per CPU-reference step (bounded sample)")
+    ap.add_argument("--float-input", action="store_true", help="feed a pre-normalised bf16 batch instead of uint8 + fused preprocessing")
     return ap.parse_args()
 
 
@@ -99,8 +117,35 @@ class ClockSampler:
                 "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm)}
 
 
-METRIC = "images/sec ViT-L+RVSA MTP step @224^2 bf16"
-WORKLOAD = "ViT-L+RVSA backbone pretrain step @224^2: fwd + synthetic heads + bwd + grad all-reduce + clip + AdamW"
+def split3(B):
+    """The three task streams of models.py:327-329 (`b, b, rest`); 8 images per GPU -> 3 | 3 | 2."""
+    if B < 3:
+        return None
+    b = (B + 2) // 3
+    return (b, b, B - 2 * b) if B - 2 * b > 0 else (b, B - b - 1, 1)
+
+
+def build_module(cfg, drop_path=0.1):
+    from mtp_b200 import ViT_Win_RVSA_V3_WSZ7
+    v = VIT[cfg["model"]]
+    torch.manual_seed(0)
+    m = ViT_Win_RVSA_V3_WSZ7(img_size=cfg["img"], patch_size=16, embed_dim=v["embed_dim"], depth=v["depth"], num_heads=v["num_heads"],
+                             mlp_ratio=4, qkv_bias=True, use_abs_pos_emb=True, interval=v["interval"], out_indices=v["out_indices"],
+                             drop_path_rate=drop_path, use_rel_pos_bias=True)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "rel_pos" in n:                      # zero-initialised in the reference: re-draw so the terms are exercised
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return m
+
+
+def fwd_gflop_per_img(cfg):
+    from oracle import rvsa_oracle as O       # formulas only (SURVEY Appendix C); nothing of the oracle is executed on the timed path
+    v = VIT[cfg["model"]]
+    oc = O.OracleConfig(img_size=cfg["img"], embed_dim=v["embed_dim"], depth=v["depth"], num_heads=v["num_heads"], interval=v["interval"],
+                        out_indices=tuple(v["out_indices"]))
+    return O.algorithmic_gflop_per_image(oc)["total"]
 
 
 # ------------------------------------------------------------------------------------------------------ CPU reference arm
@@ -133,73 +178,123 @@ def usable_threads():
     return max(c for c in cands if times[c] <= 1.15 * tmin)      # the largest count that is still (nearly) the fastest
 
 
-def cpu_reference_rate(batch, steps, warmup, threads=None):
-    """The reference's CPU path (oracle port of [V], fp32) doing the same step: fwd + synthetic heads + bwd + AdamW."""
+def cpu_reference(cfg, steps, warmup, batch, threads=None, forward_only=False):
+    """The reference's CPU path (oracle port of [V], fp32, pinned to the live reference by tests/test_oracle_vs_reference.py) doing the
+    same work on a bounded sample: forward + stand-in heads + backward (+ clip + AdamW for the `step` configs)."""
     from oracle import rvsa_oracle as O
     threads = threads or usable_threads()
     torch.set_num_threads(threads)
-    cfg = O.vit_l_config(224)
-    torch.manual_seed(0)
-    from mtp_b200 import ViT_Win_RVSA_V3_WSZ7
-    m = ViT_Win_RVSA_V3_WSZ7(img_size=224, patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4, qkv_bias=True,
-                             use_abs_pos_emb=True, interval=6, out_indices=[7, 11, 15, 23], drop_path_rate=0.1, use_rel_pos_bias=True)
-    P = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in m.state_dict().items()}
+    v = VIT[cfg["model"]]
+    oc = O.OracleConfig(img_size=cfg["img"], embed_dim=v["embed_dim"], depth=v["depth"], num_heads=v["num_heads"], interval=v["interval"],
+                        out_indices=tuple(v["out_indices"]))
+    m = build_module(cfg)
+    P = {k: (v_.detach().clone().requires_grad_(not forward_only) if v_.is_floating_point() else v_) for k, v_ in m.state_dict().items()}
     del m
-    params = [v for v in P.values() if v.is_floating_point()]
-    opt = torch.optim.AdamW(params, lr=6e-5, weight_decay=0.05)
-    x = torch.randn(batch, 3, 224, 224)
+    params = [t for t in P.values() if t.is_floating_point()]
+    opt = torch.optim.AdamW(params, lr=6e-5, weight_decay=0.05) if (cfg["mode"] == "step" and not forward_only) else None
+    x = torch.randn(batch, 3, cfg["img"], cfg["img"])
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        opt.zero_grad(set_to_none=True)
-        loss = O.synthetic_loss(O.backbone_forward(P, cfg, x))
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 5.0)
-        opt.step()
+        if forward_only:
+            with torch.no_grad():
+                O.backbone_forward(P, oc, x)
+        else:
+            for p in params:
+                p.grad = None
+            loss = O.synthetic_loss(O.backbone_forward(P, oc, x))
+            loss.backward()
+            if opt is not None:
+                torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 5.0)
+                opt.step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return batch / statistics.median(times), threads, sum(times)
 
 
-def run_reference(args, rank):
+def cpu_sample_batch(cfg):
+    return {"c2": 2, "c3": 2, "c4": 1, "c5": 1}[cfg["name"]]       # SURVEY 8d: fwd+bwd B=2 @224^2; one image at the larger sizes
+
+
+def run_reference(args, cfg, rank):
     if rank != 0:
         return
-    rate, threads, total = cpu_reference_rate(args.cpu_batch, args.steps, args.warmup)
-    ms = 1000.0 * args.cpu_batch / rate
-    sample = f"{args.cpu_batch} image(s) per step, ViT-L+RVSA @224 fwd+bwd+AdamW, fp32, {threads} threads"
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    b = cpu_sample_batch(cfg)
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)          # bounded: ~10-30 s of CPU work (SURVEY 8d: 1 warm-up + 3 timed)
+    rate, threads, total = cpu_reference(cfg, steps, warmup, b)
+    ms = 1000.0 * b / rate
+    what = "fwd+bwd+clip+AdamW" if cfg["mode"] == "step" else "fwd+bwd"
+    sample = f"{b} image(s) per step x {steps} timed steps (+{warmup} warm-up), {what}, fp32, {threads} threads, {total:.1f} s"
+    line = {"impl": "reference", "metric": cfg["metric"], "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "implementation": "oracle port of the reference ([V]) on the host cores, fp32",
-                       "per_step_batch": args.cpu_batch},
+            "config": {"workload": cfg["workload"], "implementation": "oracle port of the reference ([V]) on the host cores, fp32",
+                       "per_step_batch": b},
             "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------ native arm
-def build_model(dev):
-    from mtp_b200 import ViT_Win_RVSA_V3_WSZ7
-    torch.manual_seed(0)
-    m = ViT_Win_RVSA_V3_WSZ7(img_size=224, patch_size=16, embed_dim=MODEL["embed_dim"], depth=MODEL["depth"], num_heads=MODEL["num_heads"],
-                             mlp_ratio=4, qkv_bias=True, use_abs_pos_emb=True, interval=MODEL["interval"],
-                             out_indices=MODEL["out_indices"], drop_path_rate=0.1, use_rel_pos_bias=True)
-    g = torch.Generator().manual_seed(1)
-    with torch.no_grad():
-        for n, p in m.named_parameters():
-            if "rel_pos" in n:                      # zero-initialised in the reference: re-draw so the terms are exercised
-                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
-    return m.to(dev).train()
+class FwdBwdStep:
+    """Configs c2 / c5: backbone forward + stand-in heads + full backward, no optimizer (BASELINE: "backbone fwd+bwd")."""
+
+    def __init__(self, model, heads, use_cuda_graph):
+        from mtp_b200 import engine, engine_bwd
+        self.m, self.heads, self.use_graph = model, heads, use_cuda_graph
+        self.engine, self.engine_bwd = engine, engine_bwd
+        self.G = engine_bwd.GradStore(model, next(model.parameters()).device)
+        self.graph = None
+        self.dev = next(model.parameters()).device
+
+    def _body(self, x):
+        keep = self.engine._draw_keep(self.m, x.shape[0], x.device)
+        outs, ctx = self.engine._forward_impl(self.m, x, keep, save=True)
+        loss, douts = self.heads(outs)
+        self.G.flat.zero_()
+        self.G.touched = set()
+        self.engine_bwd.backward_impl(self.m, x, ctx, douts, grad_store=self.G)
+        return loss
+
+    def step(self, x):
+        if not self.use_graph:
+            return self._body(x)
+        if self.graph is None:
+            self._x = x.clone()
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._body(self._x)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._loss = self._body(self._x)
+        if x.data_ptr() != self._x.data_ptr():
+            self._x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self._loss
+
+    def step_from_host(self, parts):
+        if isinstance(parts, (tuple, list)):
+            x = torch.cat([p.to(self.dev, non_blocking=True) for p in parts], 0)
+        else:
+            x = parts.to(self.dev, non_blocking=True)
+        return float(self.step(x).item())
+
+    def _step_body(self, x):
+        return self._body(x)
 
 
-def gemm_profile(trainer, x):
-    """One eager (non-graph) step with CUDA events around every GEMM launch on the launching stream."""
+def gemm_flops_and_bytes(runner, x):
+    """One eager (non-graph) step with every GEMM launch recorded: count, 2*M*N*K, algorithmic bytes (operands read once +
+    outputs written once)."""
     from mtp_b200 import ops
-    recs = []
-    abytes = [0.0]
-    orig = ops.gemm
+    tot = dict(n=0, flops=0.0, bytes=0.0)
+    orig, orig_dual = ops.gemm, ops.gemm_dual
 
-    def alg_bytes(M, N, K, out, aux=None, out2=None, **_):      # operands read once + outputs written once
+    def alg_bytes(M, N, K, out, aux=None, out2=None, **_):
         b = 2.0 * (M * K + N * K) + out.element_size() * M * N
         if aux is not None:
             b += aux.element_size() * M * N
@@ -207,38 +302,28 @@ def gemm_profile(trainer, x):
             b += out2.element_size() * M * N
         return b
 
-    def timed(A, B, M, N, K, out, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = orig(A, B, M, N, K, out, **kw)
-        e1.record()
-        recs.append((e0, e1, 2.0 * M * N * K))
-        abytes[0] += alg_bytes(M, N, K, out, **kw)
-        return r
-    orig_dual = ops.gemm_dual
+    def rec(A, B, M, N, K, out, **kw):
+        tot["n"] += 1
+        tot["flops"] += 2.0 * M * N * K
+        tot["bytes"] += alg_bytes(M, N, K, out, aux=kw.get("aux"), out2=kw.get("out2"))
+        return orig(A, B, M, N, K, out, **kw)
 
-    def timed_dual(g0, g1, force_bn=0):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = orig_dual(g0, g1, force_bn)
-        e1.record()
-        recs.append((e0, e1, 2.0 * (g0["M"] * g0["N"] * g0["K"] + g1["M"] * g1["N"] * g1["K"])))
-        abytes[0] += sum(alg_bytes(g["M"], g["N"], g["K"], g["out"], aux=g.get("aux"), out2=g.get("out2")) for g in (g0, g1))
-        return r
-    ops.gemm = timed
-    ops.gemm_dual = timed_dual
+    def rec_dual(g0, g1, force_bn=0):
+        tot["n"] += 1
+        for g in (g0, g1):
+            tot["flops"] += 2.0 * g["M"] * g["N"] * g["K"]
+            tot["bytes"] += alg_bytes(g["M"], g["N"], g["K"], g["out"], aux=g.get("aux"), out2=g.get("out2"))
+        return orig_dual(g0, g1, force_bn)
+    ops.gemm, ops.gemm_dual = rec, rec_dual
     try:
-        trainer._step_body(x)
+        runner._step_body(x)
         torch.cuda.synchronize()
     finally:
-        ops.gemm = orig
-        ops.gemm_dual = orig_dual
-    ms = sum(a.elapsed_time(b) for a, b, _ in recs)
-    flops = sum(f for _, _, f in recs)
-    return len(recs), ms, flops, abytes[0]
+        ops.gemm, ops.gemm_dual = orig, orig_dual
+    return tot
 
 
-def count_launches(trainer, x):
+def count_launches(runner, x):
     """Kernels of libmtp_b200.so launched per step (entry point -> kernels it enqueues)."""
     from mtp_b200 import _lib
     per_call = {"mtp_rvsa_sampling_fwd": 2, "mtp_rvsa_attn_bwd": 3, "mtp_rvsa_sampling_bwd": 3}
@@ -246,11 +331,12 @@ def count_launches(trainer, x):
     orig = _lib.call
 
     def counting(name, *a):
-        n[0] += per_call.get(name, 1)
+        if not name.startswith(("mtp_set_", "mtp_gemm_set_", "mtp_gemm_last", "mtp_gemm_plan")):
+            n[0] += per_call.get(name, 1)
         return orig(name, *a)
     _lib.call = counting           # ops / trainer / engine_bwd all call through the module attribute
     try:
-        trainer._step_body(x)
+        runner._step_body(x)
         torch.cuda.synchronize()
     finally:
         _lib.call = orig
@@ -259,11 +345,12 @@ def count_launches(trainer, x):
 
 def main():
     args = parse()
+    cfg = dict(CONFIGS[args.config], name=args.config)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, cfg, rank)
         return
     assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device"
     torch.cuda.set_device(local)
@@ -274,15 +361,30 @@ def main():
             os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_sms))       # the SMs PretrainStep(comm_sms=) leaves to the all-reduce kernels
         dist.init_process_group("nccl", device_id=dev)
     from mtp_b200 import _lib
-    from mtp_b200.trainer import PretrainStep
+    from mtp_b200.preprocess import ImagePreprocess
+    from mtp_b200.trainer import PretrainStep, ThreeTaskHeads, synthetic_heads
     _lib.load()
-    B = args.batch
-    model = build_model(dev)
-    trainer = PretrainStep(model, lr=6e-5, weight_decay=0.05, max_norm=5.0, t_max=80000, use_cuda_graph=bool(args.graph),
-                           bucket_blocks=args.bucket_blocks, comm_sms=args.comm_sms)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.randn(B, 3, 224, 224, device=dev, generator=g).to(torch.bfloat16)
-    x_host = x.cpu().pin_memory()
+    B = args.batch or cfg["batch"]
+    S = cfg["img"]
+    model = build_module(cfg).to(dev).train()
+    u8 = not args.float_input
+    if u8:
+        model.input_preprocess = ImagePreprocess(out_dtype=torch.bfloat16)          # models.py:37-41 mean / std / bgr_to_rgb
+    split = split3(B)
+    heads = ThreeTaskHeads(split) if split else synthetic_heads
+    if cfg["mode"] == "step":
+        runner = PretrainStep(model, lr=6e-5, weight_decay=0.05, max_norm=5.0, t_max=80000, use_cuda_graph=bool(args.graph),
+                              bucket_blocks=args.bucket_blocks, comm_sms=args.comm_sms, heads=heads)
+    else:
+        runner = FwdBwdStep(model, heads, bool(args.graph))
+    g = torch.Generator().manual_seed(1234 + rank)
+    sizes = list(split) if split else [B]
+    if u8:
+        parts_host = [torch.randint(0, 256, (b, 3, S, S), dtype=torch.uint8, generator=g).pin_memory() for b in sizes]
+    else:
+        parts_host = [torch.randn(b, 3, S, S, generator=g).to(torch.bfloat16).pin_memory() for b in sizes]
+    x = torch.cat([p.to(dev) for p in parts_host], 0)
+    h2d = sum(p.numel() * p.element_size() for p in parts_host)
 
     def sync_all():
         if world > 1:
@@ -290,18 +392,23 @@ def main():
         torch.cuda.synchronize()
 
     # ---- eager instrumented passes (also serve as warm-up for kernel attributes / allocator)
-    trainer_eager_graph = trainer.use_cuda_graph
-    trainer.use_cuda_graph = False
+    want_graph = bool(args.graph)
+    runner.use_cuda_graph = False
+    if hasattr(runner, "use_graph"):
+        runner.use_graph = False
     for _ in range(2):
-        trainer.step(x)
+        runner.step(x)
     torch.cuda.synchronize()
-    launches = count_launches(trainer, x)
-    n_gemm, gemm_ms, gemm_flops, gemm_alg_bytes = gemm_profile(trainer, x)
-    trainer.use_cuda_graph = trainer_eager_graph
+    launches = count_launches(runner, x)
+    gm = gemm_flops_and_bytes(runner, x)
+    runner.use_cuda_graph = want_graph
+    if hasattr(runner, "use_graph"):
+        runner.use_graph = want_graph
 
-    # ---- device-resident timing
-    for _ in range(max(3, args.warmup)):
-        loss = trainer.step(x)
+    # ---- device-resident timing (inputs in HBM; the working set of a step is >> L2, see config.l2)
+    W = max(3, args.warmup)
+    for _ in range(W):
+        loss = runner.step(x)
     sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -309,7 +416,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = trainer.step(x)
+        loss = runner.step(x)
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -321,13 +428,13 @@ def main():
     value = world * B / (ms_step / 1e3)
     final_loss = float(loss.item())
 
-    # ---- end to end: pinned host batch -> device -> step -> loss back on the host, every step
+    # ---- end to end: pinned host uint8 streams -> device -> step -> loss back on the host, every step
     for _ in range(2):
-        trainer.step_from_host(x_host)
+        runner.step_from_host(parts_host)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        trainer.step_from_host(x_host)
+        runner.step_from_host(parts_host)
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([e2e_ms], device=dev)
@@ -335,62 +442,65 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (t.item() / args.steps / 1e3)
 
-    # ---- GEMM time inside the graph-replayed step: the same step re-captured with empty GEMM launches (mtp_gemm_set_debug_mode 4);
-    #      the difference is what the tcgen05 GEMM kernels cost in situ (operands in the state the step leaves them, PDL overlap
-    #      included).  Run last: the training state is garbage afterwards.
-    gemm_ms_graph = None
-    if args.graph and world == 1:
+    # ---- GEMM time inside the graph-replayed step, measured live at every N: the same step re-captured with empty GEMM launches
+    #      (mtp_gemm_set_debug_mode 4); the difference is what the tcgen05 GEMM kernels cost in situ -- launch gaps, PDL overlap and
+    #      store drain included, i.e. the conservative reading.  Run last: the training state is garbage afterwards.
+    gemm_ms = None
+    if args.graph and not args.no_gemm_share:
         try:
             _lib.call("mtp_gemm_set_debug_mode", 4)
-            trainer.graph = None
+            runner.graph = None
             for _ in range(3):
-                trainer.step(x)
-            torch.cuda.synchronize()
+                runner.step(x)
+            sync_all()
             e0.record()
             for _ in range(args.steps):
-                trainer.step(x)
+                runner.step(x)
             e1.record()
-            torch.cuda.synchronize()
-            gemm_ms_graph = ms_step - e0.elapsed_time(e1) / args.steps
+            sync_all()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gemm_ms = ms_step - t.item() / args.steps
         finally:
             _lib.call("mtp_gemm_set_debug_mode", 0)
-        if gemm_ms_graph is not None and gemm_ms_graph > 0:
-            gemm_ms_eager, gemm_ms = gemm_ms, gemm_ms_graph
 
     if rank == 0:
         pk = peaks()
-        # DRAM traffic of the GEMM launches of one step, from the committed ncu pass (profiles/: dram__bytes_read/write.sum per launch)
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_dram.json")))
-            per_launch = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / max(1, tj["gemm_launches"])
-            traffic = per_launch * n_gemm      # bytes per step over all GEMM launches (same unit of work as `achieved`)
-        except Exception:
-            pass
-        step_tflops = 3.0 * FWD_GFLOP_PER_IMG * (value / world) / 1e3          # per GPU, training step = 3 x forward
-        gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        gf = fwd_gflop_per_img(cfg)
+        step_tflops = 3.0 * gf * (value / world) / 1e3          # per GPU; training step = 3 x forward
+        gemm_tflops = gm["flops"] / (gemm_ms * 1e-3) / 1e12 if gemm_ms and gemm_ms > 0 else None
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": cfg["metric"], "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "per_gpu_batch": B, "global_batch": B * world, "tokens_per_gpu": B * 196, "parallelism": f"dp{world}",
-                       "cuda_graph": bool(args.graph), "l2": "per-step working set (~5 GB of weights, activations, gradients) >> 126 MB L2; no explicit flush",
-                       "loss": final_loss},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": 4},
+            "config": {"workload": cfg["workload"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
+                       "streams": list(split) if split else [B], "input": "uint8 CHW + fused MTP_DataPreprocessor" if u8 else "bf16 normalised",
+                       "tokens_per_gpu": B * (S // 16) ** 2, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
+                       "l2": "per-step working set (weights + activations + gradients, GBs) >> 126 MB L2; no explicit flush", "loss": final_loss},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches * args.steps,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of one step)", "achieved": gemm_tflops,
                          "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": (gemm_tflops / pk["tf_burst"]) if gemm_tflops else None,
-                         "traffic": traffic, "algorithmic_bytes_per_step": gemm_alg_bytes, "peak_source": pk["src"] + " (burst cuBLAS bf16)", "gemm_launches_per_step": n_gemm,
-                         "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_step if ms_step else None,
+                         "traffic": None,       # DRAM bytes are not measurable from inside the run; the ncu pass lives in profiles/
+                         "algorithmic_bytes_per_step": gm["bytes"], "peak_source": pk["src"] + " (burst cuBLAS bf16)",
+                         "gemm_launches_per_step": gm["n"], "gemm_gflop_per_step": gm["flops"] / 1e9, "gemm_ms_per_step": gemm_ms,
+                         "gemm_timing": "in situ: graph-replayed step minus the same step with empty GEMM launches (all ranks, max)",
+                         "gemm_share_of_step": gemm_ms / ms_step if gemm_ms else None,
                          "step_tflops_per_gpu": step_tflops, "step_frac_of_sustained_peak": step_tflops / pk["tf_sustained"]},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
             try:
-                rate, threads, total = cpu_reference_rate(args.cpu_batch, 2, 1)
-                line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                                        "sample": f"{args.cpu_batch} image/step x 2 timed steps (+1 warm-up), ViT-L+RVSA @224 fwd+bwd+AdamW fp32 oracle, {total:.1f} s"}
+                b = cpu_sample_batch(cfg)
+                rate, threads, total = cpu_reference(cfg, 3, 1, b)
+                what = "fwd+bwd+clip+AdamW" if cfg["mode"] == "step" else "fwd+bwd"
+                cb = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                      "sample": f"{b} images/step x 3 timed steps (+1 warm-up), {what}, fp32 oracle port of [V], {total:.1f} s"}
+                if args.config == "c3":         # SURVEY 8d also asks for the forward at B = 8
+                    frate, _, ftotal = cpu_reference(cfg, 3, 1, 8, threads=threads, forward_only=True)
+                    cb["forward_only"] = {"value": frate, "unit": "images/s", "sample": f"8 images x 3 timed forwards (+1 warm-up), {ftotal:.1f} s"}
+                line["cpu_baseline"] = cb
             except Exception as ex:      # the baseline is informative; never lose the GPU line to it
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)

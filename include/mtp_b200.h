@@ -82,6 +82,11 @@ typedef struct mtp_epilogue {
                              Linear whose cotangent this GEMM produces); 16-byte aligned */
   float* sumsq;           /* F32: optional scalar, += sum of squares of the stored outputs (gradient-norm clipping without a
                              separate pass over the weight gradients) */
+  int hilo;               /* fp32-class mode ("fp32x3", forward only): A [M, 2K] and B [N, 2K] hold every value as TWO bf16 words, hi = bf16(v)
+                             in columns [0, K) and lo = bf16(v - hi) in [K, 2K) (K-major, lda/ldb >= 2K); the kernel accumulates
+                             A_hi B_hi + A_hi B_lo + A_lo B_hi in fp32 (three passes over K through the same tcgen05 pipeline: relative error
+                             ~2^-16 instead of 2^-9).  bf16 outputs are written as hi | lo pairs too, see out_lo_offset */
+  int out_lo_offset;      /* > 0: BF16 / BF16_GELU epilogues also store lo = bf16(v - bf16(v)) at out[m * ldo + out_lo_offset + n] */
   int b_static;           /* 1: operand B is NOT written by the kernels just before this one in the stream (weights, activations
                              saved earlier): its first tiles may be fetched before the programmatic-dependent-launch wait */
 } mtp_epilogue;
@@ -239,6 +244,27 @@ int mtp_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, c
                    const float* group_lr_scale, const float* group_weight_decay, const float* state, size_t n, float lr0,
                    float eta_min, int t_max, float beta1, float beta2, float eps, float max_norm, float grad_scale,
                    mtp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * fp32-class forward mode ("fp32x3", precision="fp32x3" on the module; forward only).  Every bf16 tensor of the fast path is stored as
+ * hi | lo bf16 word pairs ([rows, 2K]: hi = bf16(v) in columns [0, K), lo = bf16(v - hi) in [K, 2K)); GEMMs run with mtp_epilogue.hilo
+ * (three tcgen05 passes, fp32 accumulate), attention in fp32.  Used to meet BASELINE north_star's "forward within 1e-3 rel of the
+ * reference" at ViT-L depth -- the reference itself is fp32 (main_pretrain.py never enters autocast) -- and as a full-depth logic check.
+ * Same operators as above: [V]:536-539 (patchify), :596 (LayerNorm), :287-433 (RVSA), :90-111 (dense attention), :807-811 (maps). */
+int mtp_split_hilo(const float* in, int ld_in, void* out_hilo, size_t rows, int K, mtp_stream_t stream);
+int mtp_patchify_hilo(const float* img, void* out_hilo, int B, int cin, int H, int W, mtp_stream_t stream);
+/* x: fp32 [rows, C], or hi|lo words where logical row r sits in physical row r / x_sub (pitch x_ld) at column (r % x_sub) * C, lo words
+ * x_lo_offset further on; y_hilo: [rows, C | C] */
+int mtp_layernorm_fwd_hilo(const void* x, int x_is_hilo, int x_ld, int x_lo_offset, int x_sub, const float* gamma, const float* beta,
+                           void* y_hilo, int rows, int C, float eps, int fuse_gelu, mtp_stream_t stream);
+int mtp_rvsa_sampling_fwd_hilo(const void* yn_hilo, const float* w_off, const float* b_off, const float* w_scale, const float* b_scale,
+                               const float* w_angle, const float* b_angle, float* pooled, float* params, int B, int h, int w, int C, int nH,
+                               mtp_stream_t stream);
+int mtp_rvsa_attn_fwd_hilo(const void* qkv_hilo, const float* params, const float* rel_pos_h, const float* rel_pos_w,
+                           const float* bias_table, void* out_hilo, int B, int h, int w, int C, int nH, mtp_stream_t stream);
+int mtp_full_attn_fwd_hilo(const void* qkv_hilo, const float* rel_pos_h, const float* rel_pos_w, void* out_hilo, int B, int gh, int gw,
+                           int C, int nH, mtp_stream_t stream);
+int mtp_tok_to_nchw_hilo(const void* tok_hilo, int ld, int lo_offset, float* out, int B, int h, int w, int C, int level, mtp_stream_t stream);
 
 #ifdef __cplusplus
 }

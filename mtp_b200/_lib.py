@@ -19,7 +19,7 @@ class Epilogue(ctypes.Structure):
     """struct mtp_epilogue (include/mtp_b200.h)."""
     _fields_ = [("mode", c_int), ("ldo", c_int), ("bias", c_void_p), ("out", c_void_p), ("out2", c_void_p),
                 ("aux", c_void_p), ("row_scale", c_void_p), ("rows_per_group", c_int), ("pos_rows", c_int),
-                ("accumulate", c_int), ("ps_h", c_int), ("ps_w", c_int), ("ps_cout", c_int), ("colsum", c_void_p), ("sumsq", c_void_p), ("b_static", c_int)]
+                ("accumulate", c_int), ("ps_h", c_int), ("ps_w", c_int), ("ps_cout", c_int), ("colsum", c_void_p), ("sumsq", c_void_p), ("hilo", c_int), ("out_lo_offset", c_int), ("b_static", c_int)]
 
 
 class GemmDesc(ctypes.Structure):
@@ -61,6 +61,13 @@ _SIGNATURES = {
     "mtp_rvsa_attn_bwd": [c_void_p] * 14 + [c_int] * 6 + [c_void_p],
     "mtp_rvsa_sampling_bwd": [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
     "mtp_full_attn_bwd": [c_void_p] * 10 + [c_int] * 5 + [c_void_p],
+    "mtp_split_hilo": [c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p],
+    "mtp_patchify_hilo": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_layernorm_fwd_hilo": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],
+    "mtp_rvsa_sampling_fwd_hilo": [c_void_p] * 9 + [c_int] * 5 + [c_void_p],
+    "mtp_rvsa_attn_fwd_hilo": [c_void_p] * 6 + [c_int] * 5 + [c_void_p],
+    "mtp_full_attn_fwd_hilo": [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
+    "mtp_tok_to_nchw_hilo": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_optim_step_begin": [c_void_p, c_void_p],
     "mtp_sumsq_f32": [c_void_p, c_size_t, c_void_p, c_void_p],
     "mtp_adamw_step": [c_void_p] * 9 + [c_size_t, c_float, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p],

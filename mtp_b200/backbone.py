@@ -118,7 +118,7 @@ class ViT_Win_RVSA_V3_WSZ7(nn.Module):
                  use_abs_pos_emb=False, use_rel_pos_bias=False, use_shared_rel_pos_bias=False,
                  out_indices=[11], interval=3, pretrained=None, restart_regression=True, *,
                  full_attn_rel_pos=True, feature_mode="multi", apply_fpn=True, final_norm=True, return_tuple=False,
-                 frozen_stages=-1):
+                 frozen_stages=-1, precision="bf16"):
         super().__init__()
         if hybrid_backbone is not None:
             raise NotImplementedError("hybrid_backbone (HybridEmbed, [V]:542-574) is unused by every MTP config")
@@ -171,6 +171,9 @@ class ViT_Win_RVSA_V3_WSZ7(nn.Module):
         self.apply_fpn = apply_fpn
         self.return_tuple = return_tuple
         self.frozen_stages = frozen_stages
+        if precision not in ("bf16", "fp32x3"):
+            raise ValueError("precision must be 'bf16' (training / fast path) or 'fp32x3' (fp32-class forward, inference / verification)")
+        self.precision = precision        # may also be switched on an existing module: m.precision = "fp32x3"
         self._engine_state = _engine.EngineState()
         self.input_preprocess = None     # optional mtp_b200.preprocess.ImagePreprocess: accept uint8 images, normalise in the patch gather
         # weights replaced wholesale: drop cached bf16 copies / refresh always-current mirrors (engine.EngineState.invalidate)

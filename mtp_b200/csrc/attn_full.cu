@@ -15,6 +15,8 @@ constexpr int FA_BQ = 64, FA_BK = 64, FA_HD = 64, FA_LD = 68, FA_THREADS = 128;
 // smem floats: Q, K, V, P tiles (64 x 68) + relh [64][gh] + relw [64][gw]
 __host__ __device__ inline int fa_smem_floats(int gh, int gw) { return 4 * FA_BQ * FA_LD + FA_BQ * (gh + gw); }
 
+// HILO (fp32-class mode): qkv [T, 6C] / out [T, 2C] hold hi | lo bf16 word pairs (lo at +3C / +C); arithmetic is fp32 throughout.
+template <bool HILO>
 __global__ void __launch_bounds__(FA_THREADS)
 full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel_h, const float* __restrict__ rel_w,
                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int gh, int gw, int C, int nH, int use_rel) {
@@ -29,7 +31,7 @@ full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * FA_BQ, n = blockIdx.y, b = blockIdx.z;
-  const int C3 = 3 * C;
+  const int C3 = (HILO ? 6 : 3) * C, LOQ = 3 * C;
   const float scale = 0.125f;
   const __nv_bfloat16* base = qkv + (size_t)b * N * C3 + n * FA_HD;
 
@@ -37,7 +39,9 @@ full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   for (int r = warp; r < FA_BQ; r += FA_THREADS / 32) {
     float2 v = make_float2(0.f, 0.f);
     if (q0 + r < N) {
-      v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + (size_t)(q0 + r) * C3 + lane * 2));
+      const __nv_bfloat16* src = base + (size_t)(q0 + r) * C3 + lane * 2;
+      v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src));
+      if (HILO) { const float2 l = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + LOQ)); v.x += l.x; v.y += l.y; }
       v.x *= scale; v.y *= scale;
     }
     *reinterpret_cast<float2*>(Qs + r * FA_LD + lane * 2) = v;
@@ -78,6 +82,11 @@ full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
         const __nv_bfloat16* src = base + (size_t)(k0 + r) * C3 + lane * 2;
         kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C));
         vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C));
+        if (HILO) {
+          const float2 kl = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C + LOQ));
+          const float2 vl = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C + LOQ));
+          kv.x += kl.x; kv.y += kl.y; vv.x += vl.x; vv.y += vl.y;
+        }
       }
       *reinterpret_cast<float2*>(Ks + r * FA_LD + lane * 2) = kv;
       *reinterpret_cast<float2*>(Vs + r * FA_LD + lane * 2) = vv;
@@ -159,9 +168,20 @@ full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
       u0.y = pack_bf16x2(o[a][2] * inv, o[a][3] * inv);
       u1.x = pack_bf16x2(o[a][4] * inv, o[a][5] * inv);
       u1.y = pack_bf16x2(o[a][6] * inv, o[a][7] * inv);
-      __nv_bfloat16* orow = out + ((size_t)b * N + q) * C + n * FA_HD;
+      __nv_bfloat16* orow = out + ((size_t)b * N + q) * (HILO ? 2 * C : C) + n * FA_HD;
       *reinterpret_cast<uint2*>(orow + tj * 4) = u0;
       *reinterpret_cast<uint2*>(orow + 32 + tj * 4) = u1;
+      if (HILO) {
+        float r[8];
+        const uint32_t w4[4] = {u0.x, u0.y, u1.x, u1.y};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 h2 = unpack_bf16x2(w4[e]); r[2 * e] = o[a][2 * e] * inv - h2.x; r[2 * e + 1] = o[a][2 * e + 1] * inv - h2.y; }
+        uint2 l0, l1;
+        l0.x = pack_bf16x2(r[0], r[1]); l0.y = pack_bf16x2(r[2], r[3]);
+        l1.x = pack_bf16x2(r[4], r[5]); l1.y = pack_bf16x2(r[6], r[7]);
+        *reinterpret_cast<uint2*>(orow + C + tj * 4) = l0;
+        *reinterpret_cast<uint2*>(orow + C + 32 + tj * 4) = l1;
+      }
       if (lse && tj == 0) lse[((size_t)b * nH + n) * N + q] = m_run[a] + __logf(l_run[a]);
     }
   }
@@ -169,6 +189,24 @@ full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 
 int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* rel_w, void* out, float* lse, int B, int gh, int gw, int C,
                             int nH, cudaStream_t st);      // attn_full_tc.cu
+
+template <bool HILO>
+static int launch_full_attn_fwd_simt(const void* qkv, const float* rel_h, const float* rel_w, void* out, float* lse, int B, int gh, int gw,
+                                     int C, int nH, cudaStream_t st) {
+  const int N = gh * gw;
+  const int smem = fa_smem_floats(gh, gw) * (int)sizeof(float);
+  MTP_REQUIRE(smem <= 220 * 1024, "mtp_full_attn_fwd: grid %dx%d too large for the rel-pos tables in shared memory", gh, gw);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(full_attn_fwd_kernel<HILO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_fwd smem attr: %s", cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  const dim3 grid(ceil_div(N, FA_BQ), nH, B);
+  (void)launch_k(full_attn_fwd_kernel<HILO>, grid, FA_THREADS, smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
+                 reinterpret_cast<__nv_bfloat16*>(out), lse, N, gh, gw, C, nH, rel_h != nullptr);
+  return check_launch("full_attn_fwd_kernel");
+}
 
 }  // namespace mtp
 
@@ -182,17 +220,14 @@ extern "C" int mtp_full_attn_fwd(const void* qkv_bf16, const float* rel_pos_h, c
   const int N = gh * gw;
   if (N <= 256 && gh <= 16 && gw <= 16)       // tensor-core path: K/V of a head resident in shared memory
     return launch_full_attn_fwd_tc(qkv_bf16, rel_pos_h, rel_pos_w, out_bf16, lse, B, gh, gw, C, nH, reinterpret_cast<cudaStream_t>(stream));
-  const int smem = fa_smem_floats(gh, gw) * (int)sizeof(float);
-  MTP_REQUIRE(smem <= 220 * 1024, "mtp_full_attn_fwd: grid %dx%d too large for the rel-pos tables in shared memory", gh, gw);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(full_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_fwd smem attr: %s", cudaGetErrorString(e));
-    attr_smem = smem;
-  }
-  const dim3 grid(ceil_div(N, FA_BQ), nH, B);
-  (void)launch_k(full_attn_fwd_kernel, grid, FA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), rel_pos_h, rel_pos_w, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, N, gh,
-      gw, C, nH, rel_pos_h != nullptr);
-  return check_launch("full_attn_fwd_kernel");
+  return launch_full_attn_fwd_simt<false>(qkv_bf16, rel_pos_h, rel_pos_w, out_bf16, lse, B, gh, gw, C, nH, reinterpret_cast<cudaStream_t>(stream));
+}
+
+/* fp32-class mode ("fp32x3"): qkv [T, 6C] / out [T, 2C] as hi | lo word pairs, fp32 arithmetic (streaming SIMT kernel at every N) */
+extern "C" int mtp_full_attn_fwd_hilo(const void* qkv_hilo, const float* rel_pos_h, const float* rel_pos_w, void* out_hilo, int B, int gh,
+                                      int gw, int C, int nH, mtp_stream_t stream) {
+  MTP_REQUIRE(qkv_hilo && out_hilo, "mtp_full_attn_fwd_hilo: null pointer");
+  MTP_REQUIRE((rel_pos_h == nullptr) == (rel_pos_w == nullptr), "mtp_full_attn_fwd_hilo: give both rel-pos tables or neither");
+  MTP_REQUIRE(B > 0 && gh > 0 && gw > 0 && C == nH * FA_HD, "mtp_full_attn_fwd_hilo: unsupported geometry");
+  return launch_full_attn_fwd_simt<true>(qkv_hilo, rel_pos_h, rel_pos_w, out_hilo, nullptr, B, gh, gw, C, nH, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -19,7 +19,7 @@ namespace mtp {
 // (1) zero-padded 7x7 mean of the LN'd tokens: CTA = (image-window, 256-channel slab); thread = (token group of 4, 4 channels):
 //     the <= 13 token loads of a thread are all in flight at once, the four groups combine through shared memory
 __global__ void __launch_bounds__(256)
-rvsa_pool_fwd_kernel(const __nv_bfloat16* __restrict__ yn, float* __restrict__ pooled, const RvsaGeom g) {
+rvsa_pool_fwd_kernel(const __nv_bfloat16* __restrict__ yn, float* __restrict__ pooled, const RvsaGeom g, int ld, int lo) {
   MTP_PDL_ENTRY();
   __shared__ float4 part[4][64];
   const int bw = blockIdx.x;
@@ -34,9 +34,15 @@ rvsa_pool_fwd_kernel(const __nv_bfloat16* __restrict__ yn, float* __restrict__ p
       const int i = tg + 4 * k;
       const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
       if (i < WS * WS && y >= 0 && y < g.h && x >= 0 && x < g.w) {
-        const uint2 u = *reinterpret_cast<const uint2*>(yn + ((size_t)(b * g.h + y) * g.w + x) * g.C + c);
+        const __nv_bfloat16* src = yn + ((size_t)(b * g.h + y) * g.w + x) * ld + c;      // ld = C, or 2C with the lo words at +lo (fp32-class mode)
+        const uint2 u = *reinterpret_cast<const uint2*>(src);
         const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y);
         s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
+        if (lo > 0) {
+          const uint2 ul = *reinterpret_cast<const uint2*>(src + lo);
+          const float2 al = unpack_bf16x2(ul.x), dl = unpack_bf16x2(ul.y);
+          s.x += al.x; s.y += al.y; s.z += dl.x; s.w += dl.y;
+        }
       }
     }
   }
@@ -94,6 +100,9 @@ constexpr int LDS_ROW = 68;      // padded fp32 row stride (floats) for Q/K/V ti
 constexpr int LDP = 52;          // row stride of the 49x49 score tile
 constexpr int RVSA_SMEM_FLOATS = 3 * NTOK * LDS_ROW + NTOK * LDP + 2 * NTOK * 8 + 2 * NTOK;
 
+// HILO (fp32-class mode): every qkv / out value is a pair of bf16 words, hi at column c and lo at column c + 3C (qkv, row pitch 6C) /
+// c + C (out, row pitch 2C); the arithmetic below is fp32 throughout, so this kernel is the exact-precision attention of that mode.
+template <bool HILO>
 __global__ void __launch_bounds__(64)
 rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
                      const float* __restrict__ rel_w, const float* __restrict__ bias_table, __nv_bfloat16* __restrict__ out,
@@ -115,7 +124,8 @@ rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
   const int nwin = g.nh * g.nw;
   const int b = bw / nwin, win = bw % nwin;
   const int wy = win / g.nw, wx = win % g.nw;
-  const int C = g.C, C3 = 3 * g.C;
+  const int C = g.C, C3 = (HILO ? 6 : 3) * g.C;      // row pitch of qkv
+  const int LOQ = 3 * g.C;                             // offset of the lo words (HILO)
   const float scale = 0.125f;          // hd^-0.5, hd = 64
 
   if (tid < NTOK) {
@@ -133,8 +143,11 @@ rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
     {
       const int y = wy * WS + j / WS - g.pt, x = wx * WS + j % WS - g.pl;
       float2 qv = make_float2(0.f, 0.f);
-      if (y >= 0 && y < g.h && x >= 0 && x < g.w)
-        qv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qkv_b + (size_t)(y * g.w + x) * C3 + lane * 2));
+      if (y >= 0 && y < g.h && x >= 0 && x < g.w) {
+        const __nv_bfloat16* src = qkv_b + (size_t)(y * g.w + x) * C3 + lane * 2;
+        qv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src));
+        if (HILO) { const float2 l = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + LOQ)); qv.x += l.x; qv.y += l.y; }
+      }
       *reinterpret_cast<float2*>(Qs + j * LDS_ROW + lane * 2) = qv;
     }
     // ---- bilinear gather of k~, v~ at sample j (grid_sample: bilinear, zeros, align_corners=True)
@@ -150,8 +163,13 @@ rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
       // taps in the zero padding or outside the padded grid contribute 0 (pad is applied after the bias, [V]:392)
       if (xx >= 0 && xx < g.w && yy >= 0 && yy < g.h) {
         const __nv_bfloat16* src = qkv_b + (size_t)(yy * g.w + xx) * C3 + lane * 2;
-        const float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C));
-        const float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C));
+        float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C));
+        float2 vv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C));
+        if (HILO) {
+          const float2 kl = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + C + LOQ));
+          const float2 vl = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src + 2 * C + LOQ));
+          kv.x += kl.x; kv.y += kl.y; vv.x += vl.x; vv.y += vl.y;
+        }
         ka.x += wgt * kv.x; ka.y += wgt * kv.y;
         va.x += wgt * vv.x; va.y += wgt * vv.y;
       }
@@ -255,9 +273,20 @@ rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
         u0.y = pack_bf16x2(acc[a][2], acc[a][3]);
         u1.x = pack_bf16x2(acc[a][4], acc[a][5]);
         u1.y = pack_bf16x2(acc[a][6], acc[a][7]);
-        __nv_bfloat16* orow = out + ((size_t)(b * g.h + y) * g.w + x) * C + n * HD;
+        __nv_bfloat16* orow = out + ((size_t)(b * g.h + y) * g.w + x) * (HILO ? 2 * C : C) + n * HD;
         *reinterpret_cast<uint2*>(orow + td * 4) = u0;
         *reinterpret_cast<uint2*>(orow + 32 + td * 4) = u1;
+        if (HILO) {
+          float r[8];
+          const uint32_t w4[4] = {u0.x, u0.y, u1.x, u1.y};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 h2 = unpack_bf16x2(w4[e]); r[2 * e] = acc[a][2 * e] - h2.x; r[2 * e + 1] = acc[a][2 * e + 1] - h2.y; }
+          uint2 l0, l1;
+          l0.x = pack_bf16x2(r[0], r[1]); l0.y = pack_bf16x2(r[2], r[3]);
+          l1.x = pack_bf16x2(r[4], r[5]); l1.y = pack_bf16x2(r[6], r[7]);
+          *reinterpret_cast<uint2*>(orow + C + td * 4) = l0;
+          *reinterpret_cast<uint2*>(orow + C + 32 + td * 4) = l1;
+        }
       }
     }
   }
@@ -265,6 +294,21 @@ rvsa_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 
 int launch_rvsa_attn_fwd_tc(const void* qkv, const float* params, const float* rel_h, const float* rel_w, const float* table, void* out,
                             float* lse, const RvsaGeom& g, cudaStream_t st);     // attn_window_tc.cu
+
+template <bool HILO>
+static int launch_rvsa_attn_fwd_simt(const void* qkv, const float* params, const float* rel_h, const float* rel_w, const float* table, void* out,
+                                     float* lse, const RvsaGeom& g, cudaStream_t st) {
+  static bool attr = false;
+  const int smem = RVSA_SMEM_FLOATS * sizeof(float);
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(rvsa_attn_fwd_kernel<HILO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_fwd smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  (void)launch_k(rvsa_attn_fwd_kernel<HILO>, g.B * g.nh * g.nw * g.nH, 64, smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv), params, rel_h,
+                 rel_w, table, reinterpret_cast<__nv_bfloat16*>(out), lse, g);
+  return check_launch("rvsa_attn_fwd_kernel");
+}
 
 }  // namespace mtp
 
@@ -278,7 +322,7 @@ extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, co
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int n_bw = B * g.nh * g.nw;
-  (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g);
+  (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g, C, 0);
   int rc = check_launch("rvsa_pool_fwd_kernel");
   if (rc) return rc;
   (void)launch_k(rvsa_heads_fwd_kernel, 5 * nH, 256, 0, st, pooled, w_off, b_off, w_scale, b_scale, w_angle, b_angle, params, n_bw, g);
@@ -293,15 +337,30 @@ extern "C" int mtp_rvsa_attn_fwd(const void* qkv_bf16, const float* params, cons
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   if (nH % 2 == 0)       // tensor-core path: two heads of a window per 128-row UMMA tile
     return launch_rvsa_attn_fwd_tc(qkv_bf16, params, rel_pos_h, rel_pos_w, bias_table, out_bf16, lse, g, reinterpret_cast<cudaStream_t>(stream));
-  static bool attr = false;
-  const int smem = RVSA_SMEM_FLOATS * sizeof(float);
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(rvsa_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_fwd smem attr: %s", cudaGetErrorString(e));
-    attr = true;
-  }
-  (void)launch_k(rvsa_attn_fwd_kernel, B * g.nh * g.nw * nH, 64, smem, reinterpret_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), params, rel_pos_h, rel_pos_w, bias_table,
-      reinterpret_cast<__nv_bfloat16*>(out_bf16), lse, g);
-  return check_launch("rvsa_attn_fwd_kernel");
+  return launch_rvsa_attn_fwd_simt<false>(qkv_bf16, params, rel_pos_h, rel_pos_w, bias_table, out_bf16, lse, g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+/* fp32-class mode ("fp32x3"): the same operator on hi | lo word pairs (qkv [T, 6C], out [T, 2C]), fp32 arithmetic throughout;
+ * yn of the sampling heads likewise ([T, 2C]). */
+extern "C" int mtp_rvsa_sampling_fwd_hilo(const void* yn_hilo, const float* w_off, const float* b_off, const float* w_scale,
+                                          const float* b_scale, const float* w_angle, const float* b_angle, float* pooled, float* params,
+                                          int B, int h, int w, int C, int nH, mtp_stream_t stream) {
+  MTP_REQUIRE(yn_hilo && w_off && b_off && w_scale && b_scale && w_angle && b_angle && pooled && params, "mtp_rvsa_sampling_fwd_hilo: null pointer");
+  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && C <= 1024, "mtp_rvsa_sampling_fwd_hilo: unsupported geometry");
+  const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n_bw = B * g.nh * g.nw;
+  (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_hilo), pooled, g, 2 * C, C);
+  int rc = check_launch("rvsa_pool_fwd_kernel");
+  if (rc) return rc;
+  (void)launch_k(rvsa_heads_fwd_kernel, 5 * nH, 256, 0, st, pooled, w_off, b_off, w_scale, b_scale, w_angle, b_angle, params, n_bw, g);
+  return check_launch("rvsa_heads_fwd_kernel");
+}
+
+extern "C" int mtp_rvsa_attn_fwd_hilo(const void* qkv_hilo, const float* params, const float* rel_pos_h, const float* rel_pos_w,
+                                      const float* bias_table, void* out_hilo, int B, int h, int w, int C, int nH, mtp_stream_t stream) {
+  MTP_REQUIRE(qkv_hilo && params && rel_pos_h && rel_pos_w && bias_table && out_hilo, "mtp_rvsa_attn_fwd_hilo: null pointer");
+  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD, "mtp_rvsa_attn_fwd_hilo: unsupported geometry");
+  const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
+  return launch_rvsa_attn_fwd_simt<true>(qkv_hilo, params, rel_pos_h, rel_pos_w, bias_table, out_hilo, nullptr, g, reinterpret_cast<cudaStream_t>(stream));
 }

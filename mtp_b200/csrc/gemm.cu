@@ -51,6 +51,7 @@ struct EpiParams {
   float* colsum;
   int b_static;
   float* sumsq;
+  int hilo, out_lo;      // fp32-class mode (see mtp_epilogue.hilo)
 };
 
 // ---- epilogue ---------------------------------------------------------------------------------------------------------
@@ -208,6 +209,12 @@ __device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[
       }
     }
     store_bf16x8(o, t[p]);
+    if (ep.out_lo > 0) {          // fp32-class mode: second bf16 word of each value, lo = bf16(v - float(bf16(v)))
+      float lo[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) lo[k] = t[p][k] - __bfloat162float(__float2bfloat16_rn(t[p][k]));
+      store_bf16x8(o + ep.out_lo, lo);
+    }
     if (ep.colsum != nullptr) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) cs[k] += __bfloat162float(__float2bfloat16_rn(t[p][k]));      // sums of the STORED values
@@ -324,7 +331,12 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   const int mg_ = CL2 ? (P.tiles_m + 1) / 2 : P.tiles_m;                                         \
   const int m0 = ((local_ % mg_) * (CL2 ? 2 : 1) + crank) * BM;                                  \
   const int n0 = (local_ / mg_) * BN;                                                            \
-  const int k_blocks = (P.K + BK - 1) / BK;
+  const int kb1_ = (P.K + BK - 1) / BK;                                                          \
+  const int k_blocks = P.ep.hilo ? 3 * kb1_ : kb1_;
+  // fp32-class mode (operands stored as [rows, 2K] = hi | lo bf16 words): the k loop runs three passes over K,
+  // A_hi B_hi + A_hi B_lo + A_lo B_hi, by moving the k coordinate of the TMA boxes; everything downstream is unchanged
+#define MTP_KA(kb) ((kb) < 2 * kb1_ ? ((kb) % kb1_) : ((kb) - kb1_))
+#define MTP_KB(kb) ((kb) < kb1_ ? (kb) : (kb) < 2 * kb1_ ? (kb) : ((kb) - 2 * kb1_))
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -345,7 +357,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
               if (!CL2) {
                 mbar_arrive_expect_tx(&full_bar[kb], Cfg::STAGE_BYTES);
                 if (!P.b_mn) {
-                  tma_load_2d(sb, &P.tmB, &full_bar[kb], kb * BK, n0);
+                  tma_load_2d(sb, &P.tmB, &full_bar[kb], MTP_KB(kb) * BK, n0);
                 } else {
 #pragma unroll
                   for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[kb], n0 + j * 64, kb * BK);
@@ -380,14 +392,14 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
             } else if (!CL2) {
               if (!b_done) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               if (!P.a_mn) {
-                tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
+                tma_load_2d(sa, &P.tmA, &full_bar[stage], MTP_KA(kb) * BK, m0);
               } else {
 #pragma unroll
                 for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
               }
               if (b_done) {
               } else if (!P.b_mn) {
-                tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * BK, n0);
+                tma_load_2d(sb, &P.tmB, &full_bar[stage], MTP_KB(kb) * BK, n0);
               } else {
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[stage], n0 + j * 64, kb * BK);
@@ -539,6 +551,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
     }
   }
 #undef MTP_DECODE_ITEM
+#undef MTP_KA
+#undef MTP_KB
 
   __syncwarp();
   tc_fence_before();
@@ -607,7 +621,7 @@ static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sc
   for (int p = 0; p < np; ++p) {
     const int tiles_m = ceil_div(pr[p].M, BM), tiles_n = ceil_div(pr[p].N, bn);
     const int n = (cl2 ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
-    const double c = ceil_div(pr[p].K, BK) * kblock_cycles(bn, cl2) + kTileFixedCycles;
+    const double c = ceil_div(pr[p].K, BK) * (pr[p].ep.hilo ? 3 : 1) * kblock_cycles(bn, cl2) + kTileFixedCycles;
     for (int i = 0; i < n; ++i) items.push_back({base + i, c});
     base += n;
   }
@@ -657,11 +671,11 @@ static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
   std::vector<int> key = {force_bn, np, num_sms()};
-  for (int p = 0; p < np; ++p) { key.push_back(pr[p].M); key.push_back(pr[p].N); key.push_back(pr[p].K); key.push_back(pr[p].b_mn); }
+  for (int p = 0; p < np; ++p) { key.push_back(pr[p].M); key.push_back(pr[p].N); key.push_back(pr[p].K); key.push_back(pr[p].b_mn + 2 * pr[p].ep.hilo); }
   auto it = cache.find(key);
   if (it != cache.end()) return &it->second;
   bool any_bmn = false, all_pairable = true;
-  for (int p = 0; p < np; ++p) { any_bmn |= pr[p].b_mn != 0; all_pairable &= ceil_div(pr[p].M, BM) >= 2; }
+  for (int p = 0; p < np; ++p) { any_bmn |= pr[p].b_mn != 0; all_pairable &= ceil_div(pr[p].M, BM) >= 2 && !pr[p].ep.hilo; }
   Config best;
   best.bn = 0;
   double best_cost = 1e300;
@@ -669,7 +683,7 @@ static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
   for (int cl = 0; cl < 2; ++cl) {
     for (int i = 0; i < 4; ++i) {
       const int bn = cand[i];
-      if (force_bn) { if (cl != (force_bn >= 1000) || bn != force_bn % 1000) continue; }
+      if (force_bn) { if (cl != (force_bn >= 1000) || bn != force_bn % 1000) continue; if (cl == 1 && !all_pairable) continue; }
       else if (cl == 1 && !all_pairable) continue;
       if (cl == 1 && any_bmn && bn % 128 != 0) continue;     // MN-major B is fetched in 64-column boxes: a pair needs an even count
       double c = build_schedule(pr, np, bn, cl == 1, nullptr);
@@ -696,9 +710,10 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
   memset(gp, 0, sizeof(gp));
   for (int p = 0; p < np; ++p) {
     const HostProblem& h = pr[p];
-    int rc = h.a_mn ? make_tmap(&gp[p].tmA, h.A, h.K, h.M, h.lda, BK) : make_tmap(&gp[p].tmA, h.A, h.M, h.K, h.lda, BM);
+    const int kcols = h.ep.hilo ? 2 * h.K : h.K;      // hi | lo words side by side
+    int rc = h.a_mn ? make_tmap(&gp[p].tmA, h.A, h.K, h.M, h.lda, BK) : make_tmap(&gp[p].tmA, h.A, h.M, kcols, h.lda, BM);
     if (rc) return rc;
-    rc = h.b_mn ? make_tmap(&gp[p].tmB, h.B, h.K, h.N, h.ldb, BK) : make_tmap(&gp[p].tmB, h.B, h.N, h.K, h.ldb, CL2 ? BN / 2 : BN);
+    rc = h.b_mn ? make_tmap(&gp[p].tmB, h.B, h.K, h.N, h.ldb, BK) : make_tmap(&gp[p].tmB, h.B, h.N, kcols, h.ldb, CL2 ? BN / 2 : BN);
     if (rc) return rc;
     gp[p].ep = h.ep;
     gp[p].M = h.M; gp[p].N = h.N; gp[p].K = h.K;
@@ -762,6 +777,12 @@ static int validate_problem(const HostProblem& h) {
     MTP_REQUIRE((ep.mode == MTP_EPI_BF16 || ep.mode == MTP_EPI_BF16_DGELU) && ((uintptr_t)ep.colsum & 15) == 0,
                 "mtp_gemm_bf16: colsum needs a BF16 / BF16_DGELU epilogue and a 16-byte aligned pointer");
   if (ep.sumsq != nullptr) MTP_REQUIRE(ep.mode == MTP_EPI_F32, "mtp_gemm_bf16: sumsq needs the F32 epilogue");
+  if (ep.hilo) {
+    MTP_REQUIRE(!h.a_mn && !h.b_mn && h.K % BK == 0 && h.lda >= 2 * h.K && h.ldb >= 2 * h.K,
+                "mtp_gemm_bf16: hilo mode needs K-major operands stored as [rows, 2K] (hi | lo) and K %% 64 == 0 (K=%d)", h.K);
+    MTP_REQUIRE(ep.mode != MTP_EPI_BF16_PIXSHUF && ep.mode != MTP_EPI_BF16_DGELU && ep.out2 == nullptr, "mtp_gemm_bf16: hilo mode is forward-only");
+  }
+  MTP_REQUIRE(ep.out_lo >= 0 && ep.out_lo % 8 == 0, "mtp_gemm_bf16: out_lo_offset must be a non-negative multiple of 8");
   if (ep.mode == MTP_EPI_BF16_PIXSHUF)
     MTP_REQUIRE(ep.ps_h > 0 && ep.ps_w > 0 && ep.ps_cout > 0 && ep.ps_cout % 32 == 0 && h.N == 4 * ep.ps_cout,
                 "mtp_gemm_bf16: bad pixel-shuffle geometry");
@@ -776,6 +797,8 @@ static EpiParams to_epi(const mtp_epilogue* ep) {
   p.colsum = ep->colsum;
   p.b_static = ep->b_static;
   p.sumsq = ep->sumsq;
+  p.hilo = ep->hilo;
+  p.out_lo = ep->out_lo_offset;
   return p;
 }
 
@@ -853,6 +876,8 @@ static EpiParams plan_epi(int n) {      // a valid epilogue for planning (never 
   EpiParams e;
   memset(&e, 0, sizeof(e));
   e.mode = MTP_EPI_BF16;
+  e.hilo = 0;
+  e.out_lo = 0;
   e.ldo = (n + 7) / 8 * 8;
   e.out = reinterpret_cast<void*>(uintptr_t(16));
   return e;

@@ -92,7 +92,7 @@ __device__ __forceinline__ void map_index(const MapGeom& g, int b, int Y, int X,
 // NCHW out[b, c, Y, X] = tok[row(b,Y,X), colbase + c];   32(X) x 32(c) tiles through shared memory
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
-tok_to_nchw_kernel(const TIn* __restrict__ tok, int ld, TOut* __restrict__ out, const MapGeom g) {
+tok_to_nchw_kernel(const TIn* __restrict__ tok, int ld, TOut* __restrict__ out, const MapGeom g, int lo) {
   MTP_PDL_ENTRY();
   __shared__ float tile[32][33];
   const int Ho = g.h << g.L, Wo = g.w << g.L;
@@ -105,7 +105,9 @@ tok_to_nchw_kernel(const TIn* __restrict__ tok, int ld, TOut* __restrict__ out, 
     if (X < Wo && c0 + tx < g.C) {
       size_t row; int cb;
       map_index(g, b, Y, X, row, cb);
-      tile[i][tx] = to_f32(tok[row * ld + cb + c0 + tx]);
+      float v = to_f32(tok[row * ld + cb + c0 + tx]);
+      if (lo > 0) v += to_f32(tok[row * ld + cb + c0 + tx + lo]);      // fp32-class mode: hi | lo word pairs (lo at +lo)
+      tile[i][tx] = v;
     }
   }
   __syncthreads();
@@ -271,12 +273,24 @@ extern "C" int mtp_tok_to_nchw(const void* tok, int tok_is_bf16, int ld, void* o
   const MapGeom g{B, h, w, C, level};
   const dim3 grid(ceil_div(w << level, 32) * (h << level), ceil_div(C, 32), B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define T2N(TI, TO) (void)launch_k(tok_to_nchw_kernel<TI, TO>, grid, 256, 0, st, reinterpret_cast<const TI*>(tok), ld, reinterpret_cast<TO*>(out), g)
+#define T2N(TI, TO) (void)launch_k(tok_to_nchw_kernel<TI, TO>, grid, 256, 0, st, reinterpret_cast<const TI*>(tok), ld, reinterpret_cast<TO*>(out), g, 0)
   if (tok_is_bf16 && out_is_bf16) T2N(__nv_bfloat16, __nv_bfloat16);
   else if (tok_is_bf16) T2N(__nv_bfloat16, float);
   else if (out_is_bf16) T2N(float, __nv_bfloat16);
   else T2N(float, float);
 #undef T2N
+  return check_launch("tok_to_nchw_kernel");
+}
+
+extern "C" int mtp_tok_to_nchw_hilo(const void* tok_hilo, int ld, int lo_offset, float* out, int B, int h, int w, int C, int level,
+                                    mtp_stream_t stream) {
+  MTP_REQUIRE(tok_hilo && out, "mtp_tok_to_nchw_hilo: null pointer");
+  MTP_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && level >= 0 && level <= 2 && lo_offset > 0 && ld >= lo_offset + (level ? 4 * C : C),
+              "mtp_tok_to_nchw_hilo: bad geometry");
+  const MapGeom g{B, h, w, C, level};
+  const dim3 grid(ceil_div(w << level, 32) * (h << level), ceil_div(C, 32), B);
+  (void)launch_k(tok_to_nchw_kernel<__nv_bfloat16, float>, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream),
+                 reinterpret_cast<const __nv_bfloat16*>(tok_hilo), ld, out, g, lo_offset);
   return check_launch("tok_to_nchw_kernel");
 }
 

@@ -271,6 +271,13 @@ def backbone_apply(m, x, keep=None):
         keep = _draw_keep(m, x.shape[0], x.device)
     params = [p for p in m.parameters()]
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+    if getattr(m, "precision", "bf16") == "fp32x3":
+        if needs_grad:
+            raise RuntimeError("mtp_b200: precision='fp32x3' is forward-only (inference / verification); wrap the call in torch.no_grad()")
+        _check_input(m, x)
+        from . import precise
+        with torch.no_grad():
+            return precise.forward(m, x.float() if x.dtype != torch.uint8 else m.input_preprocess.reference(x).contiguous())
     if not needs_grad:
         with torch.no_grad():
             outs, _ = _forward_impl(m, x, keep, save=False)

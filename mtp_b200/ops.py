@@ -21,7 +21,8 @@ def _chk(t, dtype, name):
 
 
 def gemm(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=None, out2=None, aux=None, row_scale=None,
-         rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None, ps=None, force_bn=0, colsum=None, b_static=False, sumsq=None):
+         rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None, ps=None, force_bn=0, colsum=None, b_static=False, sumsq=None,
+         hilo=False, out_lo=0):
     """acc[m,n] = sum_k A[m,k] B[n,k] with fused epilogue; see include/mtp_b200.h."""
     ep = L.Epilogue()
     ep.mode = mode
@@ -31,6 +32,7 @@ def gemm(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=No
     ep.ldo = int(ldo if ldo is not None else out.shape[-1])
     ep.bias, ep.out, ep.out2, ep.aux, ep.row_scale = _p(bias), _p(out), _p(out2), _p(aux), _p(row_scale)
     ep.rows_per_group, ep.pos_rows, ep.accumulate = int(rows_per_group), int(pos_rows), int(bool(accumulate))
+    ep.hilo, ep.out_lo_offset = int(bool(hilo)), int(out_lo)
     if ps is not None:
         ep.ps_h, ep.ps_w, ep.ps_cout = ps
     lda = int(lda if lda is not None else A.shape[-1])
