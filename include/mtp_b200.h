@@ -266,6 +266,11 @@ int mtp_full_attn_fwd_hilo(const void* qkv_hilo, const float* rel_pos_h, const f
                            int C, int nH, mtp_stream_t stream);
 int mtp_tok_to_nchw_hilo(const void* tok_hilo, int ld, int lo_offset, float* out, int B, int h, int w, int C, int level, mtp_stream_t stream);
 
+/* measurement aid: an empty kernel launch on `stream` (keeps a skipped kernel's place in a captured step; tools/step_breakdown.py) */
+int mtp_empty_launch(mtp_stream_t stream);
+/* tuning aid: cap the depth of the GEMM operand ring (0 = as deep as the shared-memory budget allows) */
+int mtp_gemm_set_max_stages(int n);
+
 #ifdef __cplusplus
 }
 #endif

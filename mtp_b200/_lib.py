@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmtp_b200.so")
+LIB_PATH = os.environ.get("MTP_B200_LIB") or os.path.join(_HERE, "libmtp_b200.so")      # env override: experimental builds (tools/)
 
 c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 
@@ -40,6 +40,7 @@ _SIGNATURES = {
     "mtp_gemm_plan": [c_int] * 9 + [ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double)],
     "mtp_gemm_set_debug": [c_void_p],
     "mtp_gemm_set_debug_mode": [c_int],
+    "mtp_gemm_set_max_stages": [c_int],
     "mtp_layernorm_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],
     "mtp_layernorm_bwd": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
@@ -68,6 +69,7 @@ _SIGNATURES = {
     "mtp_rvsa_attn_fwd_hilo": [c_void_p] * 6 + [c_int] * 5 + [c_void_p],
     "mtp_full_attn_fwd_hilo": [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
     "mtp_tok_to_nchw_hilo": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_empty_launch": [c_void_p],
     "mtp_optim_step_begin": [c_void_p, c_void_p],
     "mtp_sumsq_f32": [c_void_p, c_size_t, c_void_p, c_void_p],
     "mtp_adamw_step": [c_void_p] * 9 + [c_size_t, c_float, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p],
@@ -115,7 +117,31 @@ def check(rc, what=""):
         raise MtpError(f"{what} failed ({rc}): {load().mtp_last_error().decode()}")
 
 
+# ---- measurement aid (tools/step_breakdown.py): kernel families whose launches are replaced by an empty kernel, so that the time a
+#      family costs INSIDE the graph-replayed step can be read off as a difference.  Results are garbage while a family is skipped.
+FAMILIES = {
+    "gemm": ("mtp_gemm_bf16", "mtp_gemm_bf16_dual"),
+    "rvsa_attn_fwd": ("mtp_rvsa_attn_fwd",), "rvsa_sampling_fwd": ("mtp_rvsa_sampling_fwd",),
+    "rvsa_attn_bwd": ("mtp_rvsa_attn_bwd",), "rvsa_sampling_bwd": ("mtp_rvsa_sampling_bwd",),
+    "dense_attn_fwd": ("mtp_full_attn_fwd",), "dense_attn_bwd": ("mtp_full_attn_bwd",),
+    "layernorm_fwd": ("mtp_layernorm_fwd",), "layernorm_bwd": ("mtp_layernorm_bwd",),
+    "optimizer": ("mtp_adamw_step", "mtp_sumsq_f32", "mtp_optim_step_begin"),
+    "layout": ("mtp_patchify", "mtp_patchify_u8", "mtp_tok_to_nchw", "mtp_nchw_to_tok", "mtp_maxpool2_tok_fwd", "mtp_maxpool2_tok_bwd"),
+    "casts_colsums": ("mtp_scale_cast_bf16", "mtp_colsum_bf16", "mtp_cast_f32_bf16", "mtp_add_bf16_into_f32"),
+    "heads": ("mtp_sqloss_fwd_bwd", "mtp_sqloss_fwd_bwd_w"),
+}
+_skip = set()
+
+
+def set_skipped_families(names):
+    _skip.clear()
+    for n in names:
+        _skip.update(FAMILIES[n])
+
+
 def call(name, *args):
+    if _skip and name in _skip:
+        name, args = "mtp_empty_launch", (args[-1],)       # the stream is the last argument of every launching entry point
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise MtpError(f"{name} failed ({rc}): {load().mtp_last_error().decode()}")

@@ -36,6 +36,24 @@ def _compile(src, force, verbose):
     return obj, (r.stdout + r.stderr) if verbose else ""
 
 
+def build_variant(name, extra_flags):
+    """An experimental build of the whole library with extra nvcc flags -> mtp_b200/libmtp_b200_<name>.so (select it with MTP_B200_LIB)."""
+    odir = os.path.join(HERE, "build", name)
+    os.makedirs(odir, exist_ok=True)
+    objs = []
+    for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
+        obj = os.path.join(odir, os.path.basename(src)[:-3] + ".o")
+        r = subprocess.run([NVCC] + FLAGS + list(extra_flags) + ["-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        objs.append(obj)
+    lib = os.path.join(HERE, f"libmtp_b200_{name}.so")
+    r = subprocess.run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return lib
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
@@ -55,4 +73,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -39,6 +39,16 @@ int num_sms() {
 
 }  // namespace mtp
 
+namespace mtp {
+__global__ void empty_kernel() { MTP_PDL_ENTRY(); }
+}  // namespace mtp
+
+/* measurement aid (tools/step_breakdown.py): an empty launch that keeps a kernel's place in the stream / graph / PDL chain */
+extern "C" int mtp_empty_launch(mtp_stream_t stream) {
+  (void)mtp::launch_k(mtp::empty_kernel, 1, 32, 0, reinterpret_cast<cudaStream_t>(stream));
+  return mtp::check_launch("empty_kernel");
+}
+
 extern "C" const char* mtp_last_error(void) { return mtp::g_err; }
 extern "C" int mtp_version(void) { return 100; }
 extern "C" int mtp_set_pdl(int enabled) {

@@ -258,6 +258,8 @@ struct Sched {
   uint16_t count[MAX_SLOTS];
   uint16_t item[MAX_SLOTS][MAX_ITEMS];
   int strided_total;   // > 0: the lists above are unused; slot s walks items s, s + slots, s + 2*slots, ... < strided_total
+  int n_stages;        // depth of the smem ring actually used (<= GemmCfg::STAGES): fewer stages = less dynamic smem, so that the CTA of
+                       // the NEXT launch can become resident beside this one and hide the SM turnaround (tools/gemm_gaps.py)
   int dbg_mode;        // tuning aid: 0 normal, 1 = skip the TMA loads (MMA pipeline only), 2 = skip the MMAs (TMA pipeline only)
   long long* dbg;      // optional: [gridDim.x][8] globaltimer stamps of the pipeline phases (tuning aid, mtp_gemm_set_debug)
 };
@@ -269,16 +271,19 @@ __device__ __forceinline__ long long gtime() {
 }
 #define MTP_STAMP(i) do { if (sched.dbg) sched.dbg[blockIdx.x * 8 + (i)] = gtime(); } while (0)
 
+#ifndef MTP_GEMM_MINBLOCKS
+#define MTP_GEMM_MINBLOCKS 1      // 2: cap registers so that two CTAs (this launch's and the next one's) fit one SM -- co-residency experiments
+#endif
 template <int BN, bool CL2>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, MTP_GEMM_MINBLOCKS)
 gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__ GemmProblem p1, const __grid_constant__ Sched sched) {
   using Cfg = GemmCfg<BN, CL2>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = sched.n_stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);   // [2][BN]
@@ -335,8 +340,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   const int k_blocks = P.ep.hilo ? 3 * kb1_ : kb1_;
   // fp32-class mode (operands stored as [rows, 2K] = hi | lo bf16 words): the k loop runs three passes over K,
   // A_hi B_hi + A_hi B_lo + A_lo B_hi, by moving the k coordinate of the TMA boxes; everything downstream is unchanged
-#define MTP_KA(kb) ((kb) < 2 * kb1_ ? ((kb) % kb1_) : ((kb) - kb1_))
-#define MTP_KB(kb) ((kb) < kb1_ ? (kb) : (kb) < 2 * kb1_ ? (kb) : ((kb) - 2 * kb1_))
+#define MTP_KA(kb) ((kb) < kb1_ ? (kb) : (kb) - kb1_)                      /* hi, hi, lo (lo blocks start at kb1_) */
+#define MTP_KB(kb) ((kb) < 2 * kb1_ ? (kb) : (kb) - 2 * kb1_)              /* hi, lo, hi */
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -699,6 +704,7 @@ static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
 static int g_last_config = 0;
 static long long* g_gemm_dbg = nullptr;
 static int g_gemm_dbg_mode = 0;
+static int g_gemm_max_stages = 0;      // 0 = as many as fit the smem budget
 
 template <int BN, bool CL2>
 static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, cudaStream_t stream) {
@@ -706,6 +712,8 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
   sched.dbg = g_gemm_dbg;
   sched.dbg_mode = g_gemm_dbg_mode;
   using Cfg = GemmCfg<BN, CL2>;
+  sched.n_stages = g_gemm_max_stages > 0 ? std::max(2, std::min(Cfg::STAGES, g_gemm_max_stages)) : Cfg::STAGES;
+  const int smem_bytes = Cfg::SMEM_BYTES - (Cfg::STAGES - sched.n_stages) * Cfg::STAGE_BYTES;
   GemmProblem gp[2];
   memset(gp, 0, sizeof(gp));
   for (int p = 0; p < np; ++p) {
@@ -727,6 +735,7 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
   auto kern = gemm_bf16_kernel<BN, CL2>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -752,7 +761,7 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
     ++cfg.numAttrs;
   }
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gp[0], gp[1], sched);
   if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "gemm_bf16_kernel launch: %s", cudaGetErrorString(e));
@@ -904,6 +913,12 @@ extern "C" int mtp_gemm_set_debug(void* device_buffer) {
   return MTP_OK;
 }
 extern "C" int mtp_gemm_last_config(void) { return g_last_config; }
+/* tuning aid: cap the depth of the operand ring (0 = fill the smem budget).  A shallow ring leaves room for the next launch's CTA on the
+ * same SM (co-residency hides the SM turnaround between dependent launches, at the price of less latency cover in the mainloop). */
+extern "C" int mtp_gemm_set_max_stages(int n) {
+  g_gemm_max_stages = n > 0 ? n : 0;
+  return MTP_OK;
+}
 extern "C" int mtp_gemm_set_debug_mode(int mode) {
   g_gemm_dbg_mode = mode;
   return MTP_OK;

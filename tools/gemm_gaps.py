@@ -7,6 +7,7 @@ from mtp_b200 import ops, _lib as L
 NL = 6
 L.call("mtp_set_pdl", int(os.environ.get("MTP_PDL", "1")))
 L.call("mtp_gemm_set_debug_mode", int(os.environ.get("MTP_DBG", "0")))
+L.call("mtp_gemm_set_max_stages", int(os.environ.get("MTP_STAGES", "0")))
 if os.environ.get("MTP_TINY"):
     x = torch.randn(4096, device="cuda"); y = torch.empty(4096, device="cuda", dtype=torch.bfloat16)
     for nl in (20, 200):
@@ -18,7 +19,7 @@ if os.environ.get("MTP_TINY"):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
         print(f"tiny kernel chain of {nl}: {e0.elapsed_time(e1) * 1e3 / nl:.2f} us per launch")
-for name, M, N, K, bn in [("qkv fwd 192", 1568, 3072, 1024, 192), ("qkv fwd pair256", 1568, 3072, 1024, 1256),
+for name, M, N, K, bn in [("qkv fwd 192", 1568, 3072, 1024, 192), ("qkv fwd 128", 1568, 3072, 1024, 128), ("qkv fwd pair256", 1568, 3072, 1024, 1256),
                           ("proj fwd 128", 1568, 1024, 1024, 128), ("fc2 fwd 128", 1568, 1024, 4096, 128)]:
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
