@@ -70,6 +70,7 @@ _SIGNATURES = {
     "mtp_full_attn_fwd_hilo": [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
     "mtp_tok_to_nchw_hilo": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_empty_launch": [c_void_p],
+    "mtp_probe_launch": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_optim_step_begin": [c_void_p, c_void_p],
     "mtp_sumsq_f32": [c_void_p, c_size_t, c_void_p, c_void_p],
     "mtp_adamw_step": [c_void_p] * 9 + [c_size_t, c_float, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p],

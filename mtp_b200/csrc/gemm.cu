@@ -133,6 +133,7 @@ __device__ __forceinline__ void load_aux(const EpiParams& ep, AuxRegs& a, const 
   }
 }
 
+template <bool HILO>
 __device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[4][8], const AuxRegs& a, const float* bias_s,
                                                 const int (&m)[4], const bool (&ok)[4], int n, int N, int lane, float& sq) {
   const int i = lane & 3;
@@ -209,7 +210,7 @@ __device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[
       }
     }
     store_bf16x8(o, t[p]);
-    if (ep.out_lo > 0) {          // fp32-class mode: second bf16 word of each value, lo = bf16(v - float(bf16(v)))
+    if (HILO && ep.out_lo > 0) {          // fp32-class mode: second bf16 word of each value, lo = bf16(v - float(bf16(v)))
       float lo[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) lo[k] = t[p][k] - __bfloat162float(__float2bfloat16_rn(t[p][k]));
@@ -274,7 +275,7 @@ __device__ __forceinline__ long long gtime() {
 #ifndef MTP_GEMM_MINBLOCKS
 #define MTP_GEMM_MINBLOCKS 1      // 2: cap registers so that two CTAs (this launch's and the next one's) fit one SM -- co-residency experiments
 #endif
-template <int BN, bool CL2>
+template <int BN, bool CL2, bool HILO>
 __global__ void __launch_bounds__(GEMM_THREADS, MTP_GEMM_MINBLOCKS)
 gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__ GemmProblem p1, const __grid_constant__ Sched sched) {
   using Cfg = GemmCfg<BN, CL2>;
@@ -337,11 +338,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   const int m0 = ((local_ % mg_) * (CL2 ? 2 : 1) + crank) * BM;                                  \
   const int n0 = (local_ / mg_) * BN;                                                            \
   const int kb1_ = (P.K + BK - 1) / BK;                                                          \
-  const int k_blocks = P.ep.hilo ? 3 * kb1_ : kb1_;
+  const int k_blocks = HILO ? 3 * kb1_ : kb1_;
   // fp32-class mode (operands stored as [rows, 2K] = hi | lo bf16 words): the k loop runs three passes over K,
   // A_hi B_hi + A_hi B_lo + A_lo B_hi, by moving the k coordinate of the TMA boxes; everything downstream is unchanged
-#define MTP_KA(kb) ((kb) < kb1_ ? (kb) : (kb) - kb1_)                      /* hi, hi, lo (lo blocks start at kb1_) */
-#define MTP_KB(kb) ((kb) < 2 * kb1_ ? (kb) : (kb) - 2 * kb1_)              /* hi, lo, hi */
+#define MTP_KA(kb) (!HILO || (kb) < kb1_ ? (kb) : (kb) - kb1_)                      /* hi, hi, lo (lo blocks start at kb1_) */
+#define MTP_KB(kb) (!HILO || (kb) < 2 * kb1_ ? (kb) : (kb) - 2 * kb1_)              /* hi, lo, hi */
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -536,7 +537,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         float t[4][8];
         if (f32) lane_transpose<true>(v, t, lane);
         else lane_transpose<false>(v, t, lane);
-        epilogue_pieces(ep, t, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, item_ < items0 ? sq0 : sq1);
+        epilogue_pieces<HILO>(ep, t, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, item_ < items0 ? sq0 : sq1);
       }
       tc_fence_before();
       __syncwarp();
@@ -706,8 +707,11 @@ static long long* g_gemm_dbg = nullptr;
 static int g_gemm_dbg_mode = 0;
 static int g_gemm_max_stages = 0;      // 0 = as many as fit the smem budget
 
-template <int BN, bool CL2>
+template <int BN, bool CL2, bool HILO = false>
 static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, cudaStream_t stream) {
+  if constexpr (!HILO && !CL2) {          // the fp32-class (hi | lo, three-pass) instantiation exists for single CTAs only
+    if (pr[0].ep.hilo) return launch_grouped<BN, CL2, true>(pr, np, sched_in, stream);
+  }
   Sched sched = sched_in;
   sched.dbg = g_gemm_dbg;
   sched.dbg_mode = g_gemm_dbg_mode;
@@ -732,7 +736,7 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
   int dev_ = 0;
   cudaGetDevice(&dev_);
   bool& attr_set = attr_set_dev[dev_ & 63];
-  auto kern = gemm_bf16_kernel<BN, CL2>;
+  auto kern = gemm_bf16_kernel<BN, CL2, HILO>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -815,6 +819,7 @@ static int run_grouped(const HostProblem* pr, int np, int force_bn, cudaStream_t
   for (int p = 0; p < np; ++p) {
     int rc = validate_problem(pr[p]);
     if (rc) return rc;
+    MTP_REQUIRE(!pr[p].ep.hilo || np == 1, "mtp_gemm_bf16_dual: hilo mode is not available in grouped launches");
   }
   if (force_bn >= 1000) {
     for (int p = 0; p < np; ++p)
