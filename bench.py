@@ -326,7 +326,7 @@ def gemm_flops_and_bytes(runner, x):
 def count_launches(runner, x):
     """Kernels of libmtp_b200.so launched per step (entry point -> kernels it enqueues)."""
     from mtp_b200 import _lib
-    per_call = {"mtp_rvsa_sampling_fwd": 2, "mtp_rvsa_attn_bwd": 3, "mtp_rvsa_sampling_bwd": 3}
+    per_call = {"mtp_rvsa_attn_bwd": 3}          # attention backward + partial reduce + kv finalize (the memset is not a kernel of ours)
     n = [0]
     orig = _lib.call
 

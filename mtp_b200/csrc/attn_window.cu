@@ -95,6 +95,101 @@ rvsa_heads_fwd_kernel(const float* __restrict__ pooled, const float* __restrict_
   }
 }
 
+// (1)+(2) in ONE launch: CTA = (image-window, group of 16 output channels), 1024 threads.  Every CTA of a window recomputes the window's
+// pooled vector (49 token rows of <= 2 KB, all 13 loads of a thread in flight: the whole phase is one memory round trip), then two warps
+// per output channel take half of the dot product each.  Replaces a 128-CTA pooling launch + an 80-CTA GEMV launch whose in-situ cost was
+// 23 us per block (tools/step_breakdown.py) for ~0.2 MFLOP.
+constexpr int SF_THREADS = 1024, SF_OUT = 16;
+__global__ void __launch_bounds__(SF_THREADS)
+rvsa_sampling_fused_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float* __restrict__ w_off, const float* __restrict__ b_off,
+                               const float* __restrict__ w_sc, const float* __restrict__ b_sc, const float* __restrict__ w_ang,
+                               const float* __restrict__ b_ang, float* __restrict__ pooled, float* __restrict__ params, const RvsaGeom g,
+                               int ld, int lo) {
+  MTP_PDL_ENTRY();
+  __shared__ float4 part[4][256];
+  __shared__ float pooled_s[1024];
+  __shared__ float half_s[SF_OUT];
+  const int bw = blockIdx.x;
+  const int b = bw / (g.nh * g.nw), win = bw % (g.nh * g.nw);
+  const int wy = win / g.nw, wx = win % g.nw;
+  const int tid = threadIdx.x, tg = tid >> 8, cq = tid & 255;
+  const int c = cq * 4, C = g.C, nH = g.nH;
+  float4 s = make_float4(0, 0, 0, 0);
+  if (c < C) {
+#pragma unroll
+    for (int k = 0; k < (WS * WS + 3) / 4; ++k) {
+      const int i = tg + 4 * k;
+      const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
+      if (i < WS * WS && y >= 0 && y < g.h && x >= 0 && x < g.w) {
+        const __nv_bfloat16* src = yn + ((size_t)(b * g.h + y) * g.w + x) * ld + c;
+        const uint2 u = *reinterpret_cast<const uint2*>(src);
+        const float2 a = unpack_bf16x2(u.x), d = unpack_bf16x2(u.y);
+        s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
+        if (lo > 0) {
+          const uint2 ul = *reinterpret_cast<const uint2*>(src + lo);
+          const float2 al = unpack_bf16x2(ul.x), dl = unpack_bf16x2(ul.y);
+          s.x += al.x; s.y += al.y; s.z += dl.x; s.w += dl.y;
+        }
+      }
+    }
+  }
+  part[tg][cq] = s;
+  __syncthreads();
+  if (tg == 0 && c < C) {
+    const float4 p1 = part[1][cq], p2 = part[2][cq], p3 = part[3][cq];
+    const float inv = 1.0f / (WS * WS);                    // zeros of the padding are part of the mean ([V]:347,354)
+    s.x = (s.x + p1.x + p2.x + p3.x) * inv; s.y = (s.y + p1.y + p2.y + p3.y) * inv;
+    s.z = (s.z + p1.z + p2.z + p3.z) * inv; s.w = (s.w + p1.w + p2.w + p3.w) * inv;
+    if (blockIdx.y == 0 && pooled != nullptr) *reinterpret_cast<float4*>(pooled + (size_t)bw * C + c) = s;      // saved for the backward
+    *reinterpret_cast<float4*>(pooled_s + c) = s;
+  }
+  __syncthreads();
+  // ---- the three 1x1 convs on LeakyReLU(pooled): output order [0,2nH) offsets (head-major, x then y), [2nH,4nH) scales, [4nH,5nH) angle
+  const int warp = tid >> 5, lane = tid & 31;
+  const int k = warp >> 1, hf = warp & 1;
+  const int o = blockIdx.y * SF_OUT + k;
+  const bool live = o < 5 * nH;
+  const float* wrow = nullptr;
+  float bias = 0.f, div = 1.0f;
+  int n = 0, slot = 0;
+  if (live) {
+    if (o < 2 * nH) { wrow = w_off + (size_t)o * C; bias = b_off[o]; n = o >> 1; slot = o & 1; div = (float)((slot == 0 ? g.h : g.w) / WS); }   // sic: x by h//7, y by w//7
+    else if (o < 4 * nH) { wrow = w_sc + (size_t)(o - 2 * nH) * C; bias = b_sc[o - 2 * nH]; n = (o - 2 * nH) >> 1; slot = 2 + ((o - 2 * nH) & 1); }
+    else { wrow = w_ang + (size_t)(o - 4 * nH) * C; bias = b_ang[o - 4 * nH]; n = o - 4 * nH; slot = 4; }
+  }
+  float acc = 0.f;
+  if (live) {
+    const int cbeg = hf * 512;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cc = cbeg + i * 128 + lane * 4;
+      if (cc < C) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + cc));
+        float4 a = *reinterpret_cast<const float4*>(pooled_s + cc);
+        a.x = a.x >= 0 ? a.x : 0.01f * a.x; a.y = a.y >= 0 ? a.y : 0.01f * a.y;
+        a.z = a.z >= 0 ? a.z : 0.01f * a.z; a.w = a.w >= 0 ? a.w : 0.01f * a.w;
+        acc += wv.x * a.x + wv.y * a.y + wv.z * a.z + wv.w * a.w;
+      }
+    }
+    acc = warp_sum(acc);
+    if (hf == 1 && lane == 0) half_s[k] = acc;
+  }
+  __syncthreads();
+  if (live && hf == 0) {
+    if (lane == 0) params[((size_t)bw * nH + n) * 8 + slot] = (acc + half_s[k] + bias) / div;
+    if (slot == 4 && lane >= 1 && lane < 4) params[((size_t)bw * nH + n) * 8 + 4 + lane] = 0.f;      // unused slots 5..7
+  }
+}
+
+static int launch_rvsa_sampling_fused_fwd(const void* yn, const float* w_off, const float* b_off, const float* w_sc, const float* b_sc,
+                                          const float* w_ang, const float* b_ang, float* pooled, float* params, const RvsaGeom& g, int ld, int lo,
+                                          cudaStream_t st) {
+  const int n_bw = g.B * g.nh * g.nw;
+  (void)launch_k(rvsa_sampling_fused_fwd_kernel, dim3(n_bw, ceil_div(5 * g.nH, SF_OUT)), SF_THREADS, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn),
+                 w_off, b_off, w_sc, b_sc, w_ang, b_ang, pooled, params, g, ld, lo);
+  return check_launch("rvsa_sampling_fused_fwd_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------ attention fwd
 constexpr int LDS_ROW = 68;      // padded fp32 row stride (floats) for Q/K/V tiles: conflict-free float4 row access
 constexpr int LDP = 52;          // row stride of the 49x49 score tile
@@ -321,6 +416,7 @@ extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, co
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && C <= 1024, "mtp_rvsa_sampling_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported (need h,w>=7, C==64*nH<=1024)", B, h, w, C, nH);
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (sampling_fused_enabled()) return launch_rvsa_sampling_fused_fwd(yn_bf16, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, C, 0, st);
   const int n_bw = B * g.nh * g.nw;
   (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g, C, 0);
   int rc = check_launch("rvsa_pool_fwd_kernel");
@@ -349,6 +445,7 @@ extern "C" int mtp_rvsa_sampling_fwd_hilo(const void* yn_hilo, const float* w_of
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && C <= 1024, "mtp_rvsa_sampling_fwd_hilo: unsupported geometry");
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (sampling_fused_enabled()) return launch_rvsa_sampling_fused_fwd(yn_hilo, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, 2 * C, C, st);
   const int n_bw = B * g.nh * g.nw;
   (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_hilo), pooled, g, 2 * C, C);
   int rc = check_launch("rvsa_pool_fwd_kernel");

@@ -480,6 +480,67 @@ rvsa_sampling_wgrad_kernel(const float* __restrict__ g_out, const float* __restr
   }
 }
 
+// (1)+(2) in ONE launch: CTA = slab of 32 channels.  g (the gradient w.r.t. the 5nH raw conv outputs of every window), the slab of
+// LeakyReLU(pooled) / its derivative and the slab of the conv weights sit in shared memory; thread (c, o-group) accumulates
+// dW[o][c] over the windows, thread (c, window-group) dpooled[window][c] over the outputs.  Replaces two launches (128 + 320 CTAs).
+constexpr int SB_SLAB = 32;
+__global__ void __launch_bounds__(256)
+rvsa_sampling_fused_bwd_kernel(const float* __restrict__ dparams, const float* __restrict__ pooled, const float* __restrict__ w_off,
+                               const float* __restrict__ w_sc, const float* __restrict__ w_ang, float* __restrict__ dw_off,
+                               float* __restrict__ db_off, float* __restrict__ dw_sc, float* __restrict__ db_sc, float* __restrict__ dw_ang,
+                               float* __restrict__ db_ang, float* __restrict__ dpooled, int n_bw, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
+  extern __shared__ float sbm[];
+  const int nH = g.nH, C = g.C, NO = 5 * nH;
+  float* g_s = sbm;                          // [n_bw][NO]
+  float* a_s = g_s + n_bw * NO;              // [n_bw][32]  LeakyReLU(pooled)
+  float* k_s = a_s + n_bw * SB_SLAB;         // [n_bw][32]  LeakyReLU'(pooled)
+  float* w_s = k_s + n_bw * SB_SLAB;         // [NO][32]
+  const int tid = threadIdx.x, c0 = blockIdx.x * SB_SLAB;
+  for (int i = tid; i < n_bw * NO; i += 256) {
+    const int bw = i / NO, o = i % NO;
+    float v;
+    if (o < 2 * nH) v = dparams[((size_t)bw * nH + (o >> 1)) * 8 + (o & 1)] / (float)(((o & 1) == 0 ? g.h : g.w) / WS);
+    else if (o < 4 * nH) v = dparams[((size_t)bw * nH + ((o - 2 * nH) >> 1)) * 8 + 2 + ((o - 2 * nH) & 1)];
+    else v = dparams[((size_t)bw * nH + (o - 4 * nH)) * 8 + 4];
+    g_s[i] = v;
+  }
+  for (int i = tid; i < n_bw * SB_SLAB; i += 256) {
+    const int bw = i / SB_SLAB, c = i % SB_SLAB;
+    const float p = (c0 + c < C) ? pooled[(size_t)bw * C + c0 + c] : 0.f;
+    a_s[i] = p >= 0.f ? p : 0.01f * p;
+    k_s[i] = p >= 0.f ? 1.0f : 0.01f;
+  }
+  for (int i = tid; i < NO * SB_SLAB; i += 256) {
+    const int o = i / SB_SLAB, c = i % SB_SLAB;
+    const float* wr = o < 2 * nH ? w_off + (size_t)o * C : o < 4 * nH ? w_sc + (size_t)(o - 2 * nH) * C : w_ang + (size_t)(o - 4 * nH) * C;
+    w_s[i] = (c0 + c < C) ? wr[c0 + c] : 0.f;
+  }
+  __syncthreads();
+  const int c = tid & 31, grp = tid >> 5;
+  if (c0 + c < C) {
+    for (int o = grp; o < NO; o += 8) {            // dW[o][c] += sum_bw g[bw][o] * a[bw][c]
+      float acc = 0.f;
+      for (int bw = 0; bw < n_bw; ++bw) acc += g_s[bw * NO + o] * a_s[bw * SB_SLAB + c];
+      float* dw = o < 2 * nH ? dw_off + (size_t)o * C : o < 4 * nH ? dw_sc + (size_t)(o - 2 * nH) * C : dw_ang + (size_t)(o - 4 * nH) * C;
+      dw[c0 + c] += acc;
+    }
+    for (int bw = grp; bw < n_bw; bw += 8) {       // dpooled[bw][c] = leaky'(pooled) * sum_o g[bw][o] W[o][c]
+      float acc = 0.f;
+      for (int o = 0; o < NO; ++o) acc += g_s[bw * NO + o] * w_s[o * SB_SLAB + c];
+      dpooled[(size_t)bw * C + c0 + c] = k_s[bw * SB_SLAB + c] * acc;
+    }
+  }
+  if (blockIdx.x == 0) {                          // bias gradients
+    for (int o = tid; o < NO; o += 256) {
+      float acc = 0.f;
+      for (int bw = 0; bw < n_bw; ++bw) acc += g_s[bw * NO + o];
+      float* db = o < 2 * nH ? db_off + o : o < 4 * nH ? db_sc + (o - 2 * nH) : db_ang + (o - 4 * nH);
+      *db += acc;
+    }
+  }
+}
+
 // (3) dyn[t][c] += dpooled[window(t)][c] / 49   (AvgPool backward; only real tokens receive it)
 __global__ void __launch_bounds__(256)
 rvsa_pool_bwd_add_kernel(const float* __restrict__ dpooled, __nv_bfloat16* __restrict__ dyn, const RvsaGeom g) {
@@ -581,6 +642,23 @@ extern "C" int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, 
   const int n_bw = B * g.nh * g.nw;
   float* g_out = reinterpret_cast<float*>(workspace);            // [n_bw][5nH]
   float* dpooled = g_out + (size_t)n_bw * 5 * nH;                // [n_bw][C]
+  const int fused_smem = (n_bw * (5 * nH + 2 * SB_SLAB) + 5 * nH * SB_SLAB) * (int)sizeof(float);
+  if (sampling_fused_enabled() && fused_smem <= 160 * 1024) {
+    static int attr = 0;
+    if (fused_smem > attr) {
+      cudaError_t e = cudaFuncSetAttribute(rvsa_sampling_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem);
+      if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_sampling_fused_bwd smem attr: %s", cudaGetErrorString(e));
+      attr = fused_smem;
+    }
+    (void)launch_k(rvsa_sampling_fused_bwd_kernel, ceil_div(C, SB_SLAB), 256, fused_smem, st, dparams, pooled, w_off, w_scale, w_angle, dw_off, db_off,
+                   dw_scale, db_scale, dw_angle, db_angle, dpooled, n_bw, g);
+    int rc = check_launch("rvsa_sampling_fused_bwd_kernel");
+    if (rc || dyn_bf16 == nullptr) return rc;
+    const size_t total = (size_t)B * h * w * (C / 4);
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 8);
+    (void)launch_k(rvsa_pool_bwd_add_kernel, grid, 256, 0, st, dpooled, reinterpret_cast<__nv_bfloat16*>(dyn_bf16), g);
+    return check_launch("rvsa_pool_bwd_add_kernel");
+  }
   (void)launch_k(rvsa_sampling_bwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, dparams, pooled, w_off, w_scale, w_angle, g_out, dpooled, g);
   int rc = check_launch("rvsa_sampling_bwd_kernel");
   if (rc) return rc;

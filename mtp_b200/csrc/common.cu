@@ -1,6 +1,7 @@
 #include "common.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace mtp {
@@ -18,6 +19,15 @@ int set_error(int code, const char* fmt, ...) {
 static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl(bool on) { g_pdl = on; }
+
+bool sampling_fused_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTP_SAMPLING_FUSED");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 static int g_sm_limit = 0;
 void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
