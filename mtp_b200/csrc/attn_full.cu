@@ -5,6 +5,8 @@
 // One CTA per (image, head, 64-query tile); keys/values stream through shared memory in tiles of 64 with an online
 // softmax.  The rel-pos term factorises into two small per-query tables relh[q][jy] and relw[q][jx] that are built once
 // per query tile, so the bias costs N*(Hp+Wp)*hd MACs instead of an N x N table.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -189,6 +191,8 @@ full_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 
 int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* rel_w, void* out, float* lse, int B, int gh, int gw, int C,
                             int nH, cudaStream_t st);      // attn_full_tc.cu
+int launch_full_attn_fwd_stream_tc(const void* qkv, const float* rel_h, const float* rel_w, void* out, float* lse, int B, int gh, int gw,
+                                   int C, int nH, cudaStream_t st);      // attn_full_stream_tc.cu
 
 template <bool HILO>
 static int launch_full_attn_fwd_simt(const void* qkv, const float* rel_h, const float* rel_w, void* out, float* lse, int B, int gh, int gw,
@@ -220,6 +224,12 @@ extern "C" int mtp_full_attn_fwd(const void* qkv_bf16, const float* rel_pos_h, c
   const int N = gh * gw;
   if (N <= 256 && gh <= 16 && gw <= 16)       // tensor-core path: K/V of a head resident in shared memory
     return launch_full_attn_fwd_tc(qkv_bf16, rel_pos_h, rel_pos_w, out_bf16, lse, B, gh, gw, C, nH, reinterpret_cast<cudaStream_t>(stream));
+  {       // long sequences: K / V streamed in 128-key blocks with an online softmax, still on the tensor cores
+    static int simt = -1;
+    if (simt < 0) { const char* e = getenv("MTP_DENSE_SIMT"); simt = (e != nullptr && e[0] == '1') ? 1 : 0; }      // A/B switch
+    if (!simt && (2 * gh - 1 + 2 * gw - 1) * 65 * 4 <= 6 * 16384)      // both rel-pos tables fit the kernel's prologue staging area
+      return launch_full_attn_fwd_stream_tc(qkv_bf16, rel_pos_h, rel_pos_w, out_bf16, lse, B, gh, gw, C, nH, reinterpret_cast<cudaStream_t>(stream));
+  }
   return launch_full_attn_fwd_simt<false>(qkv_bf16, rel_pos_h, rel_pos_w, out_bf16, lse, B, gh, gw, C, nH, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -99,7 +99,8 @@ def _oracle_rvsa_from_qkv(xn, qkv, P, pre, h, w, nH):
     return Oo[:, pt:pt + h, pl:pl + w].reshape(B, N, C)
 
 
-@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 3, 3, True), (14, 1, 2, False), (16, 1, 2, True), (13, 1, 2, True), (32, 1, 2, True)])
+@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 3, 3, True), (14, 1, 2, False), (16, 1, 2, True), (13, 1, 2, True), (32, 1, 2, True),
+                                           (32, 2, 16, True), (40, 1, 2, True), (19, 1, 2, False), (64, 1, 2, True)])
 def test_full_attention_vs_oracle(grid, B, nH, rel):
     from mtp_b200 import ops
     C = nH * 64
