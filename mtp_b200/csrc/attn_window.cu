@@ -416,7 +416,7 @@ extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, co
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && C <= 1024, "mtp_rvsa_sampling_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported (need h,w>=7, C==64*nH<=1024)", B, h, w, C, nH);
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (sampling_fused_enabled()) return launch_rvsa_sampling_fused_fwd(yn_bf16, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, C, 0, st);
+  if ((sampling_fused_mask() & 1)) return launch_rvsa_sampling_fused_fwd(yn_bf16, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, C, 0, st);
   const int n_bw = B * g.nh * g.nw;
   (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g, C, 0);
   int rc = check_launch("rvsa_pool_fwd_kernel");
@@ -445,7 +445,7 @@ extern "C" int mtp_rvsa_sampling_fwd_hilo(const void* yn_hilo, const float* w_of
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && C <= 1024, "mtp_rvsa_sampling_fwd_hilo: unsupported geometry");
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (sampling_fused_enabled()) return launch_rvsa_sampling_fused_fwd(yn_hilo, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, 2 * C, C, st);
+  if ((sampling_fused_mask() & 1)) return launch_rvsa_sampling_fused_fwd(yn_hilo, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, 2 * C, C, st);
   const int n_bw = B * g.nh * g.nw;
   (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_hilo), pooled, g, 2 * C, C);
   int rc = check_launch("rvsa_pool_fwd_kernel");

@@ -643,7 +643,7 @@ extern "C" int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, 
   float* g_out = reinterpret_cast<float*>(workspace);            // [n_bw][5nH]
   float* dpooled = g_out + (size_t)n_bw * 5 * nH;                // [n_bw][C]
   const int fused_smem = (n_bw * (5 * nH + 2 * SB_SLAB) + 5 * nH * SB_SLAB) * (int)sizeof(float);
-  if (sampling_fused_enabled() && fused_smem <= 160 * 1024) {
+  if ((sampling_fused_mask() & 2) && fused_smem <= 160 * 1024) {
     static int attr = 0;
     if (fused_smem > attr) {
       cudaError_t e = cudaFuncSetAttribute(rvsa_sampling_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_smem);

@@ -20,13 +20,13 @@ static bool g_pdl = true;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl(bool on) { g_pdl = on; }
 
-bool sampling_fused_enabled() {
+int sampling_fused_mask() {          // bit 0: fused forward, bit 1: fused backward
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MTP_SAMPLING_FUSED");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    v = e != nullptr ? atoi(e) : 1;      // measured in the graph-replayed step (r2f): forward fused 11.71 vs 11.74 ms, backward fused 12.43 ms (slower: off)
   }
-  return v != 0;
+  return v;
 }
 
 static int g_sm_limit = 0;

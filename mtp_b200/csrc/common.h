@@ -19,7 +19,7 @@ inline int check_launch(const char* what) {
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 int num_sms();
-bool sampling_fused_enabled();      // A/B switch (MTP_SAMPLING_FUSED=0 restores the separate pool / GEMV / wgrad launches of the RVSA sampling heads)
+int sampling_fused_mask();      // A/B switch (MTP_SAMPLING_FUSED=0 restores the separate pool / GEMV / wgrad launches of the RVSA sampling heads)
 
 // Programmatic dependent launch (mtp_set_pdl): every kernel of this library begins with MTP_PDL_ENTRY() (griddepcontrol.wait, then
 // griddepcontrol.launch_dependents), so a kernel launched through launch_k may be scheduled while its stream predecessor drains;

@@ -344,7 +344,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
 #define MTP_KA(kb) (!HILO || (kb) < kb1_ ? (kb) : (kb) - kb1_)                      /* hi, hi, lo (lo blocks start at kb1_) */
 #define MTP_KB(kb) (!HILO || (kb) < 2 * kb1_ ? (kb) : (kb) - 2 * kb1_)              /* hi, lo, hi */
 
-  if (warp == 0) {
+  if (sched.dbg_mode == 5) {
+    // measurement aid: prologue + teardown only (barriers, TMEM alloc / dealloc, descriptor prefetch), no work
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // The whole warp walks the loop (warp-uniform control flow keeps descriptors / coordinates in uniform registers);
     // one elected lane issues.  Issuing from inside a divergent `if (lane == 0)` makes the compiler wrap every UTMALDG /
@@ -522,7 +524,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       }
       const bool f32 = mode_is_f32(ep.mode);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      const int n_chunks = (min(BN, N - n0) + 31) / 32;
+      const int n_chunks = sched.dbg_mode == 6 ? 0 : (min(BN, N - n0) + 31) / 32;      // dbg 6: accumulators are never read out
       uint32_t r[32];
       int c = hsel;
       if (c < n_chunks) tmem_ld_32x32(taddr + c * 32, r);

@@ -20,7 +20,7 @@ if os.environ.get("MTP_TINY"):
         e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
         print(f"tiny kernel chain of {nl}: {e0.elapsed_time(e1) * 1e3 / nl:.2f} us per launch")
 for name, M, N, K, bn in [("qkv fwd 192", 1568, 3072, 1024, 192), ("qkv fwd 128", 1568, 3072, 1024, 128), ("qkv fwd pair256", 1568, 3072, 1024, 1256),
-                          ("proj fwd 128", 1568, 1024, 1024, 128), ("fc2 fwd 128", 1568, 1024, 4096, 128)]:
+                          ("proj fwd 128", 1568, 1024, 1024, 128), ("fc2 fwd 128", 1568, 1024, 4096, 128)][:int(os.environ.get("MTP_NCASES", "9"))]:
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
