@@ -104,7 +104,11 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int n = blockIdx.x % nH, b = blockIdx.x / nH;
+  // one CTA per (image, head, 128-query tile): K / V of the head are re-staged by each of the (1 or 2) query-tile CTAs, which doubles the
+  // CTA count at 224^2 (2 x 128 = 256 CTAs instead of 128 on 148 SMs) for 32 KB of extra L2 reads per CTA
+  const int nqt = (N + 127) / 128;
+  const int qt_idx = blockIdx.x % nqt;
+  const int n = (blockIdx.x / nqt) % nH, b = blockIdx.x / (nqt * nH);
   const int C3 = 3 * C;
   const float scale = 0.125f;
   const __nv_bfloat16* base = qkv + (size_t)b * N * C3 + n * 64;
@@ -126,7 +130,7 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
   uint32_t phase = 0;
 
-  for (int q0 = 0; q0 < N; q0 += 128) {
+  for (int q0 = qt_idx * 128; q0 < min(N, (qt_idx + 1) * 128); q0 += 128) {
     ft_load_rows(Qs, base, C3, q0, 128, N);
     fence_proxy_async_smem();
     __syncthreads();
@@ -297,11 +301,12 @@ int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* re
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_fwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
+  const int nqt = (gh * gw + 127) / 128;
   if (gh == 14 && gw == 14 && rel_h != nullptr)
-    (void)launch_k(full_attn_fwd_tc_kernel<14>, B * nH, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
+    (void)launch_k(full_attn_fwd_tc_kernel<14>, B * nH * nqt, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
                    reinterpret_cast<__nv_bfloat16*>(out), lse, gh * gw, gh, gw, C, nH, 1);
   else
-    (void)launch_k(full_attn_fwd_tc_kernel<0>, B * nH, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
+    (void)launch_k(full_attn_fwd_tc_kernel<0>, B * nH * nqt, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
                    reinterpret_cast<__nv_bfloat16*>(out), lse, gh * gw, gh, gw, C, nH, rel_h != nullptr);
   return check_launch("full_attn_fwd_tc_kernel");
 }

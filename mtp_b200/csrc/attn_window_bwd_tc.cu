@@ -21,8 +21,11 @@ namespace mtp {
 
 constexpr int WB_THREADS = 256;
 constexpr int WB_TILE = 128 * 128;
-// Q | K~ | V~ | dO | P (2 atoms) | dS (2 atoms) | W (2 atoms) | rel tables | bias tables | coords | dSh,dSw | rw | gxy | red | mbar | slot
-constexpr int WB_SMEM = 10 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 3 * 128 * 8 + 2 * 128 + 64) * 4 + 64;
+// Q | K~ | V~ | dO | PS (2 atoms: P first, then dS) | rel tables | bias tables | coords | dSh,dSw | rw | gxy | red | mbar | slot
+// 110 KB and 256 TMEM columns per CTA, 128 registers per thread: TWO CTAs fit one SM, so the latency chains of one (gather -> MMA -> row
+// phase -> MMA -> scatter) are covered by the other (r1: 185 KB / 512 columns, one CTA per SM, 256 CTAs = 1.73 waves).
+// W (the rel-table weights) is written over the dead V~ tile; its second atom (rows 64..127 of the product, never read) aliases dO.
+constexpr int WB_SMEM = 6 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 3 * 128 * 8 + 2 * 128 + 64) * 4 + 64;
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -32,7 +35,7 @@ __device__ __forceinline__ float tile_read(const uint8_t* tile, int row, int d) 
   return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + tile_chunk_off(row, d >> 3) + (d & 7) * 2));
 }
 
-__global__ void __launch_bounds__(WB_THREADS)
+__global__ void __launch_bounds__(WB_THREADS, 2)
 rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
                         const float* __restrict__ rel_w, const float* __restrict__ bias_table, const float* __restrict__ lse,
                         const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dkv,
@@ -43,10 +46,10 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   uint8_t* Ks = Qs + WB_TILE;
   uint8_t* Vs = Ks + WB_TILE;
   uint8_t* Gs = Vs + WB_TILE;
-  uint8_t* Pt = Gs + WB_TILE;                 // 2 atoms
-  uint8_t* St = Pt + 2 * WB_TILE;             // 2 atoms
-  uint8_t* Wt = St + 2 * WB_TILE;             // 2 atoms: row q, column r = weight of q in d rel table row r (second atom zero)
-  float* relt = reinterpret_cast<float*>(Wt + 2 * WB_TILE);     // [2][13][64]
+  uint8_t* Pt = Gs + WB_TILE;                 // 2 atoms: P (block-diagonal) for dV~ = P^T dO, then overwritten by dS for dQ / dK~ / dR
+  uint8_t* St = Pt;
+  uint8_t* Wt = Vs;                           // row q, column r = weight of q in d rel table row r; written after MMA 1 has consumed V~
+  float* relt = reinterpret_cast<float*>(Pt + 2 * WB_TILE);     // [2][13][64]
   float* tabs = relt + 2 * 13 * 64;           // [2][169]
   float* cpx = tabs + 2 * 169;                // [98]
   float* cpy = cpx + 98;
@@ -68,13 +71,12 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   const int C = g.C, C3 = 3 * g.C;
   const float scale = 0.125f;
 
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   if (tid == 32) {
     mbar_init(mbar, 1);
     fence_barrier_init();
   }
-  // padding rows (49..63 of each problem) of the four operand tiles; every other row is written by the gather.  The second
-  // atom of W is left as is: it only feeds rows 64..127 of the d(rel table) product, which nobody reads.
+  // padding rows (49..63 of each problem) of the four operand tiles; every other row is written by the gather.
   for (int i = tid; i < 4 * 30 * 8; i += WB_THREADS) {
     const int tile = i / 240, rr = (i % 240) >> 3, c = i & 7;
     const int row = rr < 15 ? NTOK + rr : 64 + NTOK + (rr - 15);
@@ -94,7 +96,8 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t T_S = tmem, T_DP = tmem + 128, T_DQ = tmem + 256, T_DK = tmem + 320, T_DV = tmem + 384, T_DR = tmem + 448;
+  // S and dP are consumed into registers by the row phase; the four products of the second round reuse their columns
+  const uint32_t T_S = tmem, T_DP = tmem + 128, T_DV = tmem, T_DQ = tmem + 64, T_DK = tmem + 128, T_DR = tmem + 192;
 
   // ---- gather: 8 lanes per row, 16 B per lane (see the forward kernel)
   for (int i = tid >> 3; i < 2 * NTOK; i += WB_THREADS / 8) {
@@ -204,6 +207,9 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   float sh[WS], sw[WS];
 #pragma unroll
   for (int k = 0; k < WS; ++k) { sh[k] = 0.f; sw[k] = 0.f; }
+  uint4 dsp[8];                           // this row's dS, packed bf16 (owner threads)
+#pragma unroll
+  for (int c = 0; c < 8; ++c) dsp[c] = make_uint4(0, 0, 0, 0);
   if (!helper) {
     uint32_t r0[32], r1[32];
     tmem_ld_32x32(T_S + lane_base + 64 * p, r0);
@@ -255,23 +261,52 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     }
     uint8_t* p_mine = Pt + p * WB_TILE;
     uint8_t* p_other = Pt + (1 - p) * WB_TILE;
-    uint8_t* s_mine = St + p * WB_TILE;
-    uint8_t* s_other = St + (1 - p) * WB_TILE;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      float vp[8], vs[8];
+      float vp[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int j = c * 8 + e;
         vp[e] = j < NTOK ? pr[j < NTOK ? j : 0] : 0.f;
-        vs[e] = j < NTOK ? ds[j < NTOK ? j : 0] : 0.f;
       }
       uint4 u;
       u.x = pack_bf16x2(vp[0], vp[1]); u.y = pack_bf16x2(vp[2], vp[3]); u.z = pack_bf16x2(vp[4], vp[5]); u.w = pack_bf16x2(vp[6], vp[7]);
       *reinterpret_cast<uint4*>(p_mine + tile_chunk_off(row, c)) = u;
-      u.x = pack_bf16x2(vs[0], vs[1]); u.y = pack_bf16x2(vs[2], vs[3]); u.z = pack_bf16x2(vs[4], vs[5]); u.w = pack_bf16x2(vs[6], vs[7]);
-      *reinterpret_cast<uint4*>(s_mine + tile_chunk_off(row, c)) = u;
       *reinterpret_cast<uint4*>(p_other + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
+    }
+    // dS of this row waits in packed form until the P tile has been consumed
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float vs[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = c * 8 + e;
+        vs[e] = j < NTOK ? ds[j < NTOK ? j : 0] : 0.f;
+      }
+      dsp[c].x = pack_bf16x2(vs[0], vs[1]); dsp[c].y = pack_bf16x2(vs[2], vs[3]); dsp[c].z = pack_bf16x2(vs[4], vs[5]); dsp[c].w = pack_bf16x2(vs[6], vs[7]);
+    }
+  }
+  tc_fence_before();
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // ---- dV~ = P^T dO  (the P tile is then handed over to dS)
+  if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
+    tc_fence_after();
+    if (elect_one()) {
+      tc_mma_tiles<true, true>(T_DV, smem_u32(Pt), WB_TILE, smem_u32(Gs), 0, 128, 64, 128, false);
+      umma_commit(mbar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(mbar, 1);
+  tc_fence_after();
+  if (!helper) {
+    uint8_t* s_mine = St + p * WB_TILE;
+    uint8_t* s_other = St + (1 - p) * WB_TILE;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      *reinterpret_cast<uint4*>(s_mine + tile_chunk_off(row, c)) = dsp[c];
       *reinterpret_cast<uint4*>(s_other + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
     }
   }
@@ -279,13 +314,12 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   fence_proxy_async_smem();
   __syncthreads();
 
-  // ---- dQ = dS K~ ; dK~ = dS^T Q ; dV~ = P^T dO
+  // ---- dQ = dS K~ ; dK~ = dS^T Q ; d rel tables = W^T Q
   if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
     tc_fence_after();
     if (elect_one()) {
       tc_mma_tiles<false, true>(T_DQ, smem_u32(St), WB_TILE, smem_u32(Ks), 0, 128, 64, 128, false);
       tc_mma_tiles<true, true>(T_DK, smem_u32(St), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
-      tc_mma_tiles<true, true>(T_DV, smem_u32(Pt), WB_TILE, smem_u32(Gs), 0, 128, 64, 128, false);
       tc_mma_tiles<true, true>(T_DR, smem_u32(Wt), WB_TILE, smem_u32(Qs), 0, 128, 64, 128, false);     // d rel tables = W^T Q (both heads)
       umma_commit(mbar);
     }
@@ -302,7 +336,7 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         s += tile_read(atom, 64 * pp + qy2 * WS + qx2, (qy2 - dy) * WS + (qx2 - dx));
     part_table[((size_t)bw * g.nH + 2 * hp + pp) * 169 + idx] = s;
   }
-  mbar_wait(mbar, 1);
+  mbar_wait(mbar, 0);
   tc_fence_after();
 
   if (warp == 0) {          // rows 0..12 = d rel_pos_h partial, rows 13..25 = d rel_pos_w partial (both heads of this CTA)
@@ -470,7 +504,7 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   }
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, 256);
   }
 }
 
@@ -480,6 +514,7 @@ int launch_rvsa_attn_bwd_tc(const void* qkv, const float* params, const float* r
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(rvsa_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rvsa_attn_bwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_bwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }

@@ -22,7 +22,7 @@ constexpr int WTC_TILE = 128 * 128;                       // bytes of one 128-ro
 // smem: Q | K~ | V~ | P (2 atoms) | rel_h,rel_w fp32 [2][13][64] | table [2][169] | coords [2][98] | rw [128][8] | mbar | tmem slot
 constexpr int WTC_SMEM = 5 * WTC_TILE + 2 * 13 * 64 * 4 + 2 * 169 * 4 + 2 * 98 * 4 + 128 * 8 * 4 + 64;
 
-__global__ void __launch_bounds__(WTC_THREADS)
+__global__ void __launch_bounds__(WTC_THREADS, 2)
 rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ params, const float* __restrict__ rel_h,
                         const float* __restrict__ rel_w, const float* __restrict__ bias_table, __nv_bfloat16* __restrict__ out,
                         float* __restrict__ lse, const RvsaGeom g) {
@@ -253,6 +253,7 @@ int launch_rvsa_attn_fwd_tc(const void* qkv, const float* params, const float* r
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(rvsa_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rvsa_attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa_attn_fwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
