@@ -25,7 +25,9 @@ constexpr int WB_TILE = 128 * 128;
 // 110 KB and 256 TMEM columns per CTA, 128 registers per thread: TWO CTAs fit one SM, so the latency chains of one (gather -> MMA -> row
 // phase -> MMA -> scatter) are covered by the other (r1: 185 KB / 512 columns, one CTA per SM, 256 CTAs = 1.73 waves).
 // W (the rel-table weights) is written over the dead V~ tile; its second atom (rows 64..127 of the product, never read) aliases dO.
-constexpr int WB_SMEM = 6 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 3 * 128 * 8 + 2 * 128 + 64) * 4 + 64;
+// (dyn + 1 KB reserve) x 2 <= 228 KB  =>  dyn <= 115,712 B: the helper hand-over buffer aliases dSh, the coordinate gradients alias dSw
+constexpr int WB_SMEM = 6 * WB_TILE + (2 * 13 * 64 + 2 * 169 + 2 * 98 + 2 * 128 * 8 + 64) * 4 + 64;
+static_assert(2 * (WB_SMEM + 1024) <= 228 * 1024, "two CTAs of the RVSA backward must fit one SM");
 
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -55,9 +57,9 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   float* cpy = cpx + 98;
   float* dSh = cpy + 98;                      // [128][8]
   float* dSw = dSh + 128 * 8;
-  float* rwS = dSw + 128 * 8;                 // [128][8] rel-pos column terms computed by the helper threads
-  float* gxy = rwS + 128 * 8;                 // [128][2] d(sample coords)
-  float* red = gxy + 2 * 128;                 // [64]
+  float* rwS = dSh;                           // [128][8] rel-pos column terms handed from helper to owner (read back before dSh is written)
+  float* gxy = dSw;                           // [128][2] d(sample coords): written by the scatter, after the last reader of dSw
+  float* red = dSw + 128 * 8;                 // [64]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
