@@ -244,6 +244,14 @@ int mtp_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, c
                    const float* group_lr_scale, const float* group_weight_decay, const float* state, size_t n, float lr0,
                    float eta_min, int t_max, float beta1, float beta2, float eps, float max_norm, float grad_scale,
                    mtp_stream_t stream);
+/* data-parallel variant (bf16 gradient buckets): elements [bf16_from, n) take their (rank-summed) gradient from the bf16
+ * buffer g_bf16 (same indexing as g), the rest from the fp32 buffer g.  g_bf16 = NULL: identical to mtp_adamw_step. */
+int mtp_adamw_step_mixed(float* p, const float* g, const void* g_bf16, size_t bf16_from, float* m, float* v, void* p_bf16,
+                         const uint8_t* chunk_group, const float* group_lr_scale, const float* group_weight_decay, const float* state,
+                         size_t n, float lr0, float eta_min, int t_max, float beta1, float beta2, float eps, float max_norm,
+                         float grad_scale, mtp_stream_t stream);
+int mtp_sumsq_bf16(const void* x_bf16, size_t n, float* out, mtp_stream_t stream);
+int mtp_add_f32(const float* in, float* out, size_t n, mtp_stream_t stream);      /* out += in */
 
 /* ---------------------------------------------------------------------------------------------------------------
  * fp32-class forward mode ("fp32x3", precision="fp32x3" on the module; forward only).  Every bf16 tensor of the fast path is stored as

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "mtp_colsum_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "mtp_cast_f32_bf16": [c_void_p, c_void_p, c_size_t, c_void_p],
     "mtp_add_bf16_into_f32": [c_void_p, c_void_p, c_size_t, c_void_p],
+    "mtp_add_f32": [c_void_p, c_void_p, c_size_t, c_void_p],
     "mtp_rvsa_sampling_fwd": [c_void_p] * 9 + [c_int] * 5 + [c_void_p],
     "mtp_rvsa_attn_fwd": [c_void_p] * 7 + [c_int] * 5 + [c_void_p],
     "mtp_full_attn_fwd": [c_void_p] * 5 + [c_int] * 5 + [c_void_p],
@@ -73,6 +74,8 @@ _SIGNATURES = {
     "mtp_probe_launch": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_optim_step_begin": [c_void_p, c_void_p],
     "mtp_sumsq_f32": [c_void_p, c_size_t, c_void_p, c_void_p],
+    "mtp_sumsq_bf16": [c_void_p, c_size_t, c_void_p, c_void_p],
+    "mtp_adamw_step_mixed": [c_void_p, c_void_p, c_void_p, c_size_t] + [c_void_p] * 7 + [c_size_t, c_float, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p],
     "mtp_adamw_step": [c_void_p] * 9 + [c_size_t, c_float, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p],
 }
 _SIZE_FNS = {
@@ -126,9 +129,9 @@ FAMILIES = {
     "rvsa_attn_bwd": ("mtp_rvsa_attn_bwd",), "rvsa_sampling_bwd": ("mtp_rvsa_sampling_bwd",),
     "dense_attn_fwd": ("mtp_full_attn_fwd",), "dense_attn_bwd": ("mtp_full_attn_bwd",),
     "layernorm_fwd": ("mtp_layernorm_fwd",), "layernorm_bwd": ("mtp_layernorm_bwd",),
-    "optimizer": ("mtp_adamw_step", "mtp_sumsq_f32", "mtp_optim_step_begin"),
+    "optimizer": ("mtp_adamw_step", "mtp_adamw_step_mixed", "mtp_sumsq_f32", "mtp_sumsq_bf16", "mtp_optim_step_begin"),
     "layout": ("mtp_patchify", "mtp_patchify_u8", "mtp_tok_to_nchw", "mtp_nchw_to_tok", "mtp_maxpool2_tok_fwd", "mtp_maxpool2_tok_bwd"),
-    "casts_colsums": ("mtp_scale_cast_bf16", "mtp_colsum_bf16", "mtp_cast_f32_bf16", "mtp_add_bf16_into_f32"),
+    "casts_colsums": ("mtp_scale_cast_bf16", "mtp_colsum_bf16", "mtp_cast_f32_bf16", "mtp_add_bf16_into_f32", "mtp_add_f32"),
     "heads": ("mtp_sqloss_fwd_bwd", "mtp_sqloss_fwd_bwd_w"),
 }
 _skip = set()

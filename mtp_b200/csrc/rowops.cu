@@ -379,6 +379,28 @@ extern "C" int mtp_cast_f32_bf16(const float* in, void* out_bf16, size_t n, mtp_
   return check_launch("cast_f32_bf16_kernel");
 }
 
+namespace mtp {
+__global__ void __launch_bounds__(256) add_f32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n4) {
+  MTP_PDL_ENTRY();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(in + i * 4);
+    float4 o = *reinterpret_cast<float4*>(out + i * 4);
+    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    *reinterpret_cast<float4*>(out + i * 4) = o;
+  }
+}
+}  // namespace mtp
+
+/* out_f32 += in_f32 (pyramid-tap cotangents computed ahead of the block loop joining the residual-stream gradient) */
+extern "C" int mtp_add_f32(const float* in, float* out, size_t n, mtp_stream_t stream) {
+  MTP_REQUIRE(in && out && n % 4 == 0, "mtp_add_f32: bad args");
+  if (n == 0) return MTP_OK;
+  const size_t n4 = n / 4;
+  const int grid = (int)std::min<size_t>((n4 + 255) / 256, (size_t)num_sms() * 8);
+  (void)launch_k(mtp::add_f32_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), in, out, n4);
+  return check_launch("add_f32_kernel");
+}
+
 extern "C" int mtp_add_bf16_into_f32(const void* in_bf16, float* out, size_t n, mtp_stream_t stream) {
   MTP_REQUIRE(in_bf16 && out && n % 4 == 0, "mtp_add_bf16_into_f32: bad args");
   if (n == 0) return MTP_OK;

@@ -158,10 +158,13 @@ def _fpn_tap_backward(m, W, S, k, grad, dx, G, B, gh, gw):
     ops.gemm(du1, F_["fpn1_0_w"], T, C, 4 * C, dx, b_mn=True, mode=L.EPI_F32, accumulate=True, lda=4 * C, ldb=C)
 
 
-def backward_impl(m, x, S, grad_outs, grad_store=None, after_block=None):
+def backward_impl(m, x, S, grad_outs, grad_store=None, after_block=None, after_fpn=None):
     """Returns fp32 gradients in ``m.parameters()`` order (None where a parameter does not take part).
     ``grad_store``: reuse a persistent (pre-zeroed where accumulated) GradStore; ``after_block(i)`` is called when the
-    gradients of block i are final (used to launch the bucketed all-reduce while the backward continues)."""
+    gradients of block i are final (used to launch the bucketed all-reduce while the backward continues).
+    ``after_fpn``: when given, the whole pyramid tail (fpn1..4) is differentiated FIRST -- its cotangents w.r.t. the tapped features
+    wait in per-tap buffers until the block loop reaches their block -- and ``after_fpn()`` is called as soon as the ConvTranspose2d
+    weight gradients are final, so that their all-reduce overlaps the entire block backward instead of the last third of it."""
     W = S["W"]
     B, gh, gw, keep = S["B"], S["gh"], S["gw"], S["keep"]
     C, nH = W.C, W.nH
@@ -185,11 +188,25 @@ def backward_impl(m, x, S, grad_outs, grad_store=None, after_block=None):
 
     g16 = None                            # bf16(keep_mlp * dx) of the block about to be processed, when already emitted
     tapped = lambda j: j in taps and grad_outs[taps[j]] is not None
+    hoisted = {}
+    if after_fpn is not None and m.feature_mode != "last_norm":
+        for blk, k in sorted(taps.items(), key=lambda kv: -kv[0]):
+            if grad_outs[k] is not None:
+                buf = torch.zeros(T, C, device=dev, dtype=F32)
+                _fpn_tap_backward(m, W, S, k, grad_outs[k], buf, G, B, gh, gw)
+                hoisted[blk] = buf
+        after_fpn()
     for i in range(W.depth - 1, -1, -1):
         if tapped(i):
-            if dx is None:
-                dx = torch.zeros(T, C, device=dev, dtype=F32)
-            _fpn_tap_backward(m, W, S, taps[i], grad_outs[taps[i]], dx, G, B, gh, gw)
+            if i in hoisted:
+                if dx is None:
+                    dx = hoisted.pop(i)
+                else:
+                    L.call("mtp_add_f32", hoisted.pop(i).data_ptr(), dx.data_ptr(), dx.numel(), ops._stream())
+            else:
+                if dx is None:
+                    dx = torch.zeros(T, C, device=dev, dtype=F32)
+                _fpn_tap_backward(m, W, S, taps[i], grad_outs[taps[i]], dx, G, B, gh, gw)
         if dx is None:
             continue                      # blocks above the highest tapped block receive no gradient
         s = S["blocks"][i]

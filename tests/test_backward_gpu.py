@@ -118,3 +118,27 @@ def test_drop_path_train_mode_matches_oracle():
     assert float(k[0].min()) == 1.0 and float(k[0].max()) == 1.0          # first block has drop prob 0
     vals = set(k[3].unique().tolist())
     assert vals <= {0.0, 1.0 / 0.9} or all(abs(v) < 1e-6 or abs(v - 1 / 0.9) < 1e-5 for v in vals)
+
+
+def test_hoisted_pyramid_backward_equals_inline():
+    """The data-parallel trainer differentiates fpn1..4 ahead of the block loop (their weight gradients become final first and their
+    all-reduce overlaps the whole backward): same gradients as the inline order."""
+    from mtp_b200 import engine, engine_bwd
+    g = load_golden("tiny224")
+    m = build_module("tiny224")
+    m.load_state_dict(g["sd"])
+    m = m.cuda().eval()
+    x = g["x"].cuda()
+    res = []
+    for hoist in (False, True):
+        outs, ctx = engine._forward_impl(m, x, None, save=True)
+        douts = [torch.randn(o.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7 + k)) for k, o in enumerate(outs)]
+        called = []
+        grads = engine_bwd.backward_impl(m, x, ctx, douts, after_fpn=(lambda: called.append(1)) if hoist else None)
+        torch.cuda.synchronize()
+        assert bool(called) == hoist
+        res.append([t.clone() if t is not None else None for t in grads])
+    for (n, _), a, b in zip(m.named_parameters(), res[0], res[1]):
+        assert (a is None) == (b is None), n
+        if a is not None:
+            assert float((a - b).norm()) <= 2e-3 * max(float(a.norm()), 1e-12), n          # accumulation order of the residual-stream gradient differs
