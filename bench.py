@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-gemm-share", action="store_true", help="skip the in-situ GEMM timing pass (leaves the training state intact)")
     ap.add_argument("--bucket-blocks", type=int, default=2, help="transformer blocks per gradient all-reduce bucket (N > 1)")
     ap.add_argument("--comm-sms", type=int, default=16, help="SMs left to NCCL while the backward runs (N > 1)")
+    ap.add_argument("--grad-comm", default="bf16", choices=["bf16", "fp32"], help="dtype of the gradient all-reduce buckets (N > 1)")
     ap.add_argument("--float-input", action="store_true", help="feed a pre-normalised bf16 batch instead of uint8 + fused preprocessing")
     return ap.parse_args()
 
@@ -374,7 +375,7 @@ def main():
     heads = ThreeTaskHeads(split) if split else synthetic_heads
     if cfg["mode"] == "step":
         runner = PretrainStep(model, lr=6e-5, weight_decay=0.05, max_norm=5.0, t_max=80000, use_cuda_graph=bool(args.graph),
-                              bucket_blocks=args.bucket_blocks, comm_sms=args.comm_sms, heads=heads)
+                              bucket_blocks=args.bucket_blocks, comm_sms=args.comm_sms, heads=heads, grad_comm=args.grad_comm)
     else:
         runner = FwdBwdStep(model, heads, bool(args.graph))
     g = torch.Generator().manual_seed(1234 + rank)
@@ -476,7 +477,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["workload"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
                        "streams": list(split) if split else [B], "input": "uint8 CHW + fused MTP_DataPreprocessor" if u8 else "bf16 normalised",
-                       "tokens_per_gpu": B * (S // 16) ** 2, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
+                       "tokens_per_gpu": B * (S // 16) ** 2, "parallelism": f"dp{world}",
+                       "grad_allreduce": (f"{args.grad_comm} buckets of {args.bucket_blocks} blocks, pyramid weights first, small params fp32 last; "
+                                          f"{args.comm_sms} SMs left to NCCL") if world > 1 else None, "cuda_graph": bool(args.graph),
                        "l2": "per-step working set (weights + activations + gradients, GBs) >> 126 MB L2; no explicit flush", "loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches * args.steps,
