@@ -6,6 +6,9 @@
 //                       sums of dS that feed the rel-pos terms; finally dq = scale (dq^ + dSh Rh + dSw Rw) and
 //                       atomically accumulates d full_attn_rel_pos_{h,w} (already reduced over the tile).
 //   full_attn_bwd_dkv : CTA per (image, head, 64-key tile).  Loops over query tiles: dV += P^T dO, dK += dS^T q^.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -331,7 +334,23 @@ int launch_full_attn_bwd_tc(const void* qkv, const float* rel_h, const float* re
 
 using namespace mtp;
 
-extern "C" size_t mtp_full_attn_bwd_workspace_bytes(int B, int gh, int gw, int nH) { return (size_t)B * nH * gh * gw * sizeof(float); }
+namespace mtp {
+size_t full_attn_bwd_stream_workspace_bytes(int B, int gh, int gw, int nH);      // attn_full_stream_bwd_tc.cu
+int launch_full_attn_bwd_stream_tc(const void* qkv, const float* rel_h, const float* rel_w, const float* lse, const void* out, const void* dout,
+                                   void* dqkv, float* d_rel_h, float* d_rel_w, void* workspace, int B, int gh, int gw, int C, int nH,
+                                   cudaStream_t st);
+static bool dense_stream_bwd_ok(int gh, int gw) {
+  static int simt = -1;
+  if (simt < 0) { const char* e = getenv("MTP_DENSE_SIMT"); simt = (e != nullptr && e[0] == '1') ? 1 : 0; }      // A/B switch
+  return !simt && 2 * gh - 1 <= 128 && 2 * gw - 1 <= 128 && (2 * gh - 1 + 2 * gw - 1) * 65 * 4 + 5 * 16384 + 64 <= 227 * 1024;
+}
+}  // namespace mtp
+
+extern "C" size_t mtp_full_attn_bwd_workspace_bytes(int B, int gh, int gw, int nH) {
+  const size_t simt = (size_t)B * nH * gh * gw * sizeof(float);
+  const bool resident = gh * gw <= 256 && gh <= 16 && gw <= 16;      // must mirror the dispatch in mtp_full_attn_bwd
+  return !resident && mtp::dense_stream_bwd_ok(gh, gw) ? std::max(simt, mtp::full_attn_bwd_stream_workspace_bytes(B, gh, gw, nH)) : simt;
+}
 
 extern "C" int mtp_full_attn_bwd(const void* qkv_bf16, const float* rel_pos_h, const float* rel_pos_w, const float* lse,
                                  const void* out_bf16, const void* dout_bf16, void* dqkv_bf16, float* d_rel_pos_h,
@@ -346,6 +365,9 @@ extern "C" int mtp_full_attn_bwd(const void* qkv_bf16, const float* rel_pos_h, c
   if (N <= 256 && gh <= 16 && gw <= 16)       // tensor-core path (one CTA per image-head, K/V resident, dK/dV accumulated in TMEM)
     return launch_full_attn_bwd_tc(qkv_bf16, rel_pos_h, rel_pos_w, lse, out_bf16, dout_bf16, dqkv_bf16, d_rel_pos_h, d_rel_pos_w, B, gh, gw,
                                    C, nH, st);
+  if (dense_stream_bwd_ok(gh, gw))      // long sequences on the tensor cores: K / V block resident, dK / dV in TMEM, dQ through red.global
+    return launch_full_attn_bwd_stream_tc(qkv_bf16, rel_pos_h, rel_pos_w, lse, out_bf16, dout_bf16, dqkv_bf16, d_rel_pos_h, d_rel_pos_w, workspace, B, gh,
+                                          gw, C, nH, st);
   float* Dbuf = reinterpret_cast<float*>(workspace);
   const int smem_dq = (5 * FB_T * FB_LD + 2 * FB_T + 2 * FB_T * (gh + gw)) * (int)sizeof(float);
   const int smem_dkv = (6 * FB_T * FB_LD + 2 * FB_T + FB_T * (gh + gw)) * (int)sizeof(float);

@@ -190,7 +190,8 @@ def test_rvsa_backward_vs_oracle_autograd(grid, B, nH, big):
     print("rvsa bwd", grid, {k: "%.1e" % v for k, v in errs.items()})
 
 
-@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 1, 3, True), (14, 1, 2, False), (16, 1, 2, True), (13, 1, 2, True), (20, 1, 2, True), (14, 2, 16, True)])
+@pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 1, 3, True), (14, 1, 2, False), (16, 1, 2, True), (13, 1, 2, True), (20, 1, 2, True), (14, 2, 16, True),
+                                           (32, 1, 2, True), (32, 2, 4, True), (40, 1, 2, True), (19, 1, 2, False), (64, 1, 1, True)])
 def test_full_attention_backward_vs_autograd(grid, B, nH, rel):
     from mtp_b200 import ops
     C = nH * 64
