@@ -437,9 +437,10 @@ dense_bwd_finish_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
 
+static inline size_t sb_pad(size_t n) { return (n + 15) / 16 * 16; }      // regions start on 64-byte boundaries (float4 / red.v4 accesses)
 size_t full_attn_bwd_stream_workspace_bytes(int B, int gh, int gw, int nH) {
   const size_t N = (size_t)gh * gw, rows = (size_t)B * nH * N;
-  return (rows + 2 * rows * (gh + gw) + (size_t)B * N * nH * 64) * sizeof(float);
+  return (sb_pad(rows) + 2 * sb_pad(rows * (gh + gw)) + (size_t)B * N * nH * 64) * sizeof(float);
 }
 
 int launch_full_attn_bwd_stream_tc(const void* qkv, const float* rel_h, const float* rel_w, const float* lse, const void* out, const void* dout,
@@ -449,9 +450,9 @@ int launch_full_attn_bwd_stream_tc(const void* qkv, const float* rel_h, const fl
   const int use_rel = rel_h != nullptr;
   const size_t rows = (size_t)B * nH * N;
   float* Dbuf = reinterpret_cast<float*>(workspace);
-  float* relbuf = Dbuf + rows;
-  float* dsrow = relbuf + rows * GH;
-  float* dq_acc = dsrow + rows * GH;
+  float* relbuf = Dbuf + sb_pad(rows);
+  float* dsrow = relbuf + sb_pad(rows * GH);
+  float* dq_acc = dsrow + sb_pad(rows * GH);
   const int tab_bytes = (2 * gh - 1 + 2 * gw - 1) * SB_TLD * 4;
   const int nyb_max = std::min(gh, 128 / gw + 2);
   const int R = (nyb_max + gw) | 1;
@@ -465,7 +466,7 @@ int launch_full_attn_bwd_stream_tc(const void* qkv, const float* rel_h, const fl
   if (e == cudaSuccess && smem_main > a_main) { e = cudaFuncSetAttribute(full_attn_bwd_stream_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_main); a_main = smem_main; }
   if (e == cudaSuccess && smem_fin > a_fin) { e = cudaFuncSetAttribute(dense_bwd_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fin); a_fin = smem_fin; }
   if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_bwd_stream smem attr: %s", cudaGetErrorString(e));
-  e = cudaMemsetAsync(dsrow, 0, (rows * GH + (size_t)B * N * C) * sizeof(float), st);      // dsrow | dq_acc are contiguous
+  e = cudaMemsetAsync(dsrow, 0, (sb_pad(rows * GH) + (size_t)B * N * C) * sizeof(float), st);      // dsrow | dq_acc are contiguous
   if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_bwd_stream memset: %s", cudaGetErrorString(e));
   const dim3 grid(ceil_div(N, 128), nH, B);
   const __nv_bfloat16* q16 = reinterpret_cast<const __nv_bfloat16*>(qkv);
