@@ -166,7 +166,10 @@ def test_trainer_state_dict_round_trip_and_weight_reload():
     lb = tb.step(x).item()
     assert abs(la - lb) <= 1e-5 * abs(la), (la, lb)
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        assert torch.allclose(pa, pb, rtol=0, atol=1e-6), n
+        # one Adam step moves a weight by <= lr = 1e-3; the two runs differ by the summation order of the atomics in the gradient kernels,
+        # which Adam amplifies where g ~ 0 (m / (sqrt(v) + eps)): allow 5 % of a step on the worst element, 0.5 % in the norm
+        assert float((pa - pb).abs().max()) <= 5e-5, n
+        assert float((pa - pb).norm()) <= 5e-6 * pa.numel() ** 0.5, n
 
 
 def test_three_task_fan_out_matches_one_head_per_slice():
