@@ -667,6 +667,17 @@ static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sc
   }
   if (out) {
     for (int s = 0; s < MAX_SLOTS; ++s) out->count[s] = s < slots ? (uint16_t)cnt[s] : 0;
+    // Order inside a slot: the epilogue of a CTA's LAST item cannot hide behind a following mainloop, so items with an expensive
+    // epilogue (GELU / GELU': ~20 ALU instructions per element) go first and the cheapest epilogue (plain fp32 / bf16 store) last.
+    if (np == 2) {
+      auto heavy = [&](int id) {
+        const int items0 = (cl2 ? (ceil_div(pr[0].M, BM) + 1) / 2 : ceil_div(pr[0].M, BM)) * ceil_div(pr[0].N, bn);
+        const int m = pr[id < items0 ? 0 : 1].ep.mode;
+        return (m == MTP_EPI_BF16_GELU || m == MTP_EPI_BF16_DGELU) ? 0 : 1;      // sort key: heavy epilogues first
+      };
+      for (int s = 0; s < slots; ++s)
+        std::stable_sort(out->item[s], out->item[s] + cnt[s], [&](uint16_t a, uint16_t b) { return heavy(a) < heavy(b); });
+    }
   }
   return *std::max_element(load.begin(), load.end());
 }
