@@ -276,10 +276,6 @@ int mtp_tok_to_nchw_hilo(const void* tok_hilo, int ld, int lo_offset, float* out
 
 /* measurement aid: an empty kernel launch on `stream` (keeps a skipped kernel's place in a captured step; tools/step_breakdown.py) */
 int mtp_empty_launch(mtp_stream_t stream);
-/* stream-K scheduling of the GEMM (k-blocks of all tiles cut into one equal piece per SM; a cut tile is finished by the CTA holding its first
- * k-blocks, the others park fp32 partial sums in the workspace).  ws_f32: slots*128*256 floats, flags: slots ints zeroed once; slots >= #SMs */
-int mtp_gemm_set_streamk_workspace(float* ws_f32, int* flags, int slots);
-int mtp_gemm_set_streamk(int on);
 /* measurement aid (tools/turnaround_probe.py): do-nothing kernel with a configurable footprint; stamps[grid][4] = entry, ready, done (globaltimer ns) */
 int mtp_probe_launch(long long* stamps, int grid, int threads, int smem_bytes, int tmem_cols, int spin_ns, int pdl_early, mtp_stream_t stream);
 /* tuning aid: cap the depth of the GEMM operand ring (0 = as deep as the shared-memory budget allows) */

@@ -41,8 +41,6 @@ _SIGNATURES = {
     "mtp_gemm_set_debug": [c_void_p],
     "mtp_gemm_set_debug_mode": [c_int],
     "mtp_gemm_set_max_stages": [c_int],
-    "mtp_gemm_set_streamk_workspace": [c_void_p, c_void_p, c_int],
-    "mtp_gemm_set_streamk": [c_int],
     "mtp_layernorm_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p],
     "mtp_layernorm_bwd": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -11,7 +11,6 @@
 #include <cuda.h>
 
 #include <algorithm>
-#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -260,13 +259,6 @@ struct Sched {
   uint16_t count[MAX_SLOTS];
   uint16_t item[MAX_SLOTS][MAX_ITEMS];
   int strided_total;   // > 0: the lists above are unused; slot s walks items s, s + slots, s + 2*slots, ... < strided_total
-  // stream-K (sk_units > 0, single CTAs only): the k-blocks of all tiles form one line of sk_units units (problem 0's tiles first, m fastest);
-  // CTA c works on units [c * sk_units / P, (c + 1) * sk_units / P) (boundaries snapped to tile edges when closer than 4 k-blocks).  A tile
-  // cut between CTAs is FINISHED by the CTA holding its first k-blocks (they are the LAST thing that CTA does); every other holder (its
-  // part is the FIRST thing it does) parks its fp32 partial accumulator in sk_ws[own CTA] and raises sk_flags[own CTA].
-  int sk_units;
-  float* sk_ws;        // [gridDim.x][128][BN] fp32
-  int* sk_flags;       // [gridDim.x], zero between launches (the finishing CTA resets what it consumed)
   int n_stages;        // depth of the smem ring actually used (<= GemmCfg::STAGES): fewer stages = less dynamic smem, so that the CTA of
                        // the NEXT launch can become resident beside this one and hide the SM turnaround (tools/gemm_gaps.py)
   int dbg_mode;        // tuning aid: 0 normal, 1 = skip the TMA loads (MMA pipeline only), 2 = skip the MMAs (TMA pipeline only)
@@ -279,37 +271,6 @@ __device__ __forceinline__ long long gtime() {
   return t;
 }
 #define MTP_STAMP(i) do { if (sched.dbg) sched.dbg[blockIdx.x * 8 + (i)] = gtime(); } while (0)
-
-// ---- stream-K unit arithmetic (identical on every CTA and every warp role)
-struct SkGeom { int kb0, kb1, U0, U, P; };
-__device__ __forceinline__ void sk_tile_of(const SkGeom& g, int u, int& base, int& kbp, int& item, int items0) {
-  if (u < g.U0) { const int t = u / g.kb0; base = t * g.kb0; kbp = g.kb0; item = t; }
-  else { const int t = (u - g.U0) / g.kb1; base = g.U0 + t * g.kb1; kbp = g.kb1; item = items0 + t; }
-}
-__device__ __forceinline__ int sk_start(const SkGeom& g, int c, int items0) {      // first unit of CTA c (c == P: one past the end)
-  if (c <= 0) return 0;
-  if (c >= g.P) return g.U;
-  int b = (int)((long long)c * g.U / g.P);
-  int base, kbp, item;
-  sk_tile_of(g, b, base, kbp, item, items0);
-  const int o = b - base;
-  if (o < 4) b = base;
-  else if (kbp - o < 4) b = base + kbp;
-  return b;
-}
-struct SkSeg { int item, kb_lo, kb_hi, kbp, base; };
-// the idx-th segment of the unit range [u0, u1); returns false when there are fewer
-__device__ __forceinline__ bool sk_segment(const SkGeom& g, int u0, int u1, int idx, int items0, SkSeg& sg) {
-  int u = u0;
-  for (int i = 0; u < u1; ++i) {
-    sk_tile_of(g, u, sg.base, sg.kbp, sg.item, items0);
-    sg.kb_lo = u - sg.base;
-    sg.kb_hi = min(sg.kbp, sg.kb_lo + (u1 - u));
-    if (i == idx) return true;
-    u += sg.kb_hi - sg.kb_lo;
-  }
-  return false;
-}
 
 #ifndef MTP_GEMM_MINBLOCKS
 #define MTP_GEMM_MINBLOCKS 1      // 2: cap registers so that two CTAs (this launch's and the next one's) fit one SM -- co-residency experiments
@@ -335,24 +296,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   const int crank = CL2 ? (int)cluster_ctarank() : 0;
   const int slot = CL2 ? blockIdx.x / 2 : blockIdx.x;
   const int n_slots = CL2 ? gridDim.x / 2 : gridDim.x;
+  const int n_items = sched.strided_total > 0 ? (sched.strided_total - slot + n_slots - 1) / n_slots : sched.count[slot];
   const int groups0 = CL2 ? (p0.tiles_m + 1) / 2 : p0.tiles_m;
   const int items0 = groups0 * p0.tiles_n;
-  const bool SK = !CL2 && !HILO && sched.sk_units > 0;
-  SkGeom skg;
-  skg.kb0 = (p0.K + BK - 1) / BK;
-  skg.kb1 = p1.tiles_m > 0 ? (p1.K + BK - 1) / BK : 1;
-  skg.U0 = items0 * skg.kb0;
-  skg.U = sched.sk_units;
-  skg.P = gridDim.x;
-  const int sk_u0 = SK ? sk_start(skg, blockIdx.x, items0) : 0, sk_u1 = SK ? sk_start(skg, blockIdx.x + 1, items0) : 0;
-  int n_items;
-  if (SK) {
-    SkSeg tmp;
-    n_items = 0;
-    while (sk_segment(skg, sk_u0, sk_u1, n_items, items0, tmp)) ++n_items;
-  } else {
-    n_items = sched.strided_total > 0 ? (sched.strided_total - slot + n_slots - 1) / n_slots : sched.count[slot];
-  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p0.tmA);
@@ -385,18 +331,14 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   if (threadIdx.x == 0) MTP_STAMP(1);
 
 #define MTP_DECODE_ITEM(IT)                                                                      \
-  SkSeg seg_;                                                                                    \
-  seg_.kb_lo = 0; seg_.kb_hi = -1; seg_.base = 0; seg_.kbp = 0; seg_.item = 0;                   \
-  if (SK) sk_segment(skg, sk_u0, sk_u1, (IT), items0, seg_);                                     \
-  const int item_ = SK ? seg_.item : sched.strided_total > 0 ? slot + (IT) * n_slots : sched.item[slot][IT];      \
+  const int item_ = sched.strided_total > 0 ? slot + (IT) * n_slots : sched.item[slot][IT];      \
   const GemmProblem& P = item_ < items0 ? p0 : p1;                                               \
   const int local_ = item_ < items0 ? item_ : item_ - items0;                                    \
   const int mg_ = CL2 ? (P.tiles_m + 1) / 2 : P.tiles_m;                                         \
   const int m0 = ((local_ % mg_) * (CL2 ? 2 : 1) + crank) * BM;                                  \
   const int n0 = (local_ / mg_) * BN;                                                            \
   const int kb1_ = (P.K + BK - 1) / BK;                                                          \
-  const int k_blocks = HILO ? 3 * kb1_ : kb1_;                                                   \
-  const int kb_lo_ = SK ? seg_.kb_lo : 0, kb_hi_ = SK ? seg_.kb_hi : k_blocks;
+  const int k_blocks = HILO ? 3 * kb1_ : kb1_;
   // fp32-class mode (operands stored as [rows, 2K] = hi | lo bf16 words): the k loop runs three passes over K,
   // A_hi B_hi + A_hi B_lo + A_lo B_hi, by moving the k coordinate of the TMA boxes; everything downstream is unchanged
 #define MTP_KA(kb) (!HILO || (kb) < kb1_ ? (kb) : (kb) - kb1_)                      /* hi, hi, lo (lo blocks start at kb1_) */
@@ -416,26 +358,25 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       if (n_items > 0 && sched.dbg_mode == 0) {
         MTP_DECODE_ITEM(0)
         if (P.ep.b_static) {
-          pre = min(STAGES, kb_hi_ - kb_lo_);
+          pre = min(STAGES, k_blocks);
           for (int kb = 0; kb < pre; ++kb) {
             uint8_t* sb = smem + kb * Cfg::STAGE_BYTES + Cfg::A_BYTES;
-            const int kq = kb_lo_ + kb;
             if (elect_one()) {
               if (!CL2) {
                 mbar_arrive_expect_tx(&full_bar[kb], Cfg::STAGE_BYTES);
                 if (!P.b_mn) {
-                  tma_load_2d(sb, &P.tmB, &full_bar[kb], MTP_KB(kq) * BK, n0);
+                  tma_load_2d(sb, &P.tmB, &full_bar[kb], MTP_KB(kb) * BK, n0);
                 } else {
 #pragma unroll
-                  for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[kb], n0 + j * 64, kq * BK);
+                  for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[kb], n0 + j * 64, kb * BK);
                 }
               } else {
                 if (crank == 0) mbar_arrive_expect_tx(&full_bar[kb], 2 * Cfg::STAGE_BYTES);
                 if (!P.b_mn) {
-                  tma_load_2d_2sm(sb, &P.tmB, &full_bar[kb], kq * BK, n0 + crank * (BN / 2));
+                  tma_load_2d_2sm(sb, &P.tmB, &full_bar[kb], kb * BK, n0 + crank * (BN / 2));
                 } else {
 #pragma unroll
-                  for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &P.tmB, &full_bar[kb], n0 + crank * (BN / 2) + j * 64, kq * BK);
+                  for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &P.tmB, &full_bar[kb], n0 + crank * (BN / 2) + j * 64, kb * BK);
                 }
               }
             }
@@ -448,11 +389,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       uint32_t phase = 0;
       for (int it = 0; it < n_items; ++it) {
         MTP_DECODE_ITEM(it)
-        for (int kb = kb_lo_; kb < kb_hi_; ++kb) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          const bool b_done = it == 0 && kb - kb_lo_ < pre;      // this stage's B half (and its expect_tx) were issued above
+          const bool b_done = it == 0 && kb < pre;      // this stage's B half (and its expect_tx) were issued above
           if (elect_one()) {
             if (sched.dbg_mode == 1) {
               if (!CL2 || crank == 0) mbar_arrive(&full_bar[stage]);
@@ -513,9 +454,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb_lo_; kb < kb_hi_; ++kb) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (it == 0 && kb == kb_lo_ && lane == 0) MTP_STAMP(2);
+          if (it == 0 && kb == 0 && lane == 0) MTP_STAMP(2);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -527,8 +468,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
             } else {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
-                if (CL2) umma_bf16_2sm(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, ((kb - kb_lo_) | k) != 0);
-                else umma_bf16(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, ((kb - kb_lo_) | k) != 0);
+                if (CL2) umma_bf16_2sm(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
+                else umma_bf16(d_tmem, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
               }
               if (CL2) umma_commit_2sm_mcast(&empty_bar[stage], 0x3);   // releases the stage in BOTH CTAs
               else umma_commit(&empty_bar[stage]);                      // smem slot reusable once these MMAs retire
@@ -584,64 +525,21 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       const bool f32 = mode_is_f32(ep.mode);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const int n_chunks = sched.dbg_mode == 6 ? 0 : (min(BN, N - n0) + 31) / 32;      // dbg 6: accumulators are never read out
-      const bool sk_donor = SK && kb_lo_ > 0;                     // not the tile's first k-blocks: park the partial sums
-      const bool sk_owner = SK && kb_lo_ == 0 && kb_hi_ < k_blocks;      // first k-blocks of a cut tile: collect the others' partial sums
       uint32_t r[32];
-      if (sk_donor) {
-        // raw fp32 accumulator -> sk_ws[this CTA][row][col] (a lane owns one row: 128 contiguous bytes per 32-column chunk)
-        float* wrow = sched.sk_ws + ((size_t)blockIdx.x * BM + q * 32 + lane) * BN;
-        for (int c = hsel; c < BN / 32; c += 2) {
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
+      int c = hsel;
+      if (c < n_chunks) tmem_ld_32x32(taddr + c * 32, r);
+      for (; c < n_chunks; c += 2) {
+        AuxRegs aux;
+        load_aux(ep, aux, pm, pok, n0 + c * 32, N, lane);
+        tmem_ld_wait();
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(wrow + c * 32 + 4 * j) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        }
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      // every epilogue thread's part of the partial tile is out
-        if (et == 0) {
-          __threadfence();
-          *reinterpret_cast<volatile int*>(sched.sk_flags + blockIdx.x) = 1;
-        }
-      } else {
-        int n_don = 0;
-        if (sk_owner) {          // the CTAs after this one whose range starts inside the same tile hold the rest of its k-blocks
-          const int tile_end = seg_.base + seg_.kbp;
-          while ((int)blockIdx.x + 1 + n_don < (int)gridDim.x && sk_start(skg, blockIdx.x + 1 + n_don, items0) < tile_end) ++n_don;
-          if (lane == 0) {
-            for (int dd = 0; dd < n_don; ++dd)
-              while (*reinterpret_cast<volatile int*>(sched.sk_flags + blockIdx.x + 1 + dd) == 0) { }
-            __threadfence();
-          }
-          __syncwarp();
-        }
-        int c = hsel;
-        if (c < n_chunks) tmem_ld_32x32(taddr + c * 32, r);
-        for (; c < n_chunks; c += 2) {
-          AuxRegs aux;
-          load_aux(ep, aux, pm, pok, n0 + c * 32, N, lane);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (c + 2 < n_chunks) tmem_ld_32x32(taddr + (c + 2) * 32, r);      // next chunk streams in while this one is processed
-          for (int dd = 0; dd < n_don; ++dd) {
-            const float* prow = sched.sk_ws + ((size_t)(blockIdx.x + 1 + dd) * BM + q * 32 + lane) * BN + c * 32;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 pv4 = __ldcg(reinterpret_cast<const float4*>(prow + 4 * j));
-              v[4 * j] += pv4.x; v[4 * j + 1] += pv4.y; v[4 * j + 2] += pv4.z; v[4 * j + 3] += pv4.w;
-            }
-          }
-          float t[4][8];
-          if (f32) lane_transpose<true>(v, t, lane);
-          else lane_transpose<false>(v, t, lane);
-          epilogue_pieces<HILO>(ep, t, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, item_ < items0 ? sq0 : sq1);
-        }
-        if (n_don > 0) {         // all eight warps have consumed the partial tiles: hand the flags back for the next launch
-          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-          if (et < n_don) *reinterpret_cast<volatile int*>(sched.sk_flags + blockIdx.x + 1 + et) = 0;
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (c + 2 < n_chunks) tmem_ld_32x32(taddr + (c + 2) * 32, r);      // next chunk streams in while this one is processed
+        float t[4][8];
+        if (f32) lane_transpose<true>(v, t, lane);
+        else lane_transpose<false>(v, t, lane);
+        epilogue_pieces<HILO>(ep, t, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, item_ < items0 ? sq0 : sq1);
       }
       tc_fence_before();
       __syncwarp();
@@ -785,27 +683,13 @@ static double build_schedule(const HostProblem* pr, int np, int bn, bool cl2, Sc
 }
 
 // config choice (cached per shape signature): minimise the LPT makespan over tile widths and single / paired CTAs
-struct Config { int bn; bool cl2; Sched sched; int sk_units; };
-
-// stream-K workspace handed in by the caller (the library never allocates): partial accumulator tiles + flags, see Sched
-static float* g_sk_ws = nullptr;
-static int* g_sk_flags = nullptr;
-static int g_sk_slots = 0;
-static int g_sk_mode = -1;      // -1: read MTP_GEMM_STREAMK once (default on when a workspace is set), 0 off, 1 on
-static bool streamk_enabled() {
-  if (g_sk_mode < 0) {
-    const char* e = getenv("MTP_GEMM_STREAMK");
-    g_sk_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return g_sk_mode == 1 && g_sk_ws != nullptr && g_sk_flags != nullptr && g_sk_slots >= num_sms();
-}
+struct Config { int bn; bool cl2; Sched sched; };
 
 static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
   static std::map<std::vector<int>, Config> cache;      // node-based: returned pointers stay valid
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
-  const bool sk_ok = streamk_enabled() && force_bn < 1000;
-  std::vector<int> key = {force_bn, np, num_sms(), (int)sk_ok};
+  std::vector<int> key = {force_bn, np, num_sms()};
   for (int p = 0; p < np; ++p) { key.push_back(pr[p].M); key.push_back(pr[p].N); key.push_back(pr[p].K); key.push_back(pr[p].b_mn + 2 * pr[p].ep.hilo); }
   auto it = cache.find(key);
   if (it != cache.end()) return &it->second;
@@ -827,37 +711,7 @@ static const Config* get_config(const HostProblem* pr, int np, int force_bn) {
     }
   }
   if (best.bn == 0) return nullptr;
-  best.sk_units = 0;
-  bool any_hilo = false;
-  for (int p = 0; p < np; ++p) any_hilo |= pr[p].ep.hilo != 0;
-  if (sk_ok && !any_hilo) {
-    // stream-K: every CTA gets the same number of k-blocks, so the tile width is chosen for mainloop efficiency alone (plus the per-tile
-    // epilogue cost); it replaces the tile-granular LPT schedule whenever its modelled makespan is shorter
-    const int P = num_sms();
-    int sk_bn = 0;
-    double sk_cost = 1e300;
-    long long sk_units = 0;
-    for (int i = 0; i < 3; ++i) {
-      const int bn = cand[i];
-      if (force_bn && bn != force_bn % 1000) continue;
-      long long U = 0, tiles = 0;
-      for (int p = 0; p < np; ++p) {
-        const long long t = (long long)ceil_div(pr[p].M, BM) * ceil_div(pr[p].N, bn);
-        U += t * ceil_div(pr[p].K, BK);
-        tiles += t;
-      }
-      if (U < 8LL * P || U > 2000000000LL) continue;
-      const double c = (double)ceil_div((int)U, P) * kblock_cycles(bn, false) + kTileFixedCycles * ((double)tiles / P + 1.0);
-      if (c < sk_cost) { sk_cost = c; sk_bn = bn; sk_units = U; }
-    }
-    if (sk_bn != 0 && (force_bn || sk_cost < best_cost)) {
-      best.bn = sk_bn;
-      best.cl2 = false;
-      best.sk_units = (int)sk_units;
-    }
-  }
   build_schedule(pr, np, best.bn, best.cl2, &best.sched);
-  best.sched.sk_units = best.sk_units;
   return &cache.emplace(key, best).first->second;
 }
 
@@ -875,9 +729,6 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
   sched.dbg = g_gemm_dbg;
   sched.dbg_mode = g_gemm_dbg_mode;
   using Cfg = GemmCfg<BN, CL2>;
-  sched.sk_ws = g_sk_ws;
-  sched.sk_flags = g_sk_flags;
-  if (CL2 || HILO || !streamk_enabled()) sched.sk_units = 0;
   sched.n_stages = g_gemm_max_stages > 0 ? std::max(2, std::min(Cfg::STAGES, g_gemm_max_stages)) : Cfg::STAGES;
   const int smem_bytes = Cfg::SMEM_BYTES - (Cfg::STAGES - sched.n_stages) * Cfg::STAGE_BYTES;
   GemmProblem gp[2];
@@ -908,7 +759,6 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
   const int slots = CL2 ? num_sms() / 2 : num_sms();
   int used = 0;
   for (int s = 0; s < slots; ++s) if (sched.count[s] > 0) used = s + 1;
-  if (sched.sk_units > 0) used = slots;          // stream-K: the unit line is cut into one piece per SM
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
@@ -990,7 +840,7 @@ static int run_grouped(const HostProblem* pr, int np, int force_bn, cudaStream_t
   }
   const Config* cfg = get_config(pr, np, force_bn);
   if (cfg == nullptr) return set_error(MTP_ERR_INVALID, "mtp_gemm_bf16: no valid tile configuration (force_bn=%d)", force_bn);
-  g_last_config = cfg->bn + (cfg->cl2 ? 1000 : 0) + (cfg->sk_units > 0 ? 2000 : 0);
+  g_last_config = cfg->bn + (cfg->cl2 ? 1000 : 0);
 #define MTP_LAUNCH(BN_)                                                             \
   case BN_:                                                                         \
     return cfg->cl2 ? launch_grouped<BN_, true>(pr, np, cfg->sched, stream) : launch_grouped<BN_, false>(pr, np, cfg->sched, stream);
@@ -1081,18 +931,6 @@ extern "C" int mtp_gemm_set_debug(void* device_buffer) {
   return MTP_OK;
 }
 extern "C" int mtp_gemm_last_config(void) { return g_last_config; }
-/* Stream-K workspace (caller-owned device memory): ws_f32 >= slots * 128 * 256 floats, flags >= slots ints, ZEROED once by the caller;
- * slots >= the SM count.  Without it (or with MTP_GEMM_STREAMK=0 / mtp_gemm_set_streamk(0)) every launch uses the tile-granular schedule. */
-extern "C" int mtp_gemm_set_streamk_workspace(float* ws_f32, int* flags, int slots) {
-  g_sk_ws = ws_f32;
-  g_sk_flags = flags;
-  g_sk_slots = (ws_f32 != nullptr && flags != nullptr) ? slots : 0;
-  return MTP_OK;
-}
-extern "C" int mtp_gemm_set_streamk(int on) {
-  g_sk_mode = on ? 1 : 0;
-  return MTP_OK;
-}
 /* tuning aid: cap the depth of the operand ring (0 = fill the smem budget).  A shallow ring leaves room for the next launch's CTA on the
  * same SM (co-residency hides the SM turnaround between dependent launches, at the price of less latency cover in the mainloop). */
 extern "C" int mtp_gemm_set_max_stages(int n) {

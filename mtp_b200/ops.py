@@ -20,27 +20,10 @@ def _chk(t, dtype, name):
     assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), f"{name}: need contiguous cuda {dtype}, got {t.dtype} {t.device} contiguous={t.is_contiguous()}"
 
 
-_SK = {}
-
-
-def _ensure_streamk_workspace(device):
-    """Caller-owned scratch of the stream-K GEMM schedule (partial accumulator tiles + flags), one per device, allocated once so that
-    CUDA graphs can bake its address."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
-    if key not in _SK:
-        slots = 160
-        ws = torch.empty(slots * 128 * 256, device=device, dtype=F32)
-        flags = torch.zeros(slots, device=device, dtype=torch.int32)
-        _SK[key] = (ws, flags)
-        L.call("mtp_gemm_set_streamk_workspace", ws.data_ptr(), flags.data_ptr(), slots)
-    return _SK[key]
-
-
 def gemm(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=None, out2=None, aux=None, row_scale=None,
          rows_per_group=0, pos_rows=0, accumulate=False, ldo=None, lda=None, ldb=None, ps=None, force_bn=0, colsum=None, b_static=False, sumsq=None,
          hilo=False, out_lo=0):
     """acc[m,n] = sum_k A[m,k] B[n,k] with fused epilogue; see include/mtp_b200.h."""
-    _ensure_streamk_workspace(A.device)
     ep = L.Epilogue()
     ep.mode = mode
     ep.colsum = _p(colsum)
@@ -80,7 +63,6 @@ def _desc(A, B, M, N, K, out, *, a_mn=False, b_mn=False, mode=L.EPI_BF16, bias=N
 
 def gemm_dual(g0, g1, force_bn=0):
     """Two independent GEMMs (dicts of gemm() arguments) in one grouped persistent launch."""
-    _ensure_streamk_workspace(g0["A"].device)
     d0, d1 = _desc(**g0), _desc(**g1)
     L.call("mtp_gemm_bf16_dual", ctypes.byref(d0), ctypes.byref(d1), int(force_bn), _stream())
 
