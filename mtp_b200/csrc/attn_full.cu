@@ -222,7 +222,9 @@ extern "C" int mtp_full_attn_fwd(const void* qkv_bf16, const float* rel_pos_h, c
   MTP_REQUIRE((rel_pos_h == nullptr) == (rel_pos_w == nullptr), "mtp_full_attn_fwd: give both rel-pos tables or neither");
   MTP_REQUIRE(B > 0 && gh > 0 && gw > 0 && C == nH * FA_HD, "mtp_full_attn_fwd: B=%d grid=%dx%d C=%d nH=%d unsupported (hd must be 64)", B, gh, gw, C, nH);
   const int N = gh * gw;
-  if (N <= 256 && gh <= 16 && gw <= 16)       // tensor-core path: K/V of a head resident in shared memory
+  static int stream_all = -1;      // A/B switch: MTP_DENSE_STREAM_ALL=1 sends short sequences through the streaming kernels too
+  if (stream_all < 0) { const char* e = getenv("MTP_DENSE_STREAM_ALL"); stream_all = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  if (N <= 256 && gh <= 16 && gw <= 16 && !stream_all)       // tensor-core path: K/V of a head resident in shared memory
     return launch_full_attn_fwd_tc(qkv_bf16, rel_pos_h, rel_pos_w, out_bf16, lse, B, gh, gw, C, nH, reinterpret_cast<cudaStream_t>(stream));
   {       // long sequences: K / V streamed in 128-key blocks with an online softmax, still on the tensor cores
     static int simt = -1;

@@ -339,6 +339,11 @@ size_t full_attn_bwd_stream_workspace_bytes(int B, int gh, int gw, int nH);     
 int launch_full_attn_bwd_stream_tc(const void* qkv, const float* rel_h, const float* rel_w, const float* lse, const void* out, const void* dout,
                                    void* dqkv, float* d_rel_h, float* d_rel_w, void* workspace, int B, int gh, int gw, int C, int nH,
                                    cudaStream_t st);
+static bool dense_stream_all() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MTP_DENSE_STREAM_ALL"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 static bool dense_stream_bwd_ok(int gh, int gw) {
   static int simt = -1;
   if (simt < 0) { const char* e = getenv("MTP_DENSE_SIMT"); simt = (e != nullptr && e[0] == '1') ? 1 : 0; }      // A/B switch
@@ -348,7 +353,7 @@ static bool dense_stream_bwd_ok(int gh, int gw) {
 
 extern "C" size_t mtp_full_attn_bwd_workspace_bytes(int B, int gh, int gw, int nH) {
   const size_t simt = (size_t)B * nH * gh * gw * sizeof(float);
-  const bool resident = gh * gw <= 256 && gh <= 16 && gw <= 16;      // must mirror the dispatch in mtp_full_attn_bwd
+  const bool resident = gh * gw <= 256 && gh <= 16 && gw <= 16 && !mtp::dense_stream_all();      // must mirror the dispatch in mtp_full_attn_bwd
   return !resident && mtp::dense_stream_bwd_ok(gh, gw) ? std::max(simt, mtp::full_attn_bwd_stream_workspace_bytes(B, gh, gw, nH)) : simt;
 }
 
@@ -362,7 +367,7 @@ extern "C" int mtp_full_attn_bwd(const void* qkv_bf16, const float* rel_pos_h, c
   MTP_REQUIRE(B > 0 && gh > 0 && gw > 0 && C == nH * FB_HD, "mtp_full_attn_bwd: unsupported geometry");
   const int N = gh * gw;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (N <= 256 && gh <= 16 && gw <= 16)       // tensor-core path (one CTA per image-head, K/V resident, dK/dV accumulated in TMEM)
+  if (N <= 256 && gh <= 16 && gw <= 16 && !dense_stream_all())       // tensor-core path (one CTA per image-head, K/V resident, dK/dV accumulated in TMEM)
     return launch_full_attn_bwd_tc(qkv_bf16, rel_pos_h, rel_pos_w, lse, out_bf16, dout_bf16, dqkv_bf16, d_rel_pos_h, d_rel_pos_w, B, gh, gw,
                                    C, nH, st);
   if (dense_stream_bwd_ok(gh, gw))      // long sequences on the tensor cores: K / V block resident, dK / dV in TMEM, dQ through red.global

@@ -122,12 +122,14 @@ def _block_forward(d, x0, B, gh, gw, nH, keep_a, keep_m, save):
     T, C = x0.shape
     N = gh * gw
     y1, mean1, rstd1 = ops.layernorm_fwd(x0, d["norm1_w"], d["norm1_b"], save_stats=save)
-    qkv = torch.empty(T, 3 * C, device=x0.device, dtype=BF16)
-    ops.gemm(y1, d["qkv_w"], T, 3 * C, C, qkv, bias=d["qkv_b"], b_static=True)
     params = pooled = None
-    if d["window"]:
+    if d["window"]:      # the sampling heads only need y1: launched BEFORE the qkv GEMM, so that this light kernel follows the light LayerNorm
+        #                  (a kernel that follows a GEMM pays the GEMM's 5-7 us SM turnaround, profiles/r2_summary.md section 4)
         params, pooled = ops.rvsa_sampling_fwd(y1, d["off_w"], d["off_b"], d["sc_w"], d["sc_b"], d["ang_w"], d["ang_b"], B, gh, gw, nH,
                                                save_pooled=save)
+    qkv = torch.empty(T, 3 * C, device=x0.device, dtype=BF16)
+    ops.gemm(y1, d["qkv_w"], T, 3 * C, C, qkv, bias=d["qkv_b"], b_static=True)
+    if d["window"]:
         o, lse = ops.rvsa_attn_fwd(qkv, params, d["rel_h"], d["rel_w"], d["table"], B, gh, gw, nH, save_lse=save)
     else:
         o, lse = ops.full_attn_fwd(qkv, d["rel_h"], d["rel_w"], B, gh, gw, nH, save_lse=save)

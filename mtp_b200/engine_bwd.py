@@ -91,15 +91,20 @@ def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
                                  G.g(pre + "attn.full_attn_rel_pos_h") if has_rel else None,
                                  G.g(pre + "attn.full_attn_rel_pos_w") if has_rel else None, B, gh, gw, nH)
         ops.colsum_bf16(dqkv, G.g(pre + "attn.qkv.bias"))
-    dy1 = _linear_bwd(dqkv, s["y1"], d["qkv_w"], G.g(pre + "attn.qkv.weight"), T, 3 * C, C, sumsq=G.sumsq)
     pool = None
-    if d["window"]:                       # the pooled (AvgPool) path of the sampling heads joins dy1 inside the LayerNorm backward
+    if d["window"] and _POOL_FUSE:        # the sampling heads' backward only needs dparams: it runs BEFORE the qkv GEMMs (light kernels after
+        #                                   light kernels); its pooled (AvgPool) path joins dy1 inside the LayerNorm backward
         a = pre + "attn.sampling_"
         dpooled = ops.rvsa_sampling_bwd(dparams, s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],
                                         G.g(a + "offsets.2.weight"), G.g(a + "offsets.2.bias"), G.g(a + "scales.2.weight"),
-                                        G.g(a + "scales.2.bias"), G.g(a + "angles.2.weight"), G.g(a + "angles.2.bias"),
-                                        None if _POOL_FUSE else dy1, B, gh, gw, nH)
-        pool = (dpooled, gh, gw) if _POOL_FUSE else None
+                                        G.g(a + "scales.2.bias"), G.g(a + "angles.2.weight"), G.g(a + "angles.2.bias"), None, B, gh, gw, nH)
+        pool = (dpooled, gh, gw)
+    dy1 = _linear_bwd(dqkv, s["y1"], d["qkv_w"], G.g(pre + "attn.qkv.weight"), T, 3 * C, C, sumsq=G.sumsq)
+    if d["window"] and not _POOL_FUSE:
+        a = pre + "attn.sampling_"
+        ops.rvsa_sampling_bwd(dparams, s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],
+                              G.g(a + "offsets.2.weight"), G.g(a + "offsets.2.bias"), G.g(a + "scales.2.weight"),
+                              G.g(a + "scales.2.bias"), G.g(a + "angles.2.weight"), G.g(a + "angles.2.bias"), dy1, B, gh, gw, nH)
     if nxt is None:
         dx0 = ops.layernorm_bwd(dy1, s["x0"], s["mean1"], s["rstd1"], d["norm1_w"], None, dx1, G.g(pre + "norm1.weight"), G.g(pre + "norm1.bias"),
                                 pool_add=pool)
