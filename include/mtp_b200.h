@@ -276,6 +276,8 @@ int mtp_tok_to_nchw_hilo(const void* tok_hilo, int ld, int lo_offset, float* out
 
 /* measurement aid: an empty kernel launch on `stream` (keeps a skipped kernel's place in a captured step; tools/step_breakdown.py) */
 int mtp_empty_launch(mtp_stream_t stream);
+/* GEMM kernel variant: 1 = persistent warp-specialised kernel, 2 = one tile per CTA with two CTAs per SM (gemm.cu, "Variant 2") */
+int mtp_gemm_set_variant(int v);
 /* measurement aid (tools/turnaround_probe.py): do-nothing kernel with a configurable footprint; stamps[grid][4] = entry, ready, done (globaltimer ns) */
 int mtp_probe_launch(long long* stamps, int grid, int threads, int smem_bytes, int tmem_cols, int spin_ns, int pdl_early, mtp_stream_t stream);
 /* tuning aid: cap the depth of the GEMM operand ring (0 = as deep as the shared-memory budget allows) */

@@ -11,6 +11,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -574,6 +576,189 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   }
 }
 
+// ===================================================================================================================
+// Variant 2: ONE tile per CTA, TWO CTAs per SM (mtp_gemm_set_variant(2) / MTP_GEMM_VARIANT=2).
+//
+// Motivation (profiles/r2_summary.md section 4): behind the persistent kernel above every dependent launch pays 5-8 us of SM turnaround, because
+// a CTA of 200 KB smem / 512 TMEM columns must fully retire before its successor can become resident.  Here a CTA owns 98 KB smem (2-3
+// stage ring), one 128 x BN accumulator (<= 256 TMEM columns) and 192 threads (TMA warp, MMA warp, 4 epilogue warps), so two fit one SM:
+// while one CTA runs its epilogue the other one's mainloop owns the tensor core, and the NEXT launch's CTAs move into the slots freed by
+// early finishers, run their prologue and wait at griddepcontrol.wait before their predecessor grid has drained.  Tiles are handed to the SMs
+// by the hardware block scheduler in blockIdx order (problem 0 first), which also balances the tail dynamically.
+constexpr int G2_THREADS = 192, G2_EPI_THREADS = 128;
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN <= 128 ? 3 : 2;
+  static constexpr int TMEM_COLS = BN <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/ + BN * 4 /*bias*/;
+  static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs must fit one SM");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(G2_THREADS, 2)
+gemm2_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__ GemmProblem p1, int items0, int dbg_mode) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (dbg_mode == 4) return;
+  const int item = blockIdx.x;
+  const GemmProblem& P = item < items0 ? p0 : p1;
+  const int local = item < items0 ? item : item - items0;
+  const int m0 = (local % P.tiles_m) * BM, n0 = (local / P.tiles_m) * BN;
+  const int k_blocks = (P.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmA);
+    tma_prefetch_desc(&P.tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop, elected lane issues)
+    int pre = 0;
+    if (P.ep.b_static) {          // B tiles that do not depend on the stream predecessor: requested before the dependency wait
+      pre = min(STAGES, k_blocks);
+      for (int kb = 0; kb < pre; ++kb) {
+        uint8_t* sb = smem + kb * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[kb], Cfg::STAGE_BYTES);
+          if (!P.b_mn) {
+            tma_load_2d(sb, &P.tmB, &full_bar[kb], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[kb], n0 + j * 64, kb * BK);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    MTP_PDL_ENTRY();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+      uint8_t* sb = sa + Cfg::A_BYTES;
+      const bool b_done = kb < pre;
+      if (elect_one()) {
+        if (!b_done) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        if (!P.a_mn) {
+          tma_load_2d(sa, &P.tmA, &full_bar[stage], kb * BK, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &P.tmA, &full_bar[stage], m0 + j * 64, kb * BK);
+        }
+        if (b_done) {
+        } else if (!P.b_mn) {
+          tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[stage], n0 + j * 64, kb * BK);
+        }
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    MTP_PDL_ENTRY();
+    const uint32_t idesc = make_idesc_bf16(BM, BN, P.a_mn != 0, P.b_mn != 0);
+    const uint32_t a_lbo = P.a_mn ? 8192 : 16, b_lbo = P.b_mn ? 8192 : 16;
+    const uint64_t a_step = P.a_mn ? 128 : 2, b_step = P.b_mn ? 128 : 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+      const uint32_t sb = sa + Cfg::A_BYTES;
+      const uint64_t a_desc0 = make_smem_desc(sa, a_lbo, 1024);
+      const uint64_t b_desc0 = make_smem_desc(sb, b_lbo, 1024);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, a_desc0 + k * a_step, b_desc0 + k * b_step, idesc, (kb | k) != 0);
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue: warp w owns TMEM lane quarter w & 3, all column chunks
+    MTP_PDL_ENTRY();
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;
+    const EpiParams& ep = P.ep;
+    const int M = P.M, N = P.N;
+    if (ep.bias != nullptr) {
+      for (int i = et; i < BN; i += G2_EPI_THREADS) {
+        const int n = n0 + i;
+        bias_s[i] = n < N ? __ldg(ep.bias + (ep.ps_cout > 0 ? n % ep.ps_cout : n)) : 0.f;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_THREADS) : "memory");
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    int pm[4];
+    bool pok[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      pm[p] = m0 + q * 32 + piece_row(lane, p);
+      pok[p] = pm[p] < M && dbg_mode != 3;
+    }
+    const bool f32 = mode_is_f32(ep.mode);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int n_chunks = (min(BN, N - n0) + 31) / 32;
+    float sq = 0.f;
+    uint32_t r[32];
+    if (n_chunks > 0) tmem_ld_32x32(taddr, r);
+    for (int c = 0; c < n_chunks; ++c) {
+      AuxRegs aux;
+      load_aux(ep, aux, pm, pok, n0 + c * 32, N, lane);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (c + 1 < n_chunks) tmem_ld_32x32(taddr + (c + 1) * 32, r);
+      float t[4][8];
+      if (f32) lane_transpose<true>(v, t, lane);
+      else lane_transpose<false>(v, t, lane);
+      epilogue_pieces<false>(ep, t, aux, ep.bias != nullptr ? bias_s + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, sq);
+    }
+    if (ep.sumsq != nullptr) {
+      sq = warp_sum(sq);
+      if (lane == 0 && sq != 0.f) atomicAdd(ep.sumsq, sq);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -828,11 +1013,99 @@ static EpiParams to_epi(const mtp_epilogue* ep) {
   return p;
 }
 
+static int g_gemm_variant = -1;      // 1: persistent kernel, 2: one tile per CTA with two CTAs per SM; -1: read MTP_GEMM_VARIANT once
+static int gemm_variant() {
+  if (g_gemm_variant < 0) {
+    const char* e = getenv("MTP_GEMM_VARIANT");
+    g_gemm_variant = (e != nullptr && e[0] == '2') ? 2 : 1;
+  }
+  return g_gemm_variant;
+}
+
+template <int BN>
+static int launch_gemm2(const HostProblem* pr, int np, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  GemmProblem gp[2];
+  memset(gp, 0, sizeof(gp));
+  int items[2] = {0, 0};
+  for (int p = 0; p < np; ++p) {
+    const HostProblem& h = pr[p];
+    int rc = h.a_mn ? make_tmap(&gp[p].tmA, h.A, h.K, h.M, h.lda, BK) : make_tmap(&gp[p].tmA, h.A, h.M, h.K, h.lda, BM);
+    if (rc) return rc;
+    rc = h.b_mn ? make_tmap(&gp[p].tmB, h.B, h.K, h.N, h.ldb, BK) : make_tmap(&gp[p].tmB, h.B, h.N, h.K, h.ldb, BN);
+    if (rc) return rc;
+    gp[p].ep = h.ep;
+    gp[p].M = h.M; gp[p].N = h.N; gp[p].K = h.K;
+    gp[p].tiles_m = ceil_div(h.M, BM); gp[p].tiles_n = ceil_div(h.N, BN);
+    gp[p].a_mn = h.a_mn; gp[p].b_mn = h.b_mn;
+    items[p] = gp[p].tiles_m * gp[p].tiles_n;
+  }
+  static bool attr_set_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  bool& attr_set = attr_set_dev[dev_ & 63];
+  auto kern = gemm2_bf16_kernel<BN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "cudaFuncSetAttribute(gemm2 BN=%d): %s", BN, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.gridDim = dim3(items[0] + items[1]);
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  }
+  cfg.blockDim = dim3(G2_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gp[0], gp[1], items[0], g_gemm_dbg_mode);
+  if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "gemm2_bf16_kernel launch: %s", cudaGetErrorString(e));
+  return check_launch("gemm2_bf16_kernel");
+}
+
+// tile width of variant 2: per-SM work when the hardware deals the tiles to 2 slots per SM (both slots share one tensor core)
+static int gemm2_pick_bn(const HostProblem* pr, int np, int force_bn) {
+  if (force_bn) return force_bn % 1000;
+  const int cand[3] = {256, 192, 128};
+  int best = 256;
+  double best_c = 1e300;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    double c = 0.0;
+    long long tiles = 0;
+    for (int p = 0; p < np; ++p) {
+      const long long t = (long long)ceil_div(pr[p].M, BM) * ceil_div(pr[p].N, bn);
+      tiles += t;
+      c += (double)t * (ceil_div(pr[p].K, BK) * kblock_cycles(bn, false) + kTileFixedCycles);
+    }
+    const int P = num_sms();
+    const double per_sm = std::ceil((double)tiles / P) / ((double)tiles / P);      // quantisation of whole tiles per SM
+    c = c / P * per_sm;
+    if (c < best_c) { best_c = c; best = bn; }
+  }
+  return best;
+}
+
 static int run_grouped(const HostProblem* pr, int np, int force_bn, cudaStream_t stream) {
   for (int p = 0; p < np; ++p) {
     int rc = validate_problem(pr[p]);
     if (rc) return rc;
     MTP_REQUIRE(!pr[p].ep.hilo || np == 1, "mtp_gemm_bf16_dual: hilo mode is not available in grouped launches");
+  }
+  if (gemm_variant() == 2 && force_bn < 1000 && !pr[0].ep.hilo && (force_bn == 0 || force_bn >= 128)) {
+    const int bn = gemm2_pick_bn(pr, np, force_bn);
+    g_last_config = 3000 + bn;
+    switch (bn) {
+      case 128: return launch_gemm2<128>(pr, np, stream);
+      case 192: return launch_gemm2<192>(pr, np, stream);
+      case 256: return launch_gemm2<256>(pr, np, stream);
+      default: break;
+    }
   }
   if (force_bn >= 1000) {
     for (int p = 0; p < np; ++p)
@@ -931,6 +1204,12 @@ extern "C" int mtp_gemm_set_debug(void* device_buffer) {
   return MTP_OK;
 }
 extern "C" int mtp_gemm_last_config(void) { return g_last_config; }
+/* 1: persistent warp-specialised kernel (default); 2: one tile per CTA, two CTAs per SM (co-residency hides the SM turnaround between
+ * dependent launches).  mtp_gemm_last_config() reports 3000 + BN for variant 2. */
+extern "C" int mtp_gemm_set_variant(int v) {
+  g_gemm_variant = v == 2 ? 2 : 1;
+  return MTP_OK;
+}
 /* tuning aid: cap the depth of the operand ring (0 = fill the smem budget).  A shallow ring leaves room for the next launch's CTA on the
  * same SM (co-residency hides the SM turnaround between dependent launches, at the price of less latency cover in the mainloop). */
 extern "C" int mtp_gemm_set_max_stages(int n) {

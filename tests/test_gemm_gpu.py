@@ -205,3 +205,76 @@ def test_b_static_prefetch_matches(bn, b_mn):
         outs.append((dx, dW))
     torch.cuda.synchronize()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("case", ["qkv_fwd", "fc1_fwd_gelu", "fc2_fwd", "fc1_dgrad", "fc2_wgrad", "fc2_dual", "ragged", "pixbias"])
+def test_gemm_variant2_matches_persistent_kernel(case):
+    """Variant 2 (one tile per CTA, two CTAs per SM) against the persistent kernel: all operand layouts, the fused epilogues, the grouped launch."""
+    from mtp_b200 import ops, _lib as L
+    T, C = 1568, 1024
+    dev = "cuda"
+    bf = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(torch.bfloat16)
+
+    def run(variant):
+        L.call("mtp_gemm_set_variant", variant)
+        torch.manual_seed(11)
+        if case == "qkv_fwd":
+            A, B = bf(T, C), bf(3 * C, C)
+            out = torch.empty(T, 3 * C, device=dev, dtype=torch.bfloat16)
+            ops.gemm(A, B, T, 3 * C, C, out, bias=torch.randn(3 * C, device=dev), b_static=True)
+            outs = [out]
+        elif case == "fc1_fwd_gelu":
+            A, B = bf(T, C), bf(4 * C, C)
+            out = torch.empty(T, 4 * C, device=dev, dtype=torch.bfloat16)
+            out2 = torch.empty_like(out)
+            ops.gemm(A, B, T, 4 * C, C, out, mode=L.EPI_BF16_GELU, bias=torch.randn(4 * C, device=dev), out2=out2)
+            outs = [out, out2]
+        elif case == "fc2_fwd":
+            A, B = bf(T, 4 * C), bf(C, 4 * C)
+            out = torch.empty(T, C, device=dev)
+            ops.gemm(A, B, T, C, 4 * C, out, mode=L.EPI_F32_RESID, bias=torch.randn(C, device=dev), aux=torch.randn(T, C, device=dev),
+                     row_scale=torch.rand(8, device=dev), rows_per_group=196)
+            outs = [out]
+        elif case == "fc1_dgrad":
+            g, w = bf(T, 4 * C), bf(4 * C, C)
+            out = torch.empty(T, C, device=dev, dtype=torch.bfloat16)
+            cs = torch.zeros(C, device=dev)
+            ops.gemm(g, w, T, C, 4 * C, out, b_mn=True, lda=4 * C, ldb=C, colsum=cs)
+            outs = [out, cs]
+        elif case == "fc2_wgrad":
+            g, x = bf(T, C), bf(T, 4 * C)
+            out = torch.empty(C, 4 * C, device=dev)
+            ss = torch.zeros(1, device=dev)
+            ops.gemm(g, x, C, 4 * C, T, out, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=C, ldb=4 * C, ldo=4 * C, sumsq=ss)
+            outs = [out, ss]
+        elif case == "fc2_dual":
+            g, w, x, hp = bf(T, C), bf(C, 4 * C), bf(T, 4 * C), bf(T, 4 * C)
+            dx = torch.empty(T, 4 * C, device=dev, dtype=torch.bfloat16)
+            dW = torch.empty(C, 4 * C, device=dev)
+            cs = torch.zeros(4 * C, device=dev)
+            ops.gemm_dual(dict(A=g, B=w, M=T, N=4 * C, K=C, out=dx, b_mn=True, mode=L.EPI_BF16_DGELU, aux=hp, lda=C, ldb=4 * C, colsum=cs),
+                          dict(A=g, B=x, M=C, N=4 * C, K=T, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, lda=C, ldb=4 * C, ldo=4 * C))
+            outs = [dx, dW, cs]
+        elif case == "pixbias":
+            A, B = bf(T, C), bf(4 * C, C)
+            out = torch.empty(T, 4 * C, device=dev, dtype=torch.bfloat16)
+            ops.gemm(A, B, T, 4 * C, C, out, bias=torch.randn(C, device=dev), ps=(0, 0, C))
+            outs = [out]
+        else:       # ragged M / N / K with an accumulate epilogue
+            M, N, K = 1000, 840, 1992
+            A, B = bf(M, K), bf(N, K)
+            out = torch.randn(M, N, device=dev)
+            ops.gemm(A, B, M, N, K, out, mode=L.EPI_F32, accumulate=True)
+            outs = [out]
+        torch.cuda.synchronize()
+        return [o.float().clone() for o in outs], L.load().mtp_gemm_last_config()
+    try:
+        ref, cfg1 = run(1)
+        got, cfg2 = run(2)
+    finally:
+        L.call("mtp_gemm_set_variant", 1)
+    assert cfg1 < 3000 <= cfg2, (cfg1, cfg2)
+    for a, b in zip(got, ref):
+        assert torch.isfinite(a).all()
+        err = float((a - b).norm() / b.norm().clamp_min(1e-20))
+        assert err < 1e-5, err          # same k order per tile: identical up to the atomics of the column sums / sumsq
