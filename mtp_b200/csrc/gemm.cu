@@ -1017,7 +1017,7 @@ static int g_gemm_variant = -1;      // 1: persistent kernel, 2: one tile per CT
 static int gemm_variant() {
   if (g_gemm_variant < 0) {
     const char* e = getenv("MTP_GEMM_VARIANT");
-    g_gemm_variant = (e != nullptr && e[0] == '2') ? 2 : 1;
+    g_gemm_variant = (e != nullptr && (e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 1;
   }
   return g_gemm_variant;
 }
@@ -1097,7 +1097,9 @@ static int run_grouped(const HostProblem* pr, int np, int force_bn, cudaStream_t
     if (rc) return rc;
     MTP_REQUIRE(!pr[p].ep.hilo || np == 1, "mtp_gemm_bf16_dual: hilo mode is not available in grouped launches");
   }
-  if (gemm_variant() == 2 && force_bn < 1000 && !pr[0].ep.hilo && (force_bn == 0 || force_bn >= 128)) {
+  // variant 3: the co-resident kernel for single launches only (measured r2: single forward launches 0.4-3.4 us faster, the grouped
+  // dgrad+wgrad launches 9-12 us slower than with the persistent kernel's LPT schedule)
+  if ((gemm_variant() == 2 || (gemm_variant() == 3 && np == 1)) && force_bn < 1000 && !pr[0].ep.hilo && (force_bn == 0 || force_bn >= 128)) {
     const int bn = gemm2_pick_bn(pr, np, force_bn);
     g_last_config = 3000 + bn;
     switch (bn) {
@@ -1207,7 +1209,7 @@ extern "C" int mtp_gemm_last_config(void) { return g_last_config; }
 /* 1: persistent warp-specialised kernel (default); 2: one tile per CTA, two CTAs per SM (co-residency hides the SM turnaround between
  * dependent launches).  mtp_gemm_last_config() reports 3000 + BN for variant 2. */
 extern "C" int mtp_gemm_set_variant(int v) {
-  g_gemm_variant = v == 2 ? 2 : 1;
+  g_gemm_variant = (v == 2 || v == 3) ? v : 1;
   return MTP_OK;
 }
 /* tuning aid: cap the depth of the operand ring (0 = fill the smem budget).  A shallow ring leaves room for the next launch's CTA on the
