@@ -66,3 +66,13 @@ class FlatLayout:
         if hi_blocks < self.total:
             out.append((hi_blocks, self.total))
         return out
+
+    def split_tail(self, depth: int, bucket_blocks: int):
+        """(pyramid-weight ranges, the rest of the tail): the ConvTranspose2d weights lie behind the last block in the flat buffer and are
+        final as soon as the pyramid tail has been differentiated (first, in the data-parallel trainer); the small accumulated region and
+        the patch-embed weight are final only at the end of the backward."""
+        tail = self.tail_ranges(depth, bucket_blocks)
+        first_block = self.offsets["blocks.0.attn.qkv.weight"]
+        fpn = [r for r in tail if r[0] >= self.small_end and r[0] > first_block]
+        rest = [r for r in tail if r not in fpn]
+        return fpn, rest

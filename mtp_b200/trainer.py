@@ -235,9 +235,7 @@ class PretrainStep:
             L.call("mtp_optim_step_begin", self.state.data_ptr(), ops._stream())
         if self.comm_sms:
             L.call("mtp_set_sm_limit", max(8, L.load().mtp_num_sms() - self.comm_sms))
-        tail = self.layout.tail_ranges(len(m.blocks), self.bucket_blocks) if self.world > 1 else []
-        fpn_ranges = [r for r in tail if r[0] >= self.small_end and r[0] > self.offsets.get("blocks.0.attn.qkv.weight", 0)]
-        rest = [r for r in tail if r not in fpn_ranges]
+        fpn_ranges, rest = self.layout.split_tail(len(m.blocks), self.bucket_blocks) if self.world > 1 else ([], [])
 
         def emit(ranges):
             for lo, hi in ranges:

@@ -77,3 +77,41 @@ def test_bucketed_allreduce_gloo_world2():
         assert p.exitcode == 0
     want = torch.arange(lay.total, dtype=torch.float32) * 1.5       # mean of rank-scaled buffers
     assert torch.equal(got, want)
+
+
+def test_pyramid_first_ordering_covers_the_flat_buffer_once():
+    """Data-parallel reduction order: pyramid weights first, block buckets in backward order, small region + patch embed last -- every
+    element of the flat gradient buffer is reduced exactly once."""
+    import torch
+    from mtp_b200 import ViT_Win_RVSA_V3_WSZ7
+    from mtp_b200.flat import FlatLayout
+    m = ViT_Win_RVSA_V3_WSZ7(img_size=160, embed_dim=128, depth=6, num_heads=2, interval=3, out_indices=[1, 2, 3, 5], use_abs_pos_emb=True,
+                             qkv_bias=True, use_rel_pos_bias=True)
+    lay = FlatLayout([(n, tuple(p.shape)) for n, p in m.named_parameters()])
+    for bb in (1, 2, 4):
+        fpn, rest = lay.split_tail(6, bb)
+        buckets = list(lay.block_buckets(6, bb).values())
+        seen = torch.zeros(lay.total, dtype=torch.int32)
+        for lo, hi in fpn + buckets + rest:
+            seen[lo:hi] += 1
+        assert int(seen.min()) == 1 and int(seen.max()) == 1
+        names = [n for n in lay.order if any(lo <= lay.offsets[n] < hi for lo, hi in fpn)]
+        assert names and all(n.startswith("fpn") and n.endswith(".weight") for n in names), names
+        assert (0, lay.small_end) in rest
+
+
+def test_image_preprocess_reference_and_stream_split():
+    import torch
+    import bench
+    from mtp_b200.preprocess import ImagePreprocess
+    x = torch.randint(0, 256, (2, 3, 4, 5), dtype=torch.uint8)
+    pre = ImagePreprocess()
+    want = (x[:, [2, 1, 0]].float() - torch.tensor(pre.mean).view(1, 3, 1, 1)) / torch.tensor(pre.std).view(1, 3, 1, 1)
+    assert torch.equal(pre.reference(x), want)
+    hwc = ImagePreprocess(layout="hwc", bgr_to_rgb=False)
+    assert torch.equal(hwc.reference(x.permute(0, 2, 3, 1).contiguous()),
+                       (x.float() - torch.tensor(pre.mean).view(1, 3, 1, 1)) / torch.tensor(pre.std).view(1, 3, 1, 1))
+    assert bench.split3(8) == (3, 3, 2) and bench.split3(32) == (11, 11, 10) and bench.split3(2) is None and sum(bench.split3(4)) == 4
+    import pytest
+    with pytest.raises(ValueError):
+        ImagePreprocess(bgr_to_rgb=True, rgb_to_bgr=True)
