@@ -514,9 +514,6 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      // bias visible; also keeps the 8 warps on the same item
-      mbar_wait(&tmem_full[acc], acc_phase);
-      if (it == n_items - 1 && threadIdx.x == 64) MTP_STAMP(5);
-      tc_fence_after();
       int pm[4];
       bool pok[4];
 #pragma unroll
@@ -525,14 +522,21 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         pok[p] = pm[p] < M && sched.dbg_mode != 3;      // dbg 3: no epilogue stores (isolates the store drain at kernel end)
       }
       const bool f32 = mode_is_f32(ep.mode);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const int n_chunks = sched.dbg_mode == 6 ? 0 : (min(BN, N - n0) + 31) / 32;      // dbg 6: accumulators are never read out
-      uint32_t r[32];
+      // The aux operand (residual / GELU' pre-activation / accumulate target: global memory, ~1 us away) is requested early: the first
+      // chunk's before the accumulator is complete, each following one as soon as its registers are free (a full double buffer spills: the
+      // kernel sits at the 168-register cap of 10 warps).  Measured r2: the GELU' epilogue of the fc2 dgrad cost 8.5 us per 128 x 256 tile
+      // (1.7 us for the GELU of fc1) because every chunk waited for its own aux loads.
+      AuxRegs aux_cur;
       int c = hsel;
+      if (c < n_chunks) load_aux(ep, aux_cur, pm, pok, n0 + c * 32, N, lane);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      if (it == n_items - 1 && threadIdx.x == 64) MTP_STAMP(5);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      uint32_t r[32];
       if (c < n_chunks) tmem_ld_32x32(taddr + c * 32, r);
       for (; c < n_chunks; c += 2) {
-        AuxRegs aux;
-        load_aux(ep, aux, pm, pok, n0 + c * 32, N, lane);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -541,7 +545,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         float t[4][8];
         if (f32) lane_transpose<true>(v, t, lane);
         else lane_transpose<false>(v, t, lane);
-        epilogue_pieces<HILO>(ep, t, aux, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, item_ < items0 ? sq0 : sq1);
+        epilogue_pieces<HILO>(ep, t, aux_cur, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, item_ < items0 ? sq0 : sq1);
+        // the next chunk's aux operand goes into the registers just consumed; its latency overlaps the next TMEM wait and lane transpose
+        if (c + 2 < n_chunks) load_aux(ep, aux_cur, pm, pok, n0 + (c + 2) * 32, N, lane);
       }
       tc_fence_before();
       __syncwarp();
