@@ -26,7 +26,10 @@ def main(folder):
           f"legacy tensor pipe % (`sm__pipe_tensor_cycles_active_realtime`: does not count UTCHMMA) | TMEM ld/st issue % | achieved occupancy % | L2 hit % |")
     print("|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
     for path in sorted(glob.glob(os.path.join(folder, "*_raw.csv"))):
-        d = load(path)
+        try:
+            d = load(path)
+        except (IndexError, OSError):
+            continue          # empty export: the capture's kernel filter matched nothing
         name = d.get("Kernel Name", ("?", ""))[0].split("(")[0].replace("void ", "").replace("mtp::", "")
         dur_ns = num(d, "gpu__time_duration.sum")
         scale = {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(d.get("gpu__time_duration.sum", ("", "ns"))[1], 1.0)
