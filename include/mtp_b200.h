@@ -280,6 +280,11 @@ int mtp_empty_launch(mtp_stream_t stream);
 int mtp_gemm_set_variant(int v);
 /* measurement aid (tools/turnaround_probe.py): do-nothing kernel with a configurable footprint; stamps[grid][4] = entry, ready, done (globaltimer ns) */
 int mtp_probe_launch(long long* stamps, int grid, int threads, int smem_bytes, int tmem_cols, int spin_ns, int pdl_early, mtp_stream_t stream);
+/* same, plus end-of-kernel work: n_loads x 512 B global reads and n_tmem_ld accumulator reads per warp, then store_bytes per CTA written to buf
+   as a 128-row tile of a matrix with row pitch ldo bytes (pattern 0: 512 contiguous bytes per warp instruction, 1: 8 rows x 64 B, 2: 32 rows x 16 B,
+   3: 2 rows x 256 B) */
+int mtp_probe_launch2(long long* stamps, int grid, int threads, int smem_bytes, int tmem_cols, int spin_ns, int pdl_early, void* buf,
+                      int store_bytes, int store_pattern, int ldo, int n_tmem_ld, int n_loads, mtp_stream_t stream);
 /* tuning aid: cap the depth of the GEMM operand ring (0 = as deep as the shared-memory budget allows) */
 int mtp_gemm_set_max_stages(int n);
 

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "mtp_tok_to_nchw_hilo": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_empty_launch": [c_void_p],
     "mtp_probe_launch": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "mtp_probe_launch2": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "mtp_optim_step_begin": [c_void_p, c_void_p],
     "mtp_sumsq_f32": [c_void_p, c_size_t, c_void_p, c_void_p],
     "mtp_sumsq_bf16": [c_void_p, c_size_t, c_void_p, c_void_p],
