@@ -238,6 +238,224 @@ __device__ __forceinline__ void epilogue_pieces(const EpiParams& ep, float (&t)[
   }
 }
 
+// ---- specialised epilogue of one tile -----------------------------------------------------------------------------------------
+// Same piece layout as above, for the modes that make up the training step (bf16 / GELU / GELU' / fp32 / fp32 + residual; N a multiple of
+// 32).  The generic code resolves the mode, the piece addresses (64-bit multiplies), the DropPath row scale (an integer division) and the
+// bounds for every piece of every chunk: ncu's source view shows ~600 warp instructions per 32 x 32 chunk without the GELU math, two
+// thirds of them IMAD / ISETP / MOV / LDC, and with two epilogue warps per scheduler the tile's epilogue is issue-bound (1.3 us per pair of
+// chunk columns; the last tile's epilogue is the exposed tail of every launch, tools/gemm_gaps.py).  Here everything that does not depend
+// on the chunk is resolved once per tile and the mode is a template parameter.
+__device__ __forceinline__ long long gtime();
+
+// 16 bytes of the aux operand for each of the lane's four pieces (same byte offset from the piece's output address)
+__device__ __forceinline__ void load_aux4(float4 (&a)[4], char* const (&o)[4], const bool (&ok)[4], ptrdiff_t d) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+    if (ok[p]) a[p] = *reinterpret_cast<const float4*>(o[p] + d);
+}
+
+// bf16 outputs: plain / GELU (+ pre-activation copy) / GELU' (times the saved pre-activation)
+// (row0 = first row of this warp's TMEM lane quarter; rows >= m_end are not stored)
+template <int MODE>
+__device__ __forceinline__ void epilogue_tile_bf16(const EpiParams* epp, uint32_t taddr, int n_chunks, int hsel, int row0, int m_end, int n0,
+                                                const float* bsm, uint64_t* acc_bar, uint32_t acc_phase, long long* stamp) {
+  const EpiParams& ep = *epp;
+  const int lane = threadIdx.x & 31;
+  int m[4];
+  bool ok[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    m[p] = row0 + piece_row(lane, p);
+    ok[p] = m[p] < m_end;
+  }
+  const int i = lane & 3;
+  char* const out = reinterpret_cast<char*>(ep.out);
+  char* o[4];                                                          // this lane's first element of piece p in chunk 0
+#pragma unroll
+  for (int p = 0; p < 4; ++p) o[p] = out + ((size_t)m[p] * ep.ldo + n0 + i * 8) * 2;
+  // the GELU' pre-activation and the GELU pre-activation copy have the output's shape and pitch
+  const ptrdiff_t aux_d = MODE == MTP_EPI_BF16_DGELU ? reinterpret_cast<const char*>(ep.aux) - out : 0;
+  const bool has_out2 = MODE == MTP_EPI_BF16_GELU && ep.out2 != nullptr;
+  const ptrdiff_t out2_d = has_out2 ? reinterpret_cast<char*>(ep.out2) - out : 0;
+  float* const colsum = ep.colsum;
+  float4 aux[4];
+  int c = hsel;
+  if (MODE == MTP_EPI_BF16_DGELU && c < n_chunks) load_aux4(aux, o, ok, aux_d + c * 64);      // requested before the accumulator is complete
+  mbar_wait(acc_bar, acc_phase);
+  if (stamp != nullptr) *stamp = gtime();
+  tc_fence_after();
+  uint32_t r[32];
+  if (c < n_chunks) tmem_ld_32x32(taddr + c * 32, r);
+  for (; c < n_chunks; c += 2) {
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (c + 2 < n_chunks) tmem_ld_32x32(taddr + (c + 2) * 32, r);      // next chunk streams in while this one is processed
+    float t[4][8];
+    lane_transpose<false>(v, t, lane);
+    if (bsm != nullptr) {                                              // smem
+      const float* bs = bsm + c * 32 + i * 8;
+      float b[8];
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(bs);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(bs + 4);
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[p][k] += b[k];
+    }
+    const int cb = c * 64;
+    float cs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (!ok[p]) continue;
+      if (MODE == MTP_EPI_BF16_GELU) {
+        if (has_out2) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(o[p] + out2_d + cb), t[p]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[p][k] = gelu_erf(t[p][k]);
+      } else if (MODE == MTP_EPI_BF16_DGELU) {
+        const float4 hv = aux[p];
+        const uint32_t w[4] = {__float_as_uint(hv.x), __float_as_uint(hv.y), __float_as_uint(hv.z), __float_as_uint(hv.w)};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w[q]);
+          t[p][2 * q] *= gelu_erf_grad(f.x);
+          t[p][2 * q + 1] *= gelu_erf_grad(f.y);
+        }
+      }
+      store_bf16x8(reinterpret_cast<__nv_bfloat16*>(o[p] + cb), t[p]);
+      if (colsum != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cs[k] += __bfloat162float(__float2bfloat16_rn(t[p][k]));      // sums of the STORED values
+      }
+    }
+    if (MODE == MTP_EPI_BF16_DGELU && c + 2 < n_chunks) load_aux4(aux, o, ok, aux_d + (c + 2) * 64);      // into the registers just consumed
+    if (colsum != nullptr) {       // column sums over the warp's 32 rows: the 8 lane groups hold the same columns
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 4);
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+      }
+      if (lane < 4) {
+        float* dst = colsum + n0 + c * 32 + i * 8;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
+      }
+    }
+  }
+}
+
+// 4 rows x 4 column blocks of 4 fp32 values: after the exchange the lane holds block (lane & 3) of the group's four rows (piece_row order)
+__device__ __forceinline__ void lane_transpose16(const float (&v)[16], float (&t)[4][4], int lane) {
+  const bool b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float x0 = v[k], x1 = v[4 + k], x2 = v[8 + k], x3 = v[12 + k];
+    const float keep_lo = b1 ? x2 : x0, keep_hi = b1 ? x3 : x1;
+    const float recv_lo = __shfl_xor_sync(0xffffffffu, b1 ? x0 : x2, 2);
+    const float recv_hi = __shfl_xor_sync(0xffffffffu, b1 ? x1 : x3, 2);
+    t[0][k] = b0 ? keep_hi : keep_lo;
+    t[1][k] = b0 ? recv_hi : recv_lo;
+    t[2][k] = __shfl_xor_sync(0xffffffffu, b0 ? keep_lo : keep_hi, 1);
+    t[3][k] = __shfl_xor_sync(0xffffffffu, b0 ? recv_lo : recv_hi, 1);
+  }
+}
+
+// fp32 outputs (weight gradients; the residual stream): units of 16 columns -- the four lanes of a group write 64 contiguous bytes of a
+// row -- so that the aux operand (residual / accumulate target) can be double-buffered in registers: unit j+1's is requested before
+// unit j's arithmetic (32 aux + 32 transposed + 32 prefetched accumulator registers per 32-column chunk did not fit beside the rest).
+template <bool RESID, bool ADD>
+__device__ __forceinline__ float epilogue_tile_f32(const EpiParams* epp, uint32_t taddr, int n_chunks, int hsel, int row0, int m_end, int n0,
+                                                const float* bsm, uint64_t* acc_bar, uint32_t acc_phase, long long* stamp) {
+  const EpiParams& ep = *epp;
+  const int lane = threadIdx.x & 31;
+  int m[4];
+  bool ok[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    m[p] = row0 + piece_row(lane, p);
+    ok[p] = m[p] < m_end;
+  }
+  float sq = 0.f;      // sum of squares of the values this thread stored
+  const int i = lane & 3;
+  char* const out = reinterpret_cast<char*>(ep.out);
+  char* o[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) o[p] = out + ((size_t)m[p] * ep.ldo + n0 + i * 4) * 4;
+  const ptrdiff_t aux_d = RESID ? reinterpret_cast<const char*>(ep.aux) - out : 0;      // accumulate: the output itself
+  float rs[4] = {1.f, 1.f, 1.f, 1.f};                                  // DropPath scale of each piece's row
+  if (RESID && ep.row_scale != nullptr) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if (ok[p]) rs[p] = __ldg(ep.row_scale + m[p] / ep.rows_per_group);
+  }
+  const bool want_sq = ep.sumsq != nullptr;
+  const int n_units = hsel < n_chunks ? 2 * ((n_chunks - hsel + 1) / 2) : 0;      // this warp's chunks hsel, hsel + 2, ...: two units each
+#define MTP_UNIT_COL(j) ((hsel + 2 * ((j) >> 1)) * 32 + ((j) & 1) * 16)
+  float4 auxa[4], auxb[4];
+  if (ADD && n_units > 0) {                  // requested before the accumulator is complete
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if (ok[p]) auxa[p] = *reinterpret_cast<const float4*>(o[p] + aux_d + MTP_UNIT_COL(0) * 4);
+  }
+  mbar_wait(acc_bar, acc_phase);
+  if (stamp != nullptr) *stamp = gtime();
+  tc_fence_after();
+  uint32_t r[16];
+  if (n_units > 0) tmem_ld_32x16(taddr + MTP_UNIT_COL(0), r);
+  // one unit = 16 columns of the lane quarter's 32 rows: wait for its accumulators (already requested into r), request the next unit's
+  // accumulators and aux operand, then bias / row scale / + aux / store.  (A macro, not a function taking the two aux buffers by reference:
+  // that left both buffers in local memory.)
+#ifndef MTP_AUX_DOUBLE
+#define MTP_AUX_DOUBLE 1
+#endif
+#define MTP_F32_UNIT(ACUR, ANEXT, HAS_NEXT, NEXT_COL, COL)                                                          \
+  {                                                                                                               \
+    tmem_ld_wait();                                                                                               \
+    float v[16];                                                                                                  \
+    _Pragma("unroll") for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(r[q]);                                  \
+    if (HAS_NEXT) tmem_ld_32x16(taddr + (NEXT_COL), r);                                                           \
+    if (MTP_AUX_DOUBLE && ADD && (HAS_NEXT)) {                                                                    \
+      _Pragma("unroll") for (int p = 0; p < 4; ++p)                                                               \
+        if (ok[p]) ANEXT[p] = *reinterpret_cast<const float4*>(o[p] + aux_d + (NEXT_COL) * 4);                    \
+    }                                                                                                             \
+    float t[4][4];                                                                                                \
+    lane_transpose16(v, t, lane);                                                                                 \
+    if (bsm != nullptr) {                                                                                         \
+      const float4 b = *reinterpret_cast<const float4*>(bsm + (COL) + i * 4);                                     \
+      _Pragma("unroll") for (int p = 0; p < 4; ++p) { t[p][0] += b.x; t[p][1] += b.y; t[p][2] += b.z; t[p][3] += b.w; } \
+    }                                                                                                             \
+    _Pragma("unroll") for (int p = 0; p < 4; ++p) {                                                               \
+      if (!ok[p]) continue;                                                                                       \
+      float4 x = make_float4(rs[p] * t[p][0], rs[p] * t[p][1], rs[p] * t[p][2], rs[p] * t[p][3]);                \
+      if (ADD) { x.x += ACUR[p].x; x.y += ACUR[p].y; x.z += ACUR[p].z; x.w += ACUR[p].w; }                        \
+      *reinterpret_cast<float4*>(o[p] + (COL) * 4) = x;                                                           \
+      if (want_sq) sq += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;                                           \
+    }                                                                                                             \
+    if (!MTP_AUX_DOUBLE && ADD && (HAS_NEXT)) {                                                                   \
+      _Pragma("unroll") for (int p = 0; p < 4; ++p)                                                               \
+        if (ok[p]) ANEXT[p] = *reinterpret_cast<const float4*>(o[p] + aux_d + (NEXT_COL) * 4);                    \
+    }                                                                                                             \
+  }
+  for (int j = 0; j < n_units; j += 2) {      // n_units is even
+    const int col0 = MTP_UNIT_COL(j);
+    const bool more = j + 2 < n_units;
+#if MTP_AUX_DOUBLE
+    MTP_F32_UNIT(auxa, auxb, true, col0 + 16, col0)
+    MTP_F32_UNIT(auxb, auxa, more, col0 + 64, col0 + 16)
+#else
+    MTP_F32_UNIT(auxa, auxa, true, col0 + 16, col0)
+    MTP_F32_UNIT(auxa, auxa, more, col0 + 64, col0 + 16)
+#endif
+  }
+#undef MTP_F32_UNIT
+#undef MTP_UNIT_COL
+  return sq;
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // Grouped persistent kernel: up to two independent GEMM problems (e.g. the dgrad and the wgrad of one Linear) share one
 // launch.  Work items (tiles, or 256-row tile pairs in CL2 mode) of both problems are assigned to the CTAs by a
@@ -277,7 +495,10 @@ __device__ __forceinline__ long long gtime() {
 #ifndef MTP_GEMM_MINBLOCKS
 #define MTP_GEMM_MINBLOCKS 1      // 2: cap registers so that two CTAs (this launch's and the next one's) fit one SM -- co-residency experiments
 #endif
-template <int BN, bool CL2, bool HILO>
+// ESET: which epilogue code the kernel carries.  0 = the generic epilogue (every mode, any N);  1 = GELU, 2 = fp32 + residual,
+// 3 = bf16 | fp32 (a dgrad and / or a wgrad), 4 = GELU' | fp32 -- the specialised per-tile epilogues above, N a multiple of 32, picked by
+// the host per launch (pick_eset).  (All variants inside one kernel made ptxas spill inside the chunk loops: 168 registers.)
+template <int BN, bool CL2, bool HILO, int ESET>
 __global__ void __launch_bounds__(GEMM_THREADS, MTP_GEMM_MINBLOCKS)
 gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__ GemmProblem p1, const __grid_constant__ Sched sched) {
   using Cfg = GemmCfg<BN, CL2>;
@@ -357,7 +578,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       // B tiles of the first item's first k-blocks that are independent of the stream predecessor (ep.b_static: weights, saved
       // activations) are requested BEFORE the dependency wait, so their HBM latency overlaps the predecessor's tail
       int pre = 0;
-      if (n_items > 0 && sched.dbg_mode == 0) {
+      if (n_items > 0 && (sched.dbg_mode == 0 || sched.dbg_mode == 30)) {
         MTP_DECODE_ITEM(0)
         if (P.ep.b_static) {
           pre = min(STAGES, k_blocks);
@@ -527,13 +748,29 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
       // chunk's before the accumulator is complete, each following one as soon as its registers are free (a full double buffer spills: the
       // kernel sits at the 168-register cap of 10 warps).  Measured r2: the GELU' epilogue of the fc2 dgrad cost 8.5 us per 128 x 256 tile
       // (1.7 us for the GELU of fc1) because every chunk waited for its own aux loads.
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      float& sq_item = item_ < items0 ? sq0 : sq1;
+      const int emode = ep.mode;
+      if constexpr (ESET != 0) {
+        const float* bsf = ep.bias != nullptr ? bsm : nullptr;
+        long long* stamp5 = (sched.dbg != nullptr && it == n_items - 1 && threadIdx.x == 64) ? sched.dbg + blockIdx.x * 8 + 5 : nullptr;
+        const int row0 = m0 + q * 32, m_end = sched.dbg_mode == 3 ? 0 : M;
+        const EpiParams* epp = &P.ep;
+        if constexpr (ESET == 1) {
+          epilogue_tile_bf16<MTP_EPI_BF16_GELU>(epp, taddr, n_chunks, hsel, row0, m_end, n0, bsf, &tmem_full[acc], acc_phase, stamp5);
+        } else if constexpr (ESET == 2) {
+          sq_item += epilogue_tile_f32<true, true>(epp, taddr, n_chunks, hsel, row0, m_end, n0, bsf, &tmem_full[acc], acc_phase, stamp5);
+        } else {
+          if (emode == MTP_EPI_F32) sq_item += epilogue_tile_f32<false, false>(epp, taddr, n_chunks, hsel, row0, m_end, n0, bsf, &tmem_full[acc], acc_phase, stamp5);
+          else epilogue_tile_bf16<ESET == 3 ? MTP_EPI_BF16 : MTP_EPI_BF16_DGELU>(epp, taddr, n_chunks, hsel, row0, m_end, n0, bsf, &tmem_full[acc], acc_phase, stamp5);
+        }
+      } else {
       AuxRegs aux_cur;
       int c = hsel;
       if (c < n_chunks) load_aux(ep, aux_cur, pm, pok, n0 + c * 32, N, lane);
       mbar_wait(&tmem_full[acc], acc_phase);
       if (it == n_items - 1 && threadIdx.x == 64) MTP_STAMP(5);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       uint32_t r[32];
       if (c < n_chunks) tmem_ld_32x32(taddr + c * 32, r);
       for (; c < n_chunks; c += 2) {
@@ -545,9 +782,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
         float t[4][8];
         if (f32) lane_transpose<true>(v, t, lane);
         else lane_transpose<false>(v, t, lane);
-        epilogue_pieces<HILO>(ep, t, aux_cur, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, item_ < items0 ? sq0 : sq1);
+        epilogue_pieces<HILO>(ep, t, aux_cur, ep.bias != nullptr ? bsm + c * 32 : nullptr, pm, pok, n0 + c * 32, N, lane, sq_item);
         // the next chunk's aux operand goes into the registers just consumed; its latency overlaps the next TMEM wait and lane transpose
         if (c + 2 < n_chunks) load_aux(ep, aux_cur, pm, pok, n0 + (c + 2) * 32, N, lane);
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -575,10 +813,14 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
   __syncthreads();
   if (threadIdx.x == 0) MTP_STAMP(6);
   if (CL2) cluster_sync_all();       // no CTA leaves while its peer may still signal its barriers
-  if (warp == 1) {
-    tc_fence_after();
+  // dbg 20..22 (tools/gemm_gaps.py): where the teardown time goes -- extra stamps / dealloc from the producer warp / no fence
+  if (warp == (sched.dbg_mode == 21 ? 0 : 1)) {
+    if (sched.dbg_mode == 20 && lane == 0) MTP_STAMP(2);
+    if (sched.dbg_mode != 22) tc_fence_after();
+    if (sched.dbg_mode == 20 && lane == 0) MTP_STAMP(3);
     if (CL2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
     else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (lane == 0) MTP_STAMP(7);
   }
 }
 
@@ -911,10 +1153,41 @@ static long long* g_gemm_dbg = nullptr;
 static int g_gemm_dbg_mode = 0;
 static int g_gemm_max_stages = 0;      // 0 = as many as fit the smem budget
 
-template <int BN, bool CL2, bool HILO = false>
+// Which specialised epilogue set covers this launch (gemm_bf16_kernel's ESET); 0 = none, use the generic epilogue.
+static int pick_eset(const HostProblem* pr, int np) {
+  if (g_gemm_dbg_mode == 30) return 0;      // tuning aid: the generic epilogue everywhere (A/B)
+  bool gelu = false, resid = false, dgelu = false, plain = false;
+  for (int p = 0; p < np; ++p) {
+    const mtp::EpiParams& ep = pr[p].ep;
+    if (ep.hilo || (pr[p].N & 31) != 0) return 0;
+    switch (ep.mode) {
+      case MTP_EPI_BF16: plain = true; break;
+      case MTP_EPI_BF16_GELU: gelu = true; break;
+      case MTP_EPI_BF16_DGELU: dgelu = true; break;
+      case MTP_EPI_F32_RESID: resid = true; break;
+      case MTP_EPI_F32: if (ep.accumulate) return 0; break;
+      default: return 0;
+    }
+  }
+  if (gelu) return (np == 1) ? 1 : 0;
+  if (resid) return (np == 1) ? 2 : 0;
+  if (dgelu) return plain ? 0 : 4;
+  return 3;
+}
+
+template <int BN, bool CL2, bool HILO = false, int ESET = 0>
 static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, cudaStream_t stream) {
   if constexpr (!HILO && !CL2) {          // the fp32-class (hi | lo, three-pass) instantiation exists for single CTAs only
     if (pr[0].ep.hilo) return launch_grouped<BN, CL2, true>(pr, np, sched_in, stream);
+  }
+  if constexpr (!HILO && ESET == 0) {
+    switch (pick_eset(pr, np)) {
+      case 1: return launch_grouped<BN, CL2, false, 1>(pr, np, sched_in, stream);
+      case 2: return launch_grouped<BN, CL2, false, 2>(pr, np, sched_in, stream);
+      case 3: return launch_grouped<BN, CL2, false, 3>(pr, np, sched_in, stream);
+      case 4: return launch_grouped<BN, CL2, false, 4>(pr, np, sched_in, stream);
+      default: break;
+    }
   }
   Sched sched = sched_in;
   sched.dbg = g_gemm_dbg;
@@ -940,7 +1213,7 @@ static int launch_grouped(const HostProblem* pr, int np, const Sched& sched_in, 
   int dev_ = 0;
   cudaGetDevice(&dev_);
   bool& attr_set = attr_set_dev[dev_ & 63];
-  auto kern = gemm_bf16_kernel<BN, CL2, HILO>;
+  auto kern = gemm_bf16_kernel<BN, CL2, HILO, ESET>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

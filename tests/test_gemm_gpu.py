@@ -278,3 +278,56 @@ def test_gemm_variant2_matches_persistent_kernel(case):
         assert torch.isfinite(a).all()
         err = float((a - b).norm() / b.norm().clamp_min(1e-20))
         assert err < 1e-5, err          # same k order per tile: identical up to the atomics of the column sums / sumsq
+
+
+@pytest.mark.parametrize("bn", [0, 64, 192, 256, 1128, 1256])
+def test_specialised_epilogues_match_generic(bn):
+    """The per-mode tile epilogues (kernel template parameter ESET, picked per launch) against the generic epilogue (debug mode 30):
+    bit-identical outputs for every mode they cover, single and grouped launches, ragged M and a tile-ragged N."""
+    from mtp_b200 import ops, _lib as L
+    M, N, K = 1568, 1120, 264          # 12.25 row tiles; N = 35 chunks of 32 columns: the last tile of every width is partial
+    A, Bm = _mk((M, K), seed=51), _mk((K, N), 0.1, seed=52)
+    h = _mk((M, N), seed=53)
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    keep = torch.tensor([0.0, 1.25, 1.0, 2.0], device="cuda")
+    X, G = _mk((M, 512), seed=54), _mk((M, N), seed=55)
+
+    def run(generic):
+        L.call("mtp_gemm_set_debug_mode", 30 if generic else 0)
+        res = []
+        try:
+            o = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16); cs = torch.zeros(N, device="cuda")
+            ops.gemm(A, Bm, M, N, K, o, b_mn=True, bias=bias, colsum=cs, force_bn=bn); res += [o, cs]
+            o = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16); pre = torch.zeros_like(o)
+            ops.gemm(A, Bm, M, N, K, o, b_mn=True, mode=L.EPI_BF16_GELU, bias=bias, out2=pre, force_bn=bn); res += [o, pre]
+            o = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16); cs = torch.zeros(N, device="cuda")
+            ops.gemm(A, Bm, M, N, K, o, b_mn=True, mode=L.EPI_BF16_DGELU, aux=h, colsum=cs, force_bn=bn); res += [o, cs]
+            o = torch.zeros(M, N, device="cuda"); sq = torch.zeros(1, device="cuda")
+            ops.gemm(A, Bm, M, N, K, o, b_mn=True, mode=L.EPI_F32, sumsq=sq, force_bn=bn); res += [o, sq]
+            o = torch.zeros(M, N, device="cuda")
+            ops.gemm(A, Bm, M, N, K, o, b_mn=True, mode=L.EPI_F32_RESID, bias=bias, aux=resid, row_scale=keep, rows_per_group=392, force_bn=bn); res += [o]
+            r2 = resid.clone()                   # in place on the residual stream
+            ops.gemm(A, Bm, M, N, K, r2, b_mn=True, mode=L.EPI_F32_RESID, aux=r2, force_bn=bn); res += [r2]
+            # grouped: a dgrad-like bf16 (or GELU') problem + a wgrad-like fp32 problem with the gradient-norm partial sum
+            for mode, aux in ((L.EPI_BF16, None), (L.EPI_BF16_DGELU, _mk((M, 512), seed=56))):
+                dx = torch.zeros(M, 512, device="cuda", dtype=torch.bfloat16); dW = torch.zeros(N, 512, device="cuda")
+                cs = torch.zeros(512, device="cuda"); sq = torch.zeros(1, device="cuda")
+                W = _mk((N, 512), 0.1, seed=57)
+                ops.gemm_dual(dict(A=G, B=W, M=M, N=512, K=N, out=dx, b_mn=True, mode=mode, aux=aux, colsum=cs),
+                              dict(A=G, B=X, M=N, N=512, K=M, out=dW, a_mn=True, b_mn=True, mode=L.EPI_F32, sumsq=sq), force_bn=bn)
+                res += [dx, dW, cs, sq]
+            torch.cuda.synchronize()
+        finally:
+            L.call("mtp_gemm_set_debug_mode", 0)
+        return res
+
+    fast, gen = run(False), run(True)
+    assert len(fast) == len(gen)
+    for i, (a, b) in enumerate(zip(fast, gen)):
+        if a.numel() == 1 or (a.dim() == 1 and a.dtype == torch.float32):      # atomically accumulated sums: order differs
+            assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item()), (bn, i)
+        else:
+            assert torch.equal(a, b), (bn, i, (a.float() - b.float()).abs().max().item())
+    ref = A.float() @ Bm.float() + bias
+    assert ((fast[0].float() - ref).abs() <= 8e-3 * ref.abs() + 1e-2).all()
