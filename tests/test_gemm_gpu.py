@@ -327,6 +327,8 @@ def test_specialised_epilogues_match_generic(bn):
     for i, (a, b) in enumerate(zip(fast, gen)):
         if a.numel() == 1 or (a.dim() == 1 and a.dtype == torch.float32):      # atomically accumulated sums: order differs
             assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item()), (bn, i)
+        elif a.dtype == torch.float32:       # scale * acc + residual may or may not be contracted into an FMA: one fp32 ulp
+            assert (a - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item()), (bn, i)
         else:
             assert torch.equal(a, b), (bn, i, (a.float() - b.float()).abs().max().item())
     ref = A.float() @ Bm.float() + bias
