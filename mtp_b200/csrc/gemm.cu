@@ -487,7 +487,9 @@ struct Sched {
 
 __device__ __forceinline__ long long gtime() {
   long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  // "memory": without it the read may be scheduled ahead of a preceding bar.sync (the end-of-CTA stamp then records when the FIRST warp
+  // reached the final barrier, which read as a 5 us "turnaround" after the CTA's end for a long time)
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
   return t;
 }
 #define MTP_STAMP(i) do { if (sched.dbg) sched.dbg[blockIdx.x * 8 + (i)] = gtime(); } while (0)

@@ -44,12 +44,12 @@ for name, M, N, K, bn in [("qkv fwd 192", 1568, 3072, 1024, 192), ("qkv fwd 128"
     prev_end = None
     for i in range(NL):
         di = d[i][d[i][:, 0] > 0]
-        s, e = int(di[:, 0].min()), int(di[:, 6].max())
+        s, e = int(di[:, 0].min()), int(torch.maximum(di[:, 6], di[:, 7]).max())      # end of a CTA = its TMEM dealloc returned (stamp 7)
         smax = int(di[:, 0].max())
-        msg = f"   launch {i}: span {(e - s) / 1e3:5.1f} us, CTA starts spread {(smax - s) / 1e3:4.1f} us, first CTA end {(int(di[:, 6].min()) - s) / 1e3:5.1f}"
+        msg = f"   launch {i}: span {(e - s) / 1e3:5.1f} us, CTA starts spread {(smax - s) / 1e3:4.1f} us, first CTA end {(int(torch.maximum(di[:, 6], di[:, 7]).min()) - s) / 1e3:5.1f}"
         if prev_end is not None:
-            msg += f", gap after previous {(s - prev_end) / 1e3:5.1f} us; wait passed {(int(di[:, 1].min()) - prev_end) / 1e3:5.2f}..{(int(di[:, 1].max()) - prev_end) / 1e3:5.2f} us after previous end; first operands +{(int(di[:, 2].median()) - int(di[:, 1].median())) / 1e3:4.2f} us; MMAs done->CTA done {(int(di[:, 6].median()) - int(di[:, 5].median())) / 1e3:4.2f}"
-        msg += f"; TMEM dealloc returned {(int(di[:, 7].max()) - e) / 1e3:5.2f} us after the last end stamp (median per CTA {float((di[:, 7] - di[:, 6]).double().median()) / 1e3:4.2f})"
+            msg += f", gap after previous {(s - prev_end) / 1e3:5.1f} us; wait passed {(int(di[:, 1].min()) - prev_end) / 1e3:5.2f}..{(int(di[:, 1].max()) - prev_end) / 1e3:5.2f} us after previous end; first operands +{(int(di[:, 2].median()) - int(di[:, 1].median())) / 1e3:4.2f} us"
+        msg += f"; last accumulator complete -> CTA end {float((torch.maximum(di[:, 6], di[:, 7]) - di[:, 5]).double().max()) / 1e3:5.2f} us (max), end-of-work barrier -> dealloc returned {float((di[:, 7] - di[:, 6]).double().median()) / 1e3:4.2f} us"
         if os.environ.get("MTP_DBG") == "20":
             msg += f"; end stamp -> before fence {float((di[:, 2] - di[:, 6]).double().median()) / 1e3:4.2f}, fence {float((di[:, 3] - di[:, 2]).double().median()) / 1e3:4.2f}, dealloc {float((di[:, 7] - di[:, 3]).double().median()) / 1e3:4.2f} us (medians)"
         print(msg)
