@@ -19,7 +19,10 @@ namespace mtp {
 constexpr int FT_THREADS = 128;
 constexpr int FT_TILE = 128 * 128;       // bytes of a 128-row tile
 constexpr int FT_MAXG = 16;              // max grid side (N <= 256)
-constexpr int FT_TAB = (2 * FT_MAXG - 1) * 64;   // floats per rel-pos table
+constexpr int FT_TS = 68;               // row pitch (floats) of the rel-pos tables in shared memory: rows read by the 8 lanes of a quarter warp
+                                        // (consecutive qx) fall into different banks (pitch 64: every row in the same banks, ncu: 76 % of all
+                                        // shared-memory wavefronts of the forward kernel were conflicts)
+constexpr int FT_TAB = (2 * FT_MAXG - 1) * FT_TS;   // floats per rel-pos table
 
 // copy rows [row0, row0+nrows) of a head slice (64 bf16 per row, row pitch ld) into a swizzled tile; rows >= nvalid are zero
 __device__ __forceinline__ void ft_load_rows(uint8_t* tile, const __nv_bfloat16* src, size_t ld, int row0, int nrows, int nvalid) {
@@ -43,14 +46,14 @@ __device__ __forceinline__ void ft_rel_terms(const uint8_t* Qs, const float* rel
     for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[c * 8 + 2 * t] = f.x; qv[c * 8 + 2 * t + 1] = f.y; }
   }
   for (int k = 0; k < gh; ++k) {
-    const float* th = relh_t + (qy - k + gh - 1) * 64;
+    const float* th = relh_t + (qy - k + gh - 1) * FT_TS;
     float s = 0.f;
 #pragma unroll
     for (int d = 0; d < 64; ++d) s += qv[d] * th[d];
     rh_s[k] = s;
   }
   for (int k = 0; k < gw; ++k) {
-    const float* tw = relw_t + (qx - k + gw - 1) * 64;
+    const float* tw = relw_t + (qx - k + gw - 1) * FT_TS;
     float s = 0.f;
 #pragma unroll
     for (int d = 0; d < 64; ++d) s += qv[d] * tw[d];
@@ -74,8 +77,8 @@ __device__ __forceinline__ void ft_rel_terms_fixed(const uint8_t* Qs, const floa
     for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
 #pragma unroll
     for (int k = 0; k < G; ++k) {
-      const float4* th = reinterpret_cast<const float4*>(relh_t + (qy - k + G - 1) * 64 + c * 8);
-      const float4* tw = reinterpret_cast<const float4*>(relw_t + (qx - k + G - 1) * 64 + c * 8);
+      const float4* th = reinterpret_cast<const float4*>(relh_t + (qy - k + G - 1) * FT_TS + c * 8);
+      const float4* tw = reinterpret_cast<const float4*>(relw_t + (qx - k + G - 1) * FT_TS + c * 8);
       const float4 h0 = th[0], h1 = th[1], w0 = tw[0], w1 = tw[1];
       rh[k] += qv[0] * h0.x + qv[1] * h0.y + qv[2] * h0.z + qv[3] * h0.w + qv[4] * h1.x + qv[5] * h1.y + qv[6] * h1.z + qv[7] * h1.w;
       rw[k] += qv[0] * w0.x + qv[1] * w0.y + qv[2] * w0.z + qv[3] * w0.w + qv[4] * w1.x + qv[5] * w1.y + qv[6] * w1.z + qv[7] * w1.w;
@@ -85,6 +88,8 @@ __device__ __forceinline__ void ft_rel_terms_fixed(const uint8_t* Qs, const floa
 
 // ================================================================================================== forward
 constexpr int FTF_SMEM = FT_TILE /*Q*/ + 2 * 2 * FT_TILE /*K,V*/ + 4 * FT_TILE /*P*/ + (2 * FT_TAB + 2 * 128 * 17) * 4 + 64;
+constexpr int ftf_smem_duo(int G) { return 4 * FT_TILE /*P over Q,K*/ + ((G * G + 15) & ~15) * 128 /*V*/ + 2 * (2 * G - 1) * FT_TS * 4 + 64; }
+static_assert(2 * (ftf_smem_duo(14) + 1024) <= 228 * 1024, "two forward CTAs of the 14 x 14 case must fit one SM");
 
 template <int G>      // G > 0: gh == gw == G known at compile time (and rel-pos in use); G == 0: generic
 __global__ void __launch_bounds__(FT_THREADS)
@@ -92,16 +97,24 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                         __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int gh, int gw, int C, int nH, int use_rel) {
   MTP_PDL_ENTRY();
   extern __shared__ __align__(1024) uint8_t sm[];
-  uint8_t* Qs = sm;
-  uint8_t* Ks = Qs + FT_TILE;              // 256 rows
-  uint8_t* Vs = Ks + 2 * FT_TILE;
-  uint8_t* Pt = Vs + 2 * FT_TILE;          // 4 atoms of 128 rows
-  float* relh_t = reinterpret_cast<float*>(Pt + 4 * FT_TILE);
-  float* relw_t = relh_t + FT_TAB;
-  float* rh_s = relw_t + FT_TAB;           // [128][17] per-row rel terms
-  float* rw_s = rh_s + 128 * 17;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(rw_s + 128 * 17);
+  // G > 0 (the 14 x 14 grid of the headline configuration): a layout small enough for TWO CTAs per SM (105 KB, 256 TMEM columns, 165
+  // registers x 128 threads).  One CTA per SM = one warp per scheduler ran at 13 cycles per instruction (ncu: long / short scoreboard and
+  // instruction-fetch stalls with nothing to switch to), and 256 CTAs took two rounds on 148 SMs.  The P tile (4 atoms, 64 KB) lies over Q and
+  // K, which are dead once S = Q K^T is complete and every thread has its rel-pos terms (barrier below); O reuses the first TMEM columns of S.
+  constexpr bool DUO = G > 0;
+  constexpr int KROWS = DUO ? ((G * G + 15) & ~15) : 256;        // rows of the K and V tiles
+  constexpr int TROWS = DUO ? 2 * G - 1 : 2 * FT_MAXG - 1;        // rows of each rel-pos table
+  uint8_t* Pt = sm;                                               // 4 atoms of 128 rows
+  uint8_t* Qs = DUO ? sm : sm + 4 * FT_TILE;
+  uint8_t* Ks = Qs + FT_TILE;
+  uint8_t* Vs = DUO ? sm + 4 * FT_TILE : Ks + 2 * FT_TILE;
+  float* relh_t = reinterpret_cast<float*>(Vs + KROWS * 128);
+  float* relw_t = relh_t + TROWS * FT_TS;
+  float* rh_s = relw_t + TROWS * FT_TS;    // [128][17] per-row rel terms (generic path only)
+  float* rw_s = rh_s + (DUO ? 0 : 128 * 17);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(rw_s + (DUO ? 0 : 128 * 17));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  constexpr int TMEM_COLS = DUO ? 256 : 512;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   // one CTA per (image, head, 128-query tile): K / V of the head are re-staged by each of the (1 or 2) query-tile CTAs, which doubles the
@@ -114,19 +127,19 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   const __nv_bfloat16* base = qkv + (size_t)b * N * C3 + n * 64;
   const int N16 = (N + 15) & ~15;
 
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
   if (tid == 32) { mbar_init(mbar, 1); fence_barrier_init(); }
-  ft_load_rows(Ks, base + C, C3, 0, 256, N);
-  ft_load_rows(Vs, base + 2 * C, C3, 0, 256, N);
+  ft_load_rows(Ks, base + C, C3, 0, KROWS, N);
+  ft_load_rows(Vs, base + 2 * C, C3, 0, KROWS, N);
   if (use_rel) {
-    for (int i = tid; i < (2 * gh - 1) * 64; i += FT_THREADS) relh_t[i] = rel_h[i];
-    for (int i = tid; i < (2 * gw - 1) * 64; i += FT_THREADS) relw_t[i] = rel_w[i];
+    for (int i = tid; i < (2 * gh - 1) * 64; i += FT_THREADS) relh_t[(i >> 6) * FT_TS + (i & 63)] = rel_h[i];
+    for (int i = tid; i < (2 * gw - 1) * 64; i += FT_THREADS) relw_t[(i >> 6) * FT_TS + (i & 63)] = rel_w[i];
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t T_S = tmem, T_O = tmem + 256;
+  const uint32_t T_S = tmem, T_O = DUO ? tmem : tmem + 256;      // DUO: O is written after every row of S has been read
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
   uint32_t phase = 0;
 
@@ -154,6 +167,7 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
+    if (DUO) __syncthreads();      // P is written over Q: every thread has read its query row
 
     const int n_chunks = (N + 31) / 32;
     float m = -INFINITY;
@@ -289,7 +303,7 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     __syncthreads();          // TMEM rows and the Q / P tiles are free for the next query tile
     tc_fence_after();
   }
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* rel_w, void* out, float* lse, int B, int gh, int gw, int C,
@@ -297,13 +311,14 @@ int launch_full_attn_fwd_tc(const void* qkv, const float* rel_h, const float* re
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(full_attn_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FTF_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(full_attn_fwd_tc_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, FTF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(full_attn_fwd_tc_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, ftf_smem_duo(14));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(full_attn_fwd_tc_kernel<14>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "full_attn_fwd_tc smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
   const int nqt = (gh * gw + 127) / 128;
   if (gh == 14 && gw == 14 && rel_h != nullptr)
-    (void)launch_k(full_attn_fwd_tc_kernel<14>, B * nH * nqt, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
+    (void)launch_k(full_attn_fwd_tc_kernel<14>, B * nH * nqt, FT_THREADS, ftf_smem_duo(14), st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
                    reinterpret_cast<__nv_bfloat16*>(out), lse, gh * gw, gh, gw, C, nH, 1);
   else
     (void)launch_k(full_attn_fwd_tc_kernel<0>, B * nH * nqt, FT_THREADS, FTF_SMEM, st, reinterpret_cast<const __nv_bfloat16*>(qkv), rel_h, rel_w,
@@ -354,8 +369,8 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   ft_load_rows(Ks, base + C, C3, 0, 256, N);
   ft_load_rows(Vs, base + 2 * C, C3, 0, 256, N);
   if (use_rel) {
-    for (int i = tid; i < (2 * gh - 1) * 64; i += FT_THREADS) relh_t[i] = rel_h[i];
-    for (int i = tid; i < (2 * gw - 1) * 64; i += FT_THREADS) relw_t[i] = rel_w[i];
+    for (int i = tid; i < (2 * gh - 1) * 64; i += FT_THREADS) relh_t[(i >> 6) * FT_TS + (i & 63)] = rel_h[i];
+    for (int i = tid; i < (2 * gw - 1) * 64; i += FT_THREADS) relw_t[(i >> 6) * FT_TS + (i & 63)] = rel_w[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -519,8 +534,8 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
 #pragma unroll
         for (int k = 0; k < G; ++k) {
           const float ch = dShr[k], cw = dSwr[k];
-          const float4* th = reinterpret_cast<const float4*>(relh_t + (qy - k + G - 1) * 64);
-          const float4* tw = reinterpret_cast<const float4*>(relw_t + (qx - k + G - 1) * 64);
+          const float4* th = reinterpret_cast<const float4*>(relh_t + (qy - k + G - 1) * FT_TS);
+          const float4* tw = reinterpret_cast<const float4*>(relw_t + (qx - k + G - 1) * FT_TS);
 #pragma unroll
           for (int d = 0; d < 16; ++d) {
             const float4 a = th[d], c = tw[d];
@@ -533,13 +548,13 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       } else if (use_rel) {
         for (int k = 0; k < gh; ++k) {
           const float ch = dSh[tid * 17 + k];
-          const float* th = relh_t + (qy - k + gh - 1) * 64;
+          const float* th = relh_t + (qy - k + gh - 1) * FT_TS;
 #pragma unroll
           for (int d = 0; d < 64; ++d) dq[d] += ch * th[d];
         }
         for (int k = 0; k < gw; ++k) {
           const float cw = dSw[tid * 17 + k];
-          const float* tw = relw_t + (qx - k + gw - 1) * 64;
+          const float* tw = relw_t + (qx - k + gw - 1) * FT_TS;
 #pragma unroll
           for (int d = 0; d < 64; ++d) dq[d] += cw * tw[d];
         }
