@@ -86,9 +86,69 @@ __device__ __forceinline__ void ft_rel_terms_fixed(const uint8_t* Qs, const floa
   }
 }
 
+// ---- rel-pos terms on the tensor core (grid side G known at compile time) ---------------------------------------------------------------
+// REL[q][t] = q . R[t]  for the stacked table R = [Rh rows 0 .. 2G-2 | zero | Rw rows at 32 .. 32+2G-2 | zero] (64 rows) is one more
+// 128 x 64 x 64 MMA on the Q tile instead of 2 * G dot products of length 64 per thread (1800 FMAs + 900 shared-memory loads per row: 40 %
+// of the forward kernel's instructions).  The fp32 tables are split into bf16 hi + lo words (two accumulating MMAs): exact to 2^-17.
+// The same tile, read MN-major, is the B operand of the backward's  dq += W R  (W = the dS row / column sums).
+template <int G>
+__device__ __forceinline__ void ft_build_rel_tiles(uint8_t* hi, uint8_t* lo, const float* __restrict__ rel_h, const float* __restrict__ rel_w) {
+  static_assert(2 * G - 1 <= 32, "table rows");
+  for (int i = threadIdx.x; i < 64 * 8; i += FT_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    const int t = r < 32 ? r : r - 32;
+    uint4 uh = make_uint4(0, 0, 0, 0), ul = make_uint4(0, 0, 0, 0);
+    if (t < 2 * G - 1) {
+      const float* src = (r < 32 ? rel_h : rel_w) + t * 64 + c * 8;
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+        h[k] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+        l[k] = pack_bf16x2(v[2 * k] - __bfloat162float(h0), v[2 * k + 1] - __bfloat162float(h1));
+      }
+      uh = make_uint4(h[0], h[1], h[2], h[3]);
+      ul = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    *reinterpret_cast<uint4*>(hi + tile_chunk_off(r, c)) = uh;
+    *reinterpret_cast<uint4*>(lo + tile_chunk_off(r, c)) = ul;
+  }
+}
+
+// out[k] = v[base + s + (G - 1) - k], k < G, for a run-time shift s in [0, G): a 4-stage barrel shifter on registers (no dynamic indexing)
+template <int G>
+__device__ __forceinline__ void ft_pick_terms(const uint32_t (&v)[32], int s, float (&out)[G]) {
+  float a[2 * G - 1];
+#pragma unroll
+  for (int j = 0; j < 2 * G - 1; ++j) a[j] = __uint_as_float(v[j]);
+#pragma unroll
+  for (int st = 8; st >= 1; st >>= 1) {
+    const bool on = (s & st) != 0;
+#pragma unroll
+    for (int j = 0; j + st < 2 * G - 1; ++j) a[j] = on ? a[j + st] : a[j];
+  }
+#pragma unroll
+  for (int k = 0; k < G; ++k) out[k] = a[G - 1 - k];
+}
+
+// the inverse: out[t] = in[s + (G - 1) - t] for t - s in [0, G), else 0  (t < 32): a dS row / column sum lands on the table row it multiplies
+template <int G>
+__device__ __forceinline__ void ft_spread_terms(const float (&in)[G], int s, float (&out)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) out[j] = j < G ? in[G - 1 - j] : 0.f;
+#pragma unroll
+  for (int st = 8; st >= 1; st >>= 1) {
+    const bool on = (s & st) != 0;
+#pragma unroll
+    for (int j = 31; j >= 0; --j) out[j] = on ? (j >= st ? out[j - st] : 0.f) : out[j];
+  }
+}
+
 // ================================================================================================== forward
 constexpr int FTF_SMEM = FT_TILE /*Q*/ + 2 * 2 * FT_TILE /*K,V*/ + 4 * FT_TILE /*P*/ + (2 * FT_TAB + 2 * 128 * 17) * 4 + 64;
-constexpr int ftf_smem_duo(int G) { return 4 * FT_TILE /*P over Q,K*/ + ((G * G + 15) & ~15) * 128 /*V*/ + 2 * (2 * G - 1) * FT_TS * 4 + 64; }
+constexpr int ftf_smem_duo(int G) { return 4 * FT_TILE /*P over Q,K*/ + ((G * G + 15) & ~15) * 128 /*V*/ + 2 * 64 * 128 /*rel-pos table tiles*/ + 64; }
 static_assert(2 * (ftf_smem_duo(14) + 1024) <= 228 * 1024, "two forward CTAs of the 14 x 14 case must fit one SM");
 
 template <int G>      // G > 0: gh == gw == G known at compile time (and rel-pos in use); G == 0: generic
@@ -108,13 +168,18 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   uint8_t* Qs = DUO ? sm : sm + 4 * FT_TILE;
   uint8_t* Ks = Qs + FT_TILE;
   uint8_t* Vs = DUO ? sm + 4 * FT_TILE : Ks + 2 * FT_TILE;
-  float* relh_t = reinterpret_cast<float*>(Vs + KROWS * 128);
-  float* relw_t = relh_t + TROWS * FT_TS;
-  float* rh_s = relw_t + TROWS * FT_TS;    // [128][17] per-row rel terms (generic path only)
+  // DUO: the stacked rel-pos table as two bf16 B-operand tiles (hi, lo words) of 64 rows; generic: fp32 tables + per-row terms in smem
+  uint8_t* Rhi = Vs + KROWS * 128;         // KROWS * 128 is a multiple of 1024 for G = 14 (208 rows)
+  uint8_t* Rlo = Rhi + 64 * 128;
+  float* relh_t = reinterpret_cast<float*>(DUO ? Rlo + 64 * 128 : Vs + KROWS * 128);
+  float* relw_t = relh_t + (DUO ? 0 : TROWS * FT_TS);
+  float* rh_s = relw_t + (DUO ? 0 : TROWS * FT_TS);    // [128][17] per-row rel terms (generic path only)
   float* rw_s = rh_s + (DUO ? 0 : 128 * 17);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(rw_s + (DUO ? 0 : 128 * 17));
+  static_assert(!DUO || (KROWS * 128) % 1024 == 0, "tile alignment");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   constexpr int TMEM_COLS = DUO ? 256 : 512;
+  constexpr int GD = G > 0 ? G : 1;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   // one CTA per (image, head, 128-query tile): K / V of the head are re-staged by each of the (1 or 2) query-tile CTAs, which doubles the
@@ -131,7 +196,9 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   if (tid == 32) { mbar_init(mbar, 1); fence_barrier_init(); }
   ft_load_rows(Ks, base + C, C3, 0, KROWS, N);
   ft_load_rows(Vs, base + 2 * C, C3, 0, KROWS, N);
-  if (use_rel) {
+  if constexpr (DUO) {
+    ft_build_rel_tiles<GD>(Rhi, Rlo, rel_h, rel_w);
+  } else if (use_rel) {
     for (int i = tid; i < (2 * gh - 1) * 64; i += FT_THREADS) relh_t[(i >> 6) * FT_TS + (i & 63)] = rel_h[i];
     for (int i = tid; i < (2 * gw - 1) * 64; i += FT_THREADS) relw_t[(i >> 6) * FT_TS + (i & 63)] = rel_w[i];
   }
@@ -147,6 +214,38 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     ft_load_rows(Qs, base, C3, q0, 128, N);
     fence_proxy_async_smem();
     __syncthreads();
+    const int q = q0 + tid;
+    const bool qvalid = q < N;
+    const int qy = qvalid ? q / gw : 0, qx = qvalid ? q % gw : 0;
+    float* rh = rh_s + tid * 17;
+    float* rw = rw_s + tid * 17;
+    constexpr int GG = G > 0 ? G : 1;
+    float rhr[GG], rwr[GG];
+    if constexpr (DUO) {
+      // rel-pos terms first, into the TMEM columns S will overwrite (256 columns per CTA leave no room for both)
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Rhi), 0, 128, 64, 64, false);
+          tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Rlo), 0, 128, 64, 64, true);
+          umma_commit(mbar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      {
+        uint32_t vh[32], vw[32];
+        tmem_ld_32x32(T_S + lane_base, vh);
+        tmem_ld_32x32(T_S + lane_base + 32, vw);
+        tmem_ld_wait();
+        ft_pick_terms<GD>(vh, qy, rhr);      // rhr[k] = q . Rh[qy - k + G - 1]
+        ft_pick_terms<GD>(vw, qx, rwr);
+      }
+      tc_fence_before();
+      __syncthreads();                       // every row of REL has been read: S may overwrite it
+    }
     if (warp == 0) {      // warp-uniform issue: descriptors stay in uniform registers (no ELECT/R2UR waterfall per MMA)
       tc_fence_after();
       if (elect_one()) {
@@ -155,19 +254,12 @@ full_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       }
       __syncwarp();
     }
-    const int q = q0 + tid;
-    const bool qvalid = q < N;
-    const int qy = qvalid ? q / gw : 0, qx = qvalid ? q % gw : 0;
-    float* rh = rh_s + tid * 17;
-    float* rw = rw_s + tid * 17;
-    constexpr int GG = G > 0 ? G : 1;
-    float rhr[GG], rwr[GG];
-    if constexpr (G > 0) ft_rel_terms_fixed<G>(Qs, relh_t, relw_t, tid, qy, qx, rhr, rwr);
-    else if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
+    if constexpr (!DUO) {
+      if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
+    }
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
-    if (DUO) __syncthreads();      // P is written over Q: every thread has read its query row
 
     const int n_chunks = (N + 31) / 32;
     float m = -INFINITY;
@@ -368,7 +460,13 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   if (tid == 32) { mbar_init(mbar, 1); fence_barrier_init(); }
   ft_load_rows(Ks, base + C, C3, 0, 256, N);
   ft_load_rows(Vs, base + 2 * C, C3, 0, 256, N);
-  if (use_rel) {
+  // G > 0: the stacked rel-pos table as bf16 hi / lo operand tiles (in the space of the fp32 tables), see ft_build_rel_tiles
+  uint8_t* Rhi = reinterpret_cast<uint8_t*>(relh_t);
+  uint8_t* Rlo = Rhi + 64 * 128;
+  static_assert(2 * FT_TAB * 4 >= 2 * 64 * 128, "the table tiles fit the fp32 table region");
+  if constexpr (G > 0) {
+    ft_build_rel_tiles<GG>(Rhi, Rlo, rel_h, rel_w);
+  } else if (use_rel) {
     for (int i = tid; i < (2 * gh - 1) * 64; i += FT_THREADS) relh_t[(i >> 6) * FT_TS + (i & 63)] = rel_h[i];
     for (int i = tid; i < (2 * gw - 1) * 64; i += FT_THREADS) relw_t[(i >> 6) * FT_TS + (i & 63)] = rel_w[i];
   }
@@ -419,8 +517,32 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     float rhr[GG], rwr[GG], dShr[GG], dSwr[GG];
 #pragma unroll
     for (int k = 0; k < GG; ++k) { dShr[k] = 0.f; dSwr[k] = 0.f; }
-    if constexpr (G > 0) ft_rel_terms_fixed<G>(Qs, relh_t, relw_t, tid, qy, qx, rhr, rwr);
-    else if (use_rel) ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
+    if constexpr (G > 0) {      // rel-pos terms of the tile's rows as an MMA into the columns S will use (see the forward kernel)
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Rhi), 0, 128, 64, 64, false);
+          tc_mma_tiles<false, false>(T_S, smem_u32(Qs), 0, smem_u32(Rlo), 0, 128, 64, 64, true);
+          umma_commit(mbar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      {
+        uint32_t vh[32], vw[32];
+        tmem_ld_32x32(T_S + lane_base, vh);
+        tmem_ld_32x32(T_S + lane_base + 32, vw);
+        tmem_ld_wait();
+        ft_pick_terms<GG>(vh, qy, rhr);
+        ft_pick_terms<GG>(vw, qx, rwr);
+      }
+      tc_fence_before();
+      __syncthreads();
+    } else if (use_rel) {
+      ft_rel_terms(Qs, relh_t, relw_t, tid, qy, qx, gh, gw, rh, rw);
+    }
     float dq[64];
 #pragma unroll
     for (int d = 0; d < 64; ++d) dq[d] = 0.f;
@@ -524,28 +646,83 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       tc_fence_after();
     }
 
-    if constexpr (G > 0) {      // the W tile below reads the row sums with run-time indices: park them in shared memory
+    if constexpr (G > 0) {
+      // W[q][t] = dSh[q][qy - t + G - 1] (t < 2G-1), W[q][32 + t] = dSw[q][qx - t + G - 1]: the dS row / column sums spread over the table rows
+      // they multiply.  Two products on the tensor core:  dq += W R  (W as bf16 hi + lo tiles, R as hi + lo: exact to 2^-17) and the table
+      // gradients  dR[t][:] = sum_q W[q][t] q[q][:]  (W hi only, as before).
+      {
+        float wh[32], ww[32];
+        ft_spread_terms<GG>(dShr, qy, wh);
+        ft_spread_terms<GG>(dSwr, qx, ww);
 #pragma unroll
-      for (int k = 0; k < G; ++k) { dSh[tid * 17 + k] = dShr[k]; dSw[tid * 17 + k] = dSwr[k]; }
-    }
-    // dq = scale * (dS K + sum_k dSh[k] Rh[qy-k+gh-1] + sum_k dSw[k] Rw[qx-k+gw-1])
-    if (qvalid) {
-      if constexpr (G > 0) {
+        for (int c = 0; c < 8; ++c) {
+          uint32_t h[4], l[4];
 #pragma unroll
-        for (int k = 0; k < G; ++k) {
-          const float ch = dShr[k], cw = dSwr[k];
-          const float4* th = reinterpret_cast<const float4*>(relh_t + (qy - k + G - 1) * FT_TS);
-          const float4* tw = reinterpret_cast<const float4*>(relw_t + (qx - k + G - 1) * FT_TS);
+          for (int k = 0; k < 4; ++k) {
+            const int t = 8 * c + 2 * k;
+            const float v0 = qvalid ? (t < 32 ? wh[t] : ww[t - 32]) : 0.f, v1 = qvalid ? (t + 1 < 32 ? wh[t + 1] : ww[t + 1 - 32]) : 0.f;
+            const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
+            h[k] = pack_bf16x2(h0, h1);
+            l[k] = pack_bf16x2(v0 - h0, v1 - h1);
+          }
+          *reinterpret_cast<uint4*>(Pt + tile_chunk_off(tid, c)) = make_uint4(h[0], h[1], h[2], h[3]);                 // P tile is free
+          *reinterpret_cast<uint4*>(Pt + FT_TILE + tile_chunk_off(tid, c)) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+          // table gradients: rows 64..127 of the result (the lo words as extra "table rows") are never read
+          tc_mma_tiles<true, true>(T_S + 64, smem_u32(Pt), FT_TILE, smem_u32(Qs), 0, 128, 64, 128, false);
+          tc_mma_tiles<false, true>(T_S, smem_u32(Pt), 0, smem_u32(Rhi), 0, 128, 64, 64, false);
+          tc_mma_tiles<false, true>(T_S, smem_u32(Pt), 0, smem_u32(Rlo), 0, 128, 64, 64, true);
+          tc_mma_tiles<false, true>(T_S, smem_u32(Pt) + FT_TILE, 0, smem_u32(Rhi), 0, 128, 64, 64, true);
+          umma_commit(mbar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(T_S + lane_base, r0);
+        tmem_ld_32x32(T_S + lane_base + 32, r1);
+        tmem_ld_wait();
+        if (qvalid) {
+          __nv_bfloat16* dst = dqkv + ((size_t)b * N + q) * C3 + n * 64;
 #pragma unroll
-          for (int d = 0; d < 16; ++d) {
-            const float4 a = th[d], c = tw[d];
-            dq[4 * d] += ch * a.x + cw * c.x;
-            dq[4 * d + 1] += ch * a.y + cw * c.y;
-            dq[4 * d + 2] += ch * a.z + cw * c.z;
-            dq[4 * d + 3] += ch * a.w + cw * c.w;
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            u.x = pack_bf16x2(scale * (dq[8 * c] + __uint_as_float(r0[8 * c])), scale * (dq[8 * c + 1] + __uint_as_float(r0[8 * c + 1])));
+            u.y = pack_bf16x2(scale * (dq[8 * c + 2] + __uint_as_float(r0[8 * c + 2])), scale * (dq[8 * c + 3] + __uint_as_float(r0[8 * c + 3])));
+            u.z = pack_bf16x2(scale * (dq[8 * c + 4] + __uint_as_float(r0[8 * c + 4])), scale * (dq[8 * c + 5] + __uint_as_float(r0[8 * c + 5])));
+            u.w = pack_bf16x2(scale * (dq[8 * c + 6] + __uint_as_float(r0[8 * c + 6])), scale * (dq[8 * c + 7] + __uint_as_float(r0[8 * c + 7])));
+            *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+            u.x = pack_bf16x2(scale * (dq[32 + 8 * c] + __uint_as_float(r1[8 * c])), scale * (dq[32 + 8 * c + 1] + __uint_as_float(r1[8 * c + 1])));
+            u.y = pack_bf16x2(scale * (dq[32 + 8 * c + 2] + __uint_as_float(r1[8 * c + 2])), scale * (dq[32 + 8 * c + 3] + __uint_as_float(r1[8 * c + 3])));
+            u.z = pack_bf16x2(scale * (dq[32 + 8 * c + 4] + __uint_as_float(r1[8 * c + 4])), scale * (dq[32 + 8 * c + 5] + __uint_as_float(r1[8 * c + 5])));
+            u.w = pack_bf16x2(scale * (dq[32 + 8 * c + 6] + __uint_as_float(r1[8 * c + 6])), scale * (dq[32 + 8 * c + 7] + __uint_as_float(r1[8 * c + 7])));
+            *reinterpret_cast<uint4*>(dst + 32 + 8 * c) = u;
           }
         }
-      } else if (use_rel) {
+      }
+      if (warp < 2) {           // rows 0..63 of the table-gradient product
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(T_S + 64 + lane_base, r0);
+        tmem_ld_32x32(T_S + 64 + lane_base + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) { relacc[d] += __uint_as_float(r0[d]); relacc[32 + d] += __uint_as_float(r1[d]); }
+      }
+      tc_fence_before();
+    } else {
+    // dq = scale * (dS K + sum_k dSh[k] Rh[qy-k+gh-1] + sum_k dSw[k] Rw[qx-k+gw-1])
+    if (qvalid) {
+      if (use_rel) {
         for (int k = 0; k < gh; ++k) {
           const float ch = dSh[tid * 17 + k];
           const float* th = relh_t + (qy - k + gh - 1) * FT_TS;
@@ -612,6 +789,7 @@ full_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         for (int d = 0; d < 32; ++d) { relacc[d] += __uint_as_float(r0[d]); relacc[32 + d] += __uint_as_float(r1[d]); }
       }
       tc_fence_before();
+    }
     }
     __syncthreads();            // Q / dO tiles and dSh / dSw are rewritten by the next query tile
   }
