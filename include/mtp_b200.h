@@ -216,6 +216,15 @@ int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, const float* re
                       float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace,
                       int scratch_zeroed, int B, int h, int w, int C, int nH, mtp_stream_t stream);
 size_t mtp_rvsa_sampling_bwd_workspace_bytes(int B, int h, int w, int C, int nH);
+/* mtp_rvsa_attn_bwd + mtp_rvsa_sampling_bwd (dyn = NULL form) of one window block with their four follow-up kernels fused into one launch
+   (the reference: autograd of `[V]:372-428` and of the three sampling heads `[V]:228-243`).  dpooled [n_bw][C] fp32 is left in
+   sampling_workspace at offset n_bw * 5 * nH floats (n_bw = B * windows per image) for mtp_layernorm_bwd's pool_add. nH even. */
+int mtp_rvsa_attn_bwd_fused(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,
+                            const float* bias_table, const float* lse, const void* dout_bf16, void* dqkv_bf16, float* dparams,
+                            float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace,
+                            const float* pooled, const float* w_off, const float* w_scale, const float* w_angle, float* dw_off,
+                            float* db_off, float* dw_scale, float* db_scale, float* dw_angle, float* db_angle,
+                            void* sampling_workspace, int B, int h, int w, int C, int nH, mtp_stream_t stream);
 int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, const float* w_off, const float* w_scale,
                           const float* w_angle, float* dw_off, float* db_off, float* dw_scale, float* db_scale, float* dw_angle,
                           float* db_angle, void* dyn_bf16, void* workspace, int B, int h, int w, int C, int nH,

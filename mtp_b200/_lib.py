@@ -63,6 +63,7 @@ _SIGNATURES = {
     "mtp_sqloss_fwd_bwd_w": [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p],
     "mtp_rvsa_attn_bwd": [c_void_p] * 14 + [c_int] * 6 + [c_void_p],
     "mtp_rvsa_sampling_bwd": [c_void_p] * 13 + [c_int] * 5 + [c_void_p],
+    "mtp_rvsa_attn_bwd_fused": [c_void_p] * 25 + [c_int] * 5 + [c_void_p],
     "mtp_full_attn_bwd": [c_void_p] * 10 + [c_int] * 5 + [c_void_p],
     "mtp_split_hilo": [c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p],
     "mtp_patchify_hilo": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -128,7 +129,7 @@ def check(rc, what=""):
 FAMILIES = {
     "gemm": ("mtp_gemm_bf16", "mtp_gemm_bf16_dual"),
     "rvsa_attn_fwd": ("mtp_rvsa_attn_fwd",), "rvsa_sampling_fwd": ("mtp_rvsa_sampling_fwd",),
-    "rvsa_attn_bwd": ("mtp_rvsa_attn_bwd",), "rvsa_sampling_bwd": ("mtp_rvsa_sampling_bwd",),
+    "rvsa_attn_bwd": ("mtp_rvsa_attn_bwd", "mtp_rvsa_attn_bwd_fused"), "rvsa_sampling_bwd": ("mtp_rvsa_sampling_bwd",),
     "dense_attn_fwd": ("mtp_full_attn_fwd",), "dense_attn_bwd": ("mtp_full_attn_bwd",),
     "layernorm_fwd": ("mtp_layernorm_fwd",), "layernorm_bwd": ("mtp_layernorm_bwd",),
     "optimizer": ("mtp_adamw_step", "mtp_adamw_step_mixed", "mtp_sumsq_f32", "mtp_sumsq_bf16", "mtp_optim_step_begin"),

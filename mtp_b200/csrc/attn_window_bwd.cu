@@ -347,10 +347,9 @@ rvsa_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restr
 // A warp owns 32 consecutive outputs (coalesced rows of the partial arrays) and one slice of the partials, all of its loads in
 // flight at once; the 8 warps of a CTA hold the 8 slices of the same outputs and combine through shared memory.
 constexpr int PR_SLICES = 8;
-__global__ void __launch_bounds__(256)
-rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __restrict__ part_table, float* __restrict__ d_rel_h,
-                            float* __restrict__ d_rel_w, float* __restrict__ d_table, int n_rel_parts, int n_bw, int nH) {
-  MTP_PDL_ENTRY();
+__device__ __forceinline__ void rvsa_partials_reduce_body(const float* __restrict__ part_rel, const float* __restrict__ part_table,
+                                                          float* __restrict__ d_rel_h, float* __restrict__ d_rel_w, float* __restrict__ d_table,
+                                                          int n_rel_parts, int n_bw, int nH, int bx) {
   __shared__ float red[PR_SLICES][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_rel = 2 * (2 * WS - 1) * HD;
@@ -358,15 +357,15 @@ rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __r
   const int tab_blocks = (169 + 31) / 32;                  // per head
   float s = 0.f;
   float* dst = nullptr;
-  if ((int)blockIdx.x < rel_blocks) {
-    const int i = blockIdx.x * 32 + lane;
+  if (bx < rel_blocks) {
+    const int i = bx * 32 + lane;
     const int per = (n_rel_parts + PR_SLICES - 1) / PR_SLICES;
     const int c0 = warp * per, c1 = min(n_rel_parts, c0 + per);
 #pragma unroll 8
     for (int c = c0; c < c1; ++c) s += part_rel[(size_t)c * n_rel + i];
     dst = i < n_rel / 2 ? d_rel_h + i : d_rel_w + (i - n_rel / 2);
   } else {
-    const int e = blockIdx.x - rel_blocks;                 // (head, 32-wide displacement block)
+    const int e = bx - rel_blocks;                 // (head, 32-wide displacement block)
     const int n = e / tab_blocks, idx = (e % tab_blocks) * 32 + lane;
     if (n < nH && idx < 169) {
       const int per = (n_bw + PR_SLICES - 1) / PR_SLICES;
@@ -386,16 +385,21 @@ rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __r
   }
 }
 
+__global__ void __launch_bounds__(256)
+rvsa_partials_reduce_kernel(const float* __restrict__ part_rel, const float* __restrict__ part_table, float* __restrict__ d_rel_h,
+                            float* __restrict__ d_rel_w, float* __restrict__ d_table, int n_rel_parts, int n_bw, int nH) {
+  MTP_PDL_ENTRY();
+  rvsa_partials_reduce_body(part_rel, part_table, d_rel_h, d_rel_w, d_table, n_rel_parts, n_bw, nH, (int)blockIdx.x);
+}
+
 // dqkv[t, C + c] = bf16(dkv[t, c]) for c in [0, 2C); optionally colsum[0, 3C) += column sums of the finished bf16 dqkv (the qkv
 // bias gradient), reading the dq part the attention kernel wrote.  Thread = 4 consecutive columns, CTA = a band of rows.
-__global__ void __launch_bounds__(256)
-rvsa_kv_finalize_kernel(float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int T, int C,
-                        int rows_per_cta, int rezero) {
-  MTP_PDL_ENTRY();
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;       // column of dqkv
+__device__ __forceinline__ void rvsa_kv_finalize_body(float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum,
+                                                      int T, int C, int rows_per_cta, int rezero, int bx, int by) {
+  const int c = (bx * 256 + threadIdx.x) * 4;               // column of dqkv
   if (c >= 3 * C) return;
   if (c < C && colsum == nullptr) return;
-  const int row0 = blockIdx.y * rows_per_cta, row1 = min(T, row0 + rows_per_cta);
+  const int row0 = by * rows_per_cta, row1 = min(T, row0 + rows_per_cta);
   float4 acc = make_float4(0, 0, 0, 0);
 #pragma unroll 8
   for (int t = row0; t < row1; ++t) {
@@ -416,27 +420,36 @@ rvsa_kv_finalize_kernel(float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqk
   if (colsum != nullptr)
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + c), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
 }
+__global__ void __launch_bounds__(256)
+rvsa_kv_finalize_kernel(float* __restrict__ dkv, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ colsum, int T, int C,
+                        int rows_per_cta, int rezero) {
+  MTP_PDL_ENTRY();
+  rvsa_kv_finalize_body(dkv, dqkv, colsum, T, C, rows_per_cta, rezero, (int)blockIdx.x, (int)blockIdx.y);
+}
 
 // ------------------------------------------------------------------------------------------------ sampling heads bwd
 // (1) per (image, window): gradient w.r.t. the 5nH raw conv outputs (g_out), and the pooled-path gradient
 //     dpooled[c] = leaky'(pooled[c]) * sum_o g_o W[o][c]
-__global__ void __launch_bounds__(256)
-rvsa_sampling_bwd_kernel(const float* __restrict__ dparams, const float* __restrict__ pooled, const float* __restrict__ w_off,
-                         const float* __restrict__ w_sc, const float* __restrict__ w_ang, float* __restrict__ g_out,
-                         float* __restrict__ dpooled, const RvsaGeom g) {
-  MTP_PDL_ENTRY();
+// gradient w.r.t. raw conv output o of window bw, from the gradient of the sampling parameters (offsets are divided by the window count)
+__device__ __forceinline__ float rvsa_sampling_gout(const float* __restrict__ dparams, int bw, int o, int nH, const RvsaGeom& g) {
+  if (o < 2 * nH) return dparams[((size_t)bw * nH + (o >> 1)) * 8 + (o & 1)] / (float)(((o & 1) == 0 ? g.h : g.w) / WS);
+  if (o < 4 * nH) return dparams[((size_t)bw * nH + ((o - 2 * nH) >> 1)) * 8 + 2 + ((o - 2 * nH) & 1)];
+  return dparams[((size_t)bw * nH + (o - 4 * nH)) * 8 + 4];
+}
+
+__device__ __forceinline__ void rvsa_sampling_bwd_body(const float* __restrict__ dparams, const float* __restrict__ pooled,
+                                                       const float* __restrict__ w_off, const float* __restrict__ w_sc,
+                                                       const float* __restrict__ w_ang, float* __restrict__ g_out, float* __restrict__ dpooled,
+                                                       const RvsaGeom& g, int bx, int by) {
   __shared__ float gs[5 * 64];       // nH <= 64
-  const int bw = blockIdx.x, nH = g.nH, C = g.C;
+  const int bw = bx, nH = g.nH, C = g.C;
   for (int o = threadIdx.x; o < 5 * nH; o += 256) {
-    float v;
-    if (o < 2 * nH) v = dparams[((size_t)bw * nH + (o >> 1)) * 8 + (o & 1)] / (float)(((o & 1) == 0 ? g.h : g.w) / WS);
-    else if (o < 4 * nH) v = dparams[((size_t)bw * nH + ((o - 2 * nH) >> 1)) * 8 + 2 + ((o - 2 * nH) & 1)];
-    else v = dparams[((size_t)bw * nH + (o - 4 * nH)) * 8 + 4];
+    const float v = rvsa_sampling_gout(dparams, bw, o, nH, g);
     gs[o] = v;
-    if (blockIdx.y == 0) g_out[(size_t)bw * 5 * nH + o] = v;
+    if (by == 0 && g_out != nullptr) g_out[(size_t)bw * 5 * nH + o] = v;
   }
   __syncthreads();
-  const int c = blockIdx.y * 256 + threadIdx.x;          // CTA = (image-window, 256-channel slab)
+  const int c = by * 256 + threadIdx.x;                  // CTA = (image-window, 256-channel slab)
   if (c < C) {
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
@@ -450,34 +463,83 @@ rvsa_sampling_bwd_kernel(const float* __restrict__ dparams, const float* __restr
     dpooled[(size_t)bw * C + c] = (p >= 0.f ? 1.0f : 0.01f) * (s0 + s1);
   }
 }
-
-// (2) weight / bias gradients: dW[o][c] += sum_bw g_out[bw][o] * leaky(pooled[bw][c]) ; db[o] += sum_bw g_out[bw][o]
 __global__ void __launch_bounds__(256)
-rvsa_sampling_wgrad_kernel(const float* __restrict__ g_out, const float* __restrict__ pooled, float* __restrict__ dw_off,
-                           float* __restrict__ db_off, float* __restrict__ dw_sc, float* __restrict__ db_sc, float* __restrict__ dw_ang,
-                           float* __restrict__ db_ang, int n_bw, int nH, int C) {
+rvsa_sampling_bwd_kernel(const float* __restrict__ dparams, const float* __restrict__ pooled, const float* __restrict__ w_off,
+                         const float* __restrict__ w_sc, const float* __restrict__ w_ang, float* __restrict__ g_out,
+                         float* __restrict__ dpooled, const RvsaGeom g) {
   MTP_PDL_ENTRY();
-  const int o = blockIdx.y;                      // 0 .. 5nH-1
-  const int c = blockIdx.x * 256 + threadIdx.x;
+  rvsa_sampling_bwd_body(dparams, pooled, w_off, w_sc, w_ang, g_out, dpooled, g, (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// (2) weight / bias gradients: dW[o][c] += sum_bw g[bw][o] * leaky(pooled[bw][c]) ; db[o] += sum_bw g[bw][o], with g recomputed from dparams
+//     (so that this does not depend on kernel (1) and both can share a launch)
+__device__ __forceinline__ void rvsa_sampling_wgrad_body(const float* __restrict__ dparams, const float* __restrict__ pooled,
+                                                         float* __restrict__ dw_off, float* __restrict__ db_off, float* __restrict__ dw_sc,
+                                                         float* __restrict__ db_sc, float* __restrict__ dw_ang, float* __restrict__ db_ang,
+                                                         int n_bw, const RvsaGeom& g, int bx, int by) {
+  __shared__ float gw[256];
+  const int nH = g.nH, C = g.C;
+  const int o = by;                              // 0 .. 5nH-1
+  const int c = bx * 256 + threadIdx.x;
   float* dw; float* db; int oo;
   if (o < 2 * nH) { dw = dw_off; db = db_off; oo = o; }
   else if (o < 4 * nH) { dw = dw_sc; db = db_sc; oo = o - 2 * nH; }
   else { dw = dw_ang; db = db_ang; oo = o - 4 * nH; }
-  if (c < C) {
-    float s = 0.f;
-#pragma unroll 4
-    for (int bw = 0; bw < n_bw; ++bw) {
-      const float p = pooled[(size_t)bw * C + c];
-      s += g_out[(size_t)bw * 5 * nH + o] * (p >= 0.f ? p : 0.01f * p);
-    }
-    dw[(size_t)oo * C + c] += s;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    float s = 0.f;
+  float s = 0.f, sb = 0.f;
+  for (int bw0 = 0; bw0 < n_bw; bw0 += 256) {
+    const int nb = min(256, n_bw - bw0);
+    __syncthreads();
+    if ((int)threadIdx.x < nb) gw[threadIdx.x] = rvsa_sampling_gout(dparams, bw0 + threadIdx.x, o, nH, g);
+    __syncthreads();
+    if (c < C) {
 #pragma unroll 8
-    for (int bw = 0; bw < n_bw; ++bw) s += g_out[(size_t)bw * 5 * nH + o];
-    db[oo] += s;
+      for (int i = 0; i < nb; ++i) {
+        const float p = pooled[(size_t)(bw0 + i) * C + c];
+        s += gw[i] * (p >= 0.f ? p : 0.01f * p);
+      }
+    }
+    if (bx == 0 && threadIdx.x == 0)
+      for (int i = 0; i < nb; ++i) sb += gw[i];
   }
+  if (c < C) dw[(size_t)oo * C + c] += s;
+  if (bx == 0 && threadIdx.x == 0) db[oo] += sb;
+}
+__global__ void __launch_bounds__(256)
+rvsa_sampling_wgrad_kernel(const float* __restrict__ dparams, const float* __restrict__ pooled, float* __restrict__ dw_off,
+                           float* __restrict__ db_off, float* __restrict__ dw_sc, float* __restrict__ db_sc, float* __restrict__ dw_ang,
+                           float* __restrict__ db_ang, int n_bw, const RvsaGeom g) {
+  MTP_PDL_ENTRY();
+  rvsa_sampling_wgrad_body(dparams, pooled, dw_off, db_off, dw_sc, db_sc, dw_ang, db_ang, n_bw, g, (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// The four kernels that follow the attention backward -- finishing dK / dV (+ the qkv bias gradient), reducing the rel-pos / bias-table
+// partials, the sampling heads' input gradient and their weight gradients -- only depend on that kernel's outputs, not on each other, and
+// each is a short latency-bound launch (128 - 588 CTAs, 6 - 12 us): ONE launch, role by block range, lets them share the SMs and saves three
+// kernel boundaries per window block.
+struct RvsaTailArgs {
+  // kv finalize
+  float* dkv; __nv_bfloat16* dqkv; float* colsum; int T, C, rows_per_cta, rezero, kv_gx, kv_gy;
+  // partials reduce
+  const float* part_rel; const float* part_table; float* d_rel_h; float* d_rel_w; float* d_table; int n_rel_parts, n_bw, nH, n_pr;
+  // sampling heads
+  const float* dparams; const float* pooled; const float* w_off; const float* w_sc; const float* w_ang; float* dpooled;
+  float* dw_off; float* db_off; float* dw_sc; float* db_sc; float* dw_ang; float* db_ang; int sb_gy, wg_gx;
+  RvsaGeom g;
+};
+__global__ void __launch_bounds__(256)
+rvsa_bwd_tail_kernel(const __grid_constant__ RvsaTailArgs a) {
+  MTP_PDL_ENTRY();
+  int b = (int)blockIdx.x;
+  const int n_kv = a.kv_gx * a.kv_gy;
+  if (b < n_kv) { rvsa_kv_finalize_body(a.dkv, a.dqkv, a.colsum, a.T, a.C, a.rows_per_cta, a.rezero, b % a.kv_gx, b / a.kv_gx); return; }
+  b -= n_kv;
+  const int n_sb = a.n_bw * a.sb_gy;
+  if (b < n_sb) { rvsa_sampling_bwd_body(a.dparams, a.pooled, a.w_off, a.w_sc, a.w_ang, nullptr, a.dpooled, a.g, b % a.n_bw, b / a.n_bw); return; }
+  b -= n_sb;
+  const int n_wg = a.wg_gx * 5 * a.nH;
+  if (b < n_wg) { rvsa_sampling_wgrad_body(a.dparams, a.pooled, a.dw_off, a.db_off, a.dw_sc, a.db_sc, a.dw_ang, a.db_ang, a.n_bw, a.g, b % a.wg_gx, b / a.wg_gx); return; }
+  b -= n_wg;
+  rvsa_partials_reduce_body(a.part_rel, a.part_table, a.d_rel_h, a.d_rel_w, a.d_table, a.n_rel_parts, a.n_bw, a.nH, b);
 }
 
 // (1)+(2) in ONE launch: CTA = slab of 32 channels.  g (the gradient w.r.t. the 5nH raw conv outputs of every window), the slab of
@@ -630,6 +692,51 @@ extern "C" int mtp_rvsa_attn_bwd(const void* qkv_bf16, const float* params, cons
   return check_launch("rvsa_kv_finalize_kernel");
 }
 
+// Attention backward of a window block AND the sampling heads' backward in three launches (scratch memset, the attention kernel, the fused tail):
+// the caller gets dqkv (complete, incl. d_qkv_bias), dparams, the table / weight gradients accumulated, and dpooled [n_bw][C] (fp32) in
+// sampling_workspace at offset n_bw * 5 * nH floats for mtp_layernorm_bwd(pool_add).  Same arithmetic as mtp_rvsa_attn_bwd + mtp_rvsa_sampling_bwd.
+extern "C" int mtp_rvsa_attn_bwd_fused(const void* qkv_bf16, const float* params, const float* rel_pos_h, const float* rel_pos_w,
+                                       const float* bias_table, const float* lse, const void* dout_bf16, void* dqkv_bf16, float* dparams,
+                                       float* d_rel_pos_h, float* d_rel_pos_w, float* d_bias_table, float* d_qkv_bias, void* workspace,
+                                       const float* pooled, const float* w_off, const float* w_scale, const float* w_angle, float* dw_off,
+                                       float* db_off, float* dw_scale, float* db_scale, float* dw_angle, float* db_angle,
+                                       void* sampling_workspace, int B, int h, int w, int C, int nH, mtp_stream_t stream) {
+  MTP_REQUIRE(qkv_bf16 && params && rel_pos_h && rel_pos_w && bias_table && lse && dout_bf16 && dqkv_bf16 && dparams && d_rel_pos_h &&
+                  d_rel_pos_w && d_bias_table && workspace && pooled && w_off && w_scale && w_angle && dw_off && db_off && dw_scale &&
+                  db_scale && dw_angle && db_angle && sampling_workspace, "mtp_rvsa_attn_bwd_fused: null pointer");
+  MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && nH % 2 == 0 && nH <= 64, "mtp_rvsa_attn_bwd_fused: B=%d h=%d w=%d C=%d nH=%d unsupported",
+              B, h, w, C, nH);
+  const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n_cta = B * g.nh * g.nw * nH, n_bw = n_cta / nH;
+  float* part_rel = reinterpret_cast<float*>(workspace);
+  float* part_table = part_rel + (size_t)n_cta * (2 * (2 * WS - 1) * HD);
+  float* dkv = part_table + (size_t)n_cta * 169;
+  const size_t T = (size_t)B * h * w;
+  cudaError_t e = cudaMemsetAsync(dkv, 0, T * 2 * C * sizeof(float), st);
+  if (e != cudaSuccess) return set_error(MTP_ERR_CUDA, "rvsa bwd memset: %s", cudaGetErrorString(e));
+  int rc = launch_rvsa_attn_bwd_tc(qkv_bf16, params, rel_pos_h, rel_pos_w, bias_table, lse, dout_bf16, dqkv_bf16, dkv, dparams, part_rel, part_table,
+                                   g, st);
+  if (rc) return rc;
+  RvsaTailArgs a;
+  a.dkv = dkv; a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16); a.colsum = d_qkv_bias; a.T = (int)T; a.C = C; a.rezero = 0;
+  a.kv_gx = ceil_div(3 * C, 1024);
+  const int gy = std::max(1, std::min(ceil_div((int)T, 8), 4 * num_sms() / a.kv_gx));
+  a.rows_per_cta = ceil_div((int)T, gy);
+  a.kv_gy = ceil_div((int)T, a.rows_per_cta);
+  a.part_rel = part_rel; a.part_table = part_table; a.d_rel_h = d_rel_pos_h; a.d_rel_w = d_rel_pos_w; a.d_table = d_bias_table;
+  a.n_rel_parts = n_cta / 2; a.n_bw = n_bw; a.nH = nH;
+  a.n_pr = 2 * (2 * WS - 1) * HD / 32 + nH * ((169 + 31) / 32);
+  a.dparams = dparams; a.pooled = pooled; a.w_off = w_off; a.w_sc = w_scale; a.w_ang = w_angle;
+  a.dpooled = reinterpret_cast<float*>(sampling_workspace) + (size_t)n_bw * 5 * nH;
+  a.dw_off = dw_off; a.db_off = db_off; a.dw_sc = dw_scale; a.db_sc = db_scale; a.dw_ang = dw_angle; a.db_ang = db_angle;
+  a.sb_gy = ceil_div(C, 256); a.wg_gx = ceil_div(C, 256);
+  a.g = g;
+  const int grid = a.kv_gx * a.kv_gy + n_bw * a.sb_gy + a.wg_gx * 5 * nH + a.n_pr;
+  (void)launch_k(rvsa_bwd_tail_kernel, grid, 256, 0, st, a);
+  return check_launch("rvsa_bwd_tail_kernel");
+}
+
 extern "C" int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, const float* w_off, const float* w_scale,
                                      const float* w_angle, float* dw_off, float* db_off, float* dw_scale, float* db_scale,
                                      float* dw_angle, float* db_angle, void* dyn_bf16, void* workspace, int B, int h, int w, int C,
@@ -662,8 +769,8 @@ extern "C" int mtp_rvsa_sampling_bwd(const float* dparams, const float* pooled, 
   (void)launch_k(rvsa_sampling_bwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, dparams, pooled, w_off, w_scale, w_angle, g_out, dpooled, g);
   int rc = check_launch("rvsa_sampling_bwd_kernel");
   if (rc) return rc;
-  (void)launch_k(rvsa_sampling_wgrad_kernel, dim3(ceil_div(C, 256), 5 * nH), 256, 0, st, g_out, pooled, dw_off, db_off, dw_scale, db_scale, dw_angle,
-                                                                             db_angle, n_bw, nH, C);
+  (void)launch_k(rvsa_sampling_wgrad_kernel, dim3(ceil_div(C, 256), 5 * nH), 256, 0, st, dparams, pooled, dw_off, db_off, dw_scale, db_scale, dw_angle,
+                 db_angle, n_bw, g);
   rc = check_launch("rvsa_sampling_wgrad_kernel");
   if (rc || dyn_bf16 == nullptr) return rc;      // no dyn: the caller hands dpooled (workspace + n_bw*5*nH floats) to mtp_layernorm_bwd
   const size_t total = (size_t)B * h * w * (C / 4);

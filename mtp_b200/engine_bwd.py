@@ -19,6 +19,7 @@ from . import _lib as L
 from . import engine, ops
 
 BF16, F32 = torch.bfloat16, torch.float32
+_TAIL_FUSE = os.environ.get("MTP_TAIL_FUSE", "1") != "0"      # A/B: the fused follow-up launch of the window blocks' backward
 _POOL_FUSE = os.environ.get("MTP_POOL_FUSE", "1") != "0"      # A/B switch: 0 = separate rvsa_pool_bwd_add kernel
 
 
@@ -80,7 +81,18 @@ def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
     dx1, g1 = ops.layernorm_bwd(dy2, s["x1"], s["mean2"], s["rstd2"], d["norm2_w"], None, dx2, G.g(pre + "norm2.weight"),
                                 G.g(pre + "norm2.bias"), cast=(ka, N, G.g(pre + "attn.proj.bias")))
     do = _linear_bwd(g1, s["o"], d["proj_w"], G.g(pre + "attn.proj.weight"), T, C, C, sumsq=G.sumsq)
-    if d["window"]:
+    pool = None
+    fused_tail = d["window"] and _POOL_FUSE and _TAIL_FUSE and nH % 2 == 0
+    if fused_tail:      # attention backward + sampling heads' backward; their four follow-up kernels share one launch
+        a = pre + "attn.sampling_"
+        dqkv, dpooled = ops.rvsa_attn_bwd_fused(s["qkv"], s["params"], d["rel_h"], d["rel_w"], d["table"], s["lse"], do,
+                                                G.g(pre + "attn.rel_pos_h"), G.g(pre + "attn.rel_pos_w"),
+                                                G.g(pre + "attn.relative_position_bias_table"), G.g(pre + "attn.qkv.bias"),
+                                                s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],
+                                                G.g(a + "offsets.2.weight"), G.g(a + "offsets.2.bias"), G.g(a + "scales.2.weight"),
+                                                G.g(a + "scales.2.bias"), G.g(a + "angles.2.weight"), G.g(a + "angles.2.bias"), B, gh, gw, nH)
+        pool = (dpooled, gh, gw)
+    elif d["window"]:
         dqkv, dparams = ops.rvsa_attn_bwd(s["qkv"], s["params"], d["rel_h"], d["rel_w"], d["table"], s["lse"], do,
                                           G.g(pre + "attn.rel_pos_h"), G.g(pre + "attn.rel_pos_w"),
                                           G.g(pre + "attn.relative_position_bias_table"), B, gh, gw, nH,
@@ -91,8 +103,7 @@ def _block_backward(i, d, s, dx2, g2, G, B, gh, gw, nH, keep, nxt=None):
                                  G.g(pre + "attn.full_attn_rel_pos_h") if has_rel else None,
                                  G.g(pre + "attn.full_attn_rel_pos_w") if has_rel else None, B, gh, gw, nH)
         ops.colsum_bf16(dqkv, G.g(pre + "attn.qkv.bias"))
-    pool = None
-    if d["window"] and _POOL_FUSE:        # the sampling heads' backward only needs dparams: it runs BEFORE the qkv GEMMs (light kernels after
+    if d["window"] and _POOL_FUSE and not fused_tail:        # the sampling heads' backward only needs dparams: it runs BEFORE the qkv GEMMs (light kernels after
         #                                   light kernels); its pooled (AvgPool) path joins dy1 inside the LayerNorm backward
         a = pre + "attn.sampling_"
         dpooled = ops.rvsa_sampling_bwd(dparams, s["pooled"], d["off_w"], d["sc_w"], d["ang_w"],

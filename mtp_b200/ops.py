@@ -215,6 +215,26 @@ def rvsa_attn_bwd(qkv, params, rel_h, rel_w, table, lse, dout, d_rel_h, d_rel_w,
     return dqkv, dparams
 
 
+def rvsa_attn_bwd_fused(qkv, params, rel_h, rel_w, table, lse, dout, d_rel_h, d_rel_w, d_table, d_qkv_bias, pooled, w_off, w_sc, w_ang,
+                        dw_off, db_off, dw_sc, db_sc, dw_ang, db_ang, B, h, w, nH):
+    """rvsa_attn_bwd + rvsa_sampling_bwd(dyn=None) with their follow-up kernels in one launch; returns (dqkv, dpooled [B*nWin, C] fp32)."""
+    C = qkv.shape[-1] // 3
+    dqkv = torch.empty_like(qkv)
+    dparams = torch.empty_like(params)
+    lib = L.load()
+    n1 = lib.mtp_rvsa_bwd_workspace_bytes(B, h, w, C, nH)
+    n2 = lib.mtp_rvsa_sampling_bwd_workspace_bytes(B, h, w, C, nH)
+    n1 = (n1 + 255) // 256 * 256
+    ws = _workspace(n1 + n2, qkv.device)
+    L.call("mtp_rvsa_attn_bwd_fused", qkv.data_ptr(), params.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(), table.data_ptr(), lse.data_ptr(),
+           dout.data_ptr(), dqkv.data_ptr(), dparams.data_ptr(), d_rel_h.data_ptr(), d_rel_w.data_ptr(), d_table.data_ptr(), _p(d_qkv_bias),
+           ws.data_ptr(), pooled.data_ptr(), w_off.data_ptr(), w_sc.data_ptr(), w_ang.data_ptr(), dw_off.data_ptr(), db_off.data_ptr(),
+           dw_sc.data_ptr(), db_sc.data_ptr(), dw_ang.data_ptr(), db_ang.data_ptr(), ws.data_ptr() + n1, B, h, w, C, nH, _stream())
+    n_bw = pooled.shape[0]
+    sws = ws[n1 // 4:]      # fp32 workspace: the sampling part starts n1 bytes in
+    return dqkv, sws[n_bw * 5 * nH: n_bw * 5 * nH + n_bw * C].view(n_bw, C)
+
+
 def rvsa_sampling_bwd(dparams, pooled, w_off, w_sc, w_ang, dw_off, db_off, dw_sc, db_sc, dw_ang, db_ang, dyn, B, h, w, nH):
     """``dyn=None``: returns dpooled [B*nWin, C] (fp32) for ``layernorm_bwd(pool_add=...)`` instead of adding it into dyn."""
     C = pooled.shape[-1]

@@ -188,6 +188,25 @@ def test_rvsa_backward_vs_oracle_autograd(grid, B, nH, big):
         errs[k + "_b"] = _close(gb[k].cpu(), Pl[f"a.sampling_{k}.2.bias"].grad, 1.5e-2, f"d sampling_{k}.bias")
     errs["dyn"] = _close(dyn.float().cpu().reshape(B, N, C), xn.grad, 1.5e-2, "pooled-path grad")
     print("rvsa bwd", grid, {k: "%.1e" % v for k, v in errs.items()})
+    # the fused form (one launch for the four follow-up kernels) computes the same thing: compare against the separate launches above
+    f_rel_h, f_rel_w, f_table, f_bias = z(rel_h), z(rel_w), z(table), torch.zeros(3 * C, device="cuda")
+    fw = {k: z(v) for k, v in w.items()}
+    fb = {k: torch.zeros(v.shape[0], device="cuda") for k, v in w.items()}
+    dqkv_f, dpooled_f = ops.rvsa_attn_bwd_fused(qkv_d, params, rel_h, rel_w, table, lse, d(gout.reshape(-1, C)).to(torch.bfloat16),
+                                                f_rel_h, f_rel_w, f_table, f_bias, pooled, w["offsets"], w["scales"], w["angles"],
+                                                fw["offsets"], fb["offsets"], fw["scales"], fb["scales"], fw["angles"], fb["angles"], B, grid, grid, nH)
+    dpooled_s = ops.rvsa_sampling_bwd(dparams, pooled, w["offsets"], w["scales"], w["angles"], z(w["offsets"]), z(gb["offsets"]), z(w["scales"]),
+                                      z(gb["scales"]), z(w["angles"]), z(gb["angles"]), None, B, grid, grid, nH).clone()
+    torch.cuda.synchronize()
+
+    def same(a, b, what, tol=2e-3):          # the fp32 scatter sums are accumulated with atomics: order-dependent in the last bits
+        assert (a.float() - b.float()).norm().item() <= tol * max(b.float().norm().item(), 1e-6), what
+    same(dqkv_f, dqkv, "fused dqkv")
+    same(f_rel_h, g_rel_h, "fused d rel_pos_h"); same(f_rel_w, g_rel_w, "fused d rel_pos_w"); same(f_table, g_table, "fused d table")
+    same(f_bias, g_qkv_bias, "fused d qkv bias")
+    for k in ("offsets", "scales", "angles"):
+        same(fw[k], gw[k], f"fused d sampling_{k}.weight"); same(fb[k], gb[k], f"fused d sampling_{k}.bias")
+    same(dpooled_f, dpooled_s, "fused dpooled")
 
 
 @pytest.mark.parametrize("grid,B,nH,rel", [(14, 2, 2, True), (10, 1, 3, True), (14, 1, 2, False), (16, 1, 2, True), (13, 1, 2, True), (20, 1, 2, True), (14, 2, 16, True),
