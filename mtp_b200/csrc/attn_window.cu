@@ -137,115 +137,24 @@ rvsa_sampling_fused_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float
   if (c < C) {
     // all 13 row loads of this thread are issued before the first one is consumed (written as load-then-accumulate per row the compiler kept
     // them in program order: 13 serialised L2 round trips, the bulk of the kernel's 14 us)
-  part[tg][cq] = s;
-  __syncthreads();
-  if (tg == 0 && c < g.C) {
-    const float4 p1 = part[1][cq], p2 = part[2][cq], p3 = part[3][cq];
-    const float inv = 1.0f / (WS * WS);                    // zeros of the padding are part of the mean ([V]:347,354)
-    s.x = (s.x + p1.x + p2.x + p3.x) * inv; s.y = (s.y + p1.y + p2.y + p3.y) * inv;
-    s.z = (s.z + p1.z + p2.z + p3.z) * inv; s.w = (s.w + p1.w + p2.w + p3.w) * inv;
-    *reinterpret_cast<float4*>(pooled + (size_t)bw * g.C + c) = s;
-  }
-}
-
-// (2) the three 1x1 convs on LeakyReLU(pooled): CTA = one of the 5nH output channels, its weight row kept in registers,
-//     warps stride over the (image, window) rows
-__global__ void __launch_bounds__(256)
-rvsa_heads_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w_off, const float* __restrict__ b_off,
-                      const float* __restrict__ w_sc, const float* __restrict__ b_sc, const float* __restrict__ w_ang,
-                      const float* __restrict__ b_ang, float* __restrict__ params, int n_bw, const RvsaGeom g) {
-  MTP_PDL_ENTRY();
-  const int o = blockIdx.x, nH = g.nH, C = g.C;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // output order: [0,2nH) offsets (head-major, x then y), [2nH,4nH) scales, [4nH,5nH) angle
-  const float* wrow;
-  float bias;
-  int n, slot;
-  float div = 1.0f;
-  if (o < 2 * nH) { wrow = w_off + (size_t)o * C; bias = b_off[o]; n = o >> 1; slot = o & 1; div = (float)((slot == 0 ? g.h : g.w) / WS); }   // sic: x by h//7, y by w//7
-  else if (o < 4 * nH) { wrow = w_sc + (size_t)(o - 2 * nH) * C; bias = b_sc[o - 2 * nH]; n = (o - 2 * nH) >> 1; slot = 2 + ((o - 2 * nH) & 1); }
-  else { wrow = w_ang + (size_t)(o - 4 * nH) * C; bias = b_ang[o - 4 * nH]; n = o - 4 * nH; slot = 4; }
-  float4 wv[8];                                           // C <= 1024: 8 float4 per lane
-#pragma unroll
-  for (int i = 0; i < 8; ++i) wv[i] = (i * 128 + lane * 4 < C) ? __ldg(reinterpret_cast<const float4*>(wrow + i * 128 + lane * 4)) : make_float4(0, 0, 0, 0);
-  for (int bw = warp; bw < n_bw; bw += 8) {
-    const float* pr = pooled + (size_t)bw * C;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i * 128 + lane * 4 < C) {
-        float4 a = *reinterpret_cast<const float4*>(pr + i * 128 + lane * 4);
-        a.x = a.x >= 0 ? a.x : 0.01f * a.x; a.y = a.y >= 0 ? a.y : 0.01f * a.y;
-        a.z = a.z >= 0 ? a.z : 0.01f * a.z; a.w = a.w >= 0 ? a.w : 0.01f * a.w;
-        s += wv[i].x * a.x + wv[i].y * a.y + wv[i].z * a.z + wv[i].w * a.w;
-      }
-    }
-    s = warp_sum(s) + bias;
-    if (lane == 0) params[((size_t)bw * nH + n) * 8 + slot] = s / div;
-    if (slot == 4 && lane >= 1 && lane < 4) params[((size_t)bw * nH + n) * 8 + 4 + lane] = 0.f;      // unused slots 5..7
-  }
-}
-
-// (1)+(2) in ONE launch: CTA = (image-window, group of 16 output channels), 1024 threads.  Every CTA of a window recomputes the window's
-// pooled vector (49 token rows of <= 2 KB, all 13 loads of a thread in flight: the whole phase is one memory round trip), then two warps
-// per output channel take half of the dot product each.  Replaces a 128-CTA pooling launch + an 80-CTA GEMV launch whose in-situ cost was
-// 23 us per block (tools/step_breakdown.py) for ~0.2 MFLOP.
-constexpr int SF_THREADS = 1024, SF_OUT = 16;
-__global__ void __launch_bounds__(SF_THREADS)
-rvsa_sampling_fused_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float* __restrict__ w_off, const float* __restrict__ b_off,
-                               const float* __restrict__ w_sc, const float* __restrict__ b_sc, const float* __restrict__ w_ang,
-                               const float* __restrict__ b_ang, float* __restrict__ pooled, float* __restrict__ params, const RvsaGeom g,
-                               int ld, int lo) {
-  MTP_PDL_ENTRY();
-  __shared__ float4 part[4][256];
-  __shared__ float pooled_s[1024];
-  __shared__ float half_s[SF_OUT];
-  const int bw = blockIdx.x;
-  const int b = bw / (g.nh * g.nw), win = bw % (g.nh * g.nw);
-  const int wy = win / g.nw, wx = win % g.nw;
-  const int tid = threadIdx.x, tg = tid >> 8, cq = tid & 255;
-  const int c = cq * 4, C = g.C, nH = g.nH;
-  // ---- the three 1x1 convs: output order [0,2nH) offsets (head-major, x then y), [2nH,4nH) scales, [4nH,5nH) angle
-  const int warp = tid >> 5, lane = tid & 31;
-  const int k = warp >> 1, hf = warp & 1;
-  const int o = blockIdx.y * SF_OUT + k;
-  const bool live = o < 5 * nH;
-  const float* wrow = nullptr;
-  float bias = 0.f, div = 1.0f;
-  int n = 0, slot = 0;
-  if (live) {
-    if (o < 2 * nH) { wrow = w_off + (size_t)o * C; bias = b_off[o]; n = o >> 1; slot = o & 1; div = (float)((slot == 0 ? g.h : g.w) / WS); }   // sic: x by h//7, y by w//7
-    else if (o < 4 * nH) { wrow = w_sc + (size_t)(o - 2 * nH) * C; bias = b_sc[o - 2 * nH]; n = (o - 2 * nH) >> 1; slot = 2 + ((o - 2 * nH) & 1); }
-    else { wrow = w_ang + (size_t)(o - 4 * nH) * C; bias = b_ang[o - 4 * nH]; n = o - 4 * nH; slot = 4; }
-  }
-  float4 wv[4];      // this lane's 16 weights of output channel o (half hf of the row), requested before the pooling so their latency overlaps it
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int cc = hf * 512 + i * 128 + lane * 4;
-    wv[i] = (live && cc < C) ? __ldg(reinterpret_cast<const float4*>(wrow + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float4 s = make_float4(0, 0, 0, 0);
-  if (c < C) {
-    // all 13 row loads of this thread are issued before the first one is consumed (written as load-then-accumulate per row the compiler kept
-    // them in program order: 13 serialised L2 round trips, the bulk of the kernel's 14 us)
     constexpr int NR = (WS * WS + 3) / 4;
     uint2 v[NR], vl[NR];
     const __nv_bfloat16* org = yn + c;
 #pragma unroll
-    for (int k = 0; k < NR; ++k) {
-      const int i = tg + 4 * k;
+    for (int kk = 0; kk < NR; ++kk) {
+      const int i = tg + 4 * kk;
       const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
       const bool ok = i < WS * WS && y >= 0 && y < g.h && x >= 0 && x < g.w;
       const __nv_bfloat16* src = org + ((size_t)(b * g.h + (ok ? y : 0)) * g.w + (ok ? x : 0)) * ld;
-      v[k] = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);
-      vl[k] = (ok && lo > 0) ? __ldg(reinterpret_cast<const uint2*>(src + lo)) : make_uint2(0u, 0u);
+      v[kk] = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);
+      vl[kk] = (ok && lo > 0) ? __ldg(reinterpret_cast<const uint2*>(src + lo)) : make_uint2(0u, 0u);
     }
 #pragma unroll
-    for (int k = 0; k < NR; ++k) {
-      const float2 a = unpack_bf16x2(v[k].x), d = unpack_bf16x2(v[k].y);
+    for (int kk = 0; kk < NR; ++kk) {
+      const float2 a = unpack_bf16x2(v[kk].x), d = unpack_bf16x2(v[kk].y);
       s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
       if (lo > 0) {
-        const float2 al = unpack_bf16x2(vl[k].x), dl = unpack_bf16x2(vl[k].y);
+        const float2 al = unpack_bf16x2(vl[kk].x), dl = unpack_bf16x2(vl[kk].y);
         s.x += al.x; s.y += al.y; s.z += dl.x; s.w += dl.y;
       }
     }
