@@ -127,37 +127,30 @@ rvsa_sampling_fused_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float
     else if (o < 4 * nH) { wrow = w_sc + (size_t)(o - 2 * nH) * C; bias = b_sc[o - 2 * nH]; n = (o - 2 * nH) >> 1; slot = 2 + ((o - 2 * nH) & 1); }
     else { wrow = w_ang + (size_t)(o - 4 * nH) * C; bias = b_ang[o - 4 * nH]; n = o - 4 * nH; slot = 4; }
   }
-  float4 wv[4];      // this lane's 16 weights of output channel o (half hf of the row), requested before the pooling so their latency overlaps it
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int cc = hf * 512 + i * 128 + lane * 4;
-    wv[i] = (live && cc < C) ? __ldg(reinterpret_cast<const float4*>(wrow + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   float4 s = make_float4(0, 0, 0, 0);
   if (c < C) {
     // all 13 row loads of this thread are issued before the first one is consumed (written as load-then-accumulate per row the compiler kept
     // them in program order: 13 serialised L2 round trips, the bulk of the kernel's 14 us)
     constexpr int NR = (WS * WS + 3) / 4;
-    uint2 v[NR], vl[NR];
     const __nv_bfloat16* org = yn + c;
-#pragma unroll
-    for (int kk = 0; kk < NR; ++kk) {
-      const int i = tg + 4 * kk;
-      const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;
-      const bool ok = i < WS * WS && y >= 0 && y < g.h && x >= 0 && x < g.w;
-      const __nv_bfloat16* src = org + ((size_t)(b * g.h + (ok ? y : 0)) * g.w + (ok ? x : 0)) * ld;
-      v[kk] = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);
-      vl[kk] = (ok && lo > 0) ? __ldg(reinterpret_cast<const uint2*>(src + lo)) : make_uint2(0u, 0u);
+#define MTP_POOL_PASS(OFF)                                                                                        \
+    {                                                                                                               \
+      uint2 v[NR];                                                                                                  \
+      _Pragma("unroll") for (int kk = 0; kk < NR; ++kk) {                                                           \
+        const int i = tg + 4 * kk;                                                                                  \
+        const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;                                         \
+        const bool ok = i < WS * WS && y >= 0 && y < g.h && x >= 0 && x < g.w;                                      \
+        const __nv_bfloat16* src = org + ((size_t)(b * g.h + (ok ? y : 0)) * g.w + (ok ? x : 0)) * ld + (OFF);      \
+        v[kk] = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);                               \
+      }                                                                                                             \
+      _Pragma("unroll") for (int kk = 0; kk < NR; ++kk) {                                                           \
+        const float2 a = unpack_bf16x2(v[kk].x), d = unpack_bf16x2(v[kk].y);                                        \
+        s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;                                                             \
+      }                                                                                                             \
     }
-#pragma unroll
-    for (int kk = 0; kk < NR; ++kk) {
-      const float2 a = unpack_bf16x2(v[kk].x), d = unpack_bf16x2(v[kk].y);
-      s.x += a.x; s.y += a.y; s.z += d.x; s.w += d.y;
-      if (lo > 0) {
-        const float2 al = unpack_bf16x2(vl[kk].x), dl = unpack_bf16x2(vl[kk].y);
-        s.x += al.x; s.y += al.y; s.z += dl.x; s.w += dl.y;
-      }
-    }
+    MTP_POOL_PASS(0)
+    if (lo > 0) MTP_POOL_PASS(lo)      // the lo words of the fp32-class mode
+#undef MTP_POOL_PASS
   }
   part[tg][cq] = s;
   __syncthreads();
@@ -170,7 +163,7 @@ rvsa_sampling_fused_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float
     *reinterpret_cast<float4*>(pooled_s + c) = s;
   }
   __syncthreads();
-  // ---- the three 1x1 convs on LeakyReLU(pooled) (weight rows were requested at kernel entry)
+  // ---- the three 1x1 convs on LeakyReLU(pooled)
   float acc = 0.f;
   if (live) {
     const int cbeg = hf * 512;
@@ -178,7 +171,7 @@ rvsa_sampling_fused_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float
     for (int i = 0; i < 4; ++i) {
       const int cc = cbeg + i * 128 + lane * 4;
       if (cc < C) {
-        const float4 w4 = wv[i];
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + cc));
         float4 a = *reinterpret_cast<const float4*>(pooled_s + cc);
         a.x = a.x >= 0 ? a.x : 0.01f * a.x; a.y = a.y >= 0 ? a.y : 0.01f * a.y;
         a.z = a.z >= 0 ? a.z : 0.01f * a.z; a.w = a.w >= 0 ? a.w : 0.01f * a.w;
