@@ -59,7 +59,10 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     const int row = rr < 15 ? NTOK + rr : 64 + NTOK + (rr - 15);
     *reinterpret_cast<uint4*>(Qs + tile * WTC_TILE + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
   }
-  for (int i = tid; i < 2 * 13 * 64; i += WTC_THREADS) relt[i] = i < 13 * 64 ? rel_h[i] : rel_w[i - 13 * 64];
+  for (int i = tid; i < 2 * 13 * 64; i += WTC_THREADS) {      // chunk-swizzled rows (tab_chunk_off): lanes of a warp read different rows
+    const int t = i / (13 * 64), r = (i % (13 * 64)) >> 6, d = i & 63;
+    relt[t * 13 * 64 + tab_chunk_off(r, d >> 2) + (d & 3)] = t == 0 ? rel_h[i] : rel_w[i - 13 * 64];
+  }
   for (int i = tid; i < 2 * 169; i += WTC_THREADS) tabs[i] = bias_table[(i % 169) * g.nH + 2 * hp + i / 169];
   if (tid < 98) {
     const int p = tid / NTOK, j = tid % NTOK;
@@ -153,8 +156,9 @@ rvsa_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w4[t]); qv[2 * t] = f.x; qv[2 * t + 1] = f.y; }
 #pragma unroll
       for (int k = 0; k < WS; ++k) {
-        const float4* th = reinterpret_cast<const float4*>(tbase + (qq - k + WS - 1) * HD + c * 8);
-        const float4 h0 = th[0], h1 = th[1];
+        const int tr = qq - k + WS - 1;
+        const float4 h0 = *reinterpret_cast<const float4*>(tbase + tab_chunk_off(tr, 2 * c));
+        const float4 h1 = *reinterpret_cast<const float4*>(tbase + tab_chunk_off(tr, 2 * c + 1));
         rh[k] += qv[0] * h0.x + qv[1] * h0.y + qv[2] * h0.z + qv[3] * h0.w + qv[4] * h1.x + qv[5] * h1.y + qv[6] * h1.z + qv[7] * h1.w;
       }
     }

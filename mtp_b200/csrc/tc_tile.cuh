@@ -30,6 +30,12 @@ __device__ __forceinline__ void tc_mma_tiles(uint32_t d_tmem, uint32_t a_base, u
   }
 }
 
+
+// fp32 [rows][64] tables in shared memory read as float4 by lanes that index DIFFERENT rows (rel-pos tables: the row depends on the lane's
+// token): with a 256-byte row pitch every row starts in bank 0 and a quarter warp serialises.  16-byte chunk c of row r is stored at chunk
+// c ^ (r & 7) instead (no padding: the RVSA backward has 104 bytes of shared memory to spare).  Returns the float offset of chunk c of row r.
+__device__ __forceinline__ int tab_chunk_off(int r, int c) { return r * 64 + ((c ^ (r & 7)) << 2); }
+
 // zero a region of shared memory cooperatively (bytes multiple of 16)
 __device__ __forceinline__ void smem_zero(void* p, int bytes, int tid, int nthreads) {
   uint4* q = reinterpret_cast<uint4*>(p);
