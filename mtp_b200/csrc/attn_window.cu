@@ -127,21 +127,27 @@ rvsa_sampling_fused_fwd_kernel(const __nv_bfloat16* __restrict__ yn, const float
     else if (o < 4 * nH) { wrow = w_sc + (size_t)(o - 2 * nH) * C; bias = b_sc[o - 2 * nH]; n = (o - 2 * nH) >> 1; slot = 2 + ((o - 2 * nH) & 1); }
     else { wrow = w_ang + (size_t)(o - 4 * nH) * C; bias = b_ang[o - 4 * nH]; n = o - 4 * nH; slot = 4; }
   }
+  // element offsets of the window's 49 token rows (-1: padding), computed once per CTA: the per-row index arithmetic (two divisions by 7, bounds,
+  // a 64-bit multiply) was most of the kernel's instructions (ncu: 860 per warp, issue slots 56 % busy)
+  __shared__ int rowoff_s[52];
+  if (tid < 52) {
+    const int y = wy * WS + tid / WS - g.pt, x = wx * WS + tid % WS - g.pl;
+    const bool ok = tid < WS * WS && y >= 0 && y < g.h && x >= 0 && x < g.w;
+    rowoff_s[tid] = ok ? ((b * g.h + y) * g.w + x) * ld : -1;      // < 2^31 elements (B * h * w * ld)
+  }
+  __syncthreads();
   float4 s = make_float4(0, 0, 0, 0);
   if (c < C) {
     // all 13 row loads of this thread are issued before the first one is consumed (written as load-then-accumulate per row the compiler kept
-    // them in program order: 13 serialised L2 round trips, the bulk of the kernel's 14 us)
+    // them in program order: 13 serialised L2 round trips)
     constexpr int NR = (WS * WS + 3) / 4;
     const __nv_bfloat16* org = yn + c;
 #define MTP_POOL_PASS(OFF)                                                                                        \
     {                                                                                                               \
       uint2 v[NR];                                                                                                  \
       _Pragma("unroll") for (int kk = 0; kk < NR; ++kk) {                                                           \
-        const int i = tg + 4 * kk;                                                                                  \
-        const int y = wy * WS + i / WS - g.pt, x = wx * WS + i % WS - g.pl;                                         \
-        const bool ok = i < WS * WS && y >= 0 && y < g.h && x >= 0 && x < g.w;                                      \
-        const __nv_bfloat16* src = org + ((size_t)(b * g.h + (ok ? y : 0)) * g.w + (ok ? x : 0)) * ld + (OFF);      \
-        v[kk] = ok ? __ldg(reinterpret_cast<const uint2*>(src)) : make_uint2(0u, 0u);                               \
+        const int off = rowoff_s[tg + 4 * kk];                                                                      \
+        v[kk] = off >= 0 ? __ldg(reinterpret_cast<const uint2*>(org + off + (OFF))) : make_uint2(0u, 0u);           \
       }                                                                                                             \
       _Pragma("unroll") for (int kk = 0; kk < NR; ++kk) {                                                           \
         const float2 a = unpack_bf16x2(v[kk].x), d = unpack_bf16x2(v[kk].y);                                        \
@@ -423,7 +429,8 @@ extern "C" int mtp_rvsa_sampling_fwd(const void* yn_bf16, const float* w_off, co
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && C <= 1024, "mtp_rvsa_sampling_fwd: B=%d h=%d w=%d C=%d nH=%d unsupported (need h,w>=7, C==64*nH<=1024)", B, h, w, C, nH);
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if ((sampling_fused_mask() & 1)) return launch_rvsa_sampling_fused_fwd(yn_bf16, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, C, 0, st);
+  if ((sampling_fused_mask() & 1) && (size_t)B * h * w * C < ((size_t)1 << 31))      // the fused kernel keeps 32-bit row offsets
+    return launch_rvsa_sampling_fused_fwd(yn_bf16, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, C, 0, st);
   const int n_bw = B * g.nh * g.nw;
   (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_bf16), pooled, g, C, 0);
   int rc = check_launch("rvsa_pool_fwd_kernel");
@@ -452,7 +459,8 @@ extern "C" int mtp_rvsa_sampling_fwd_hilo(const void* yn_hilo, const float* w_of
   MTP_REQUIRE(B > 0 && h >= WS && w >= WS && C == nH * HD && C <= 1024, "mtp_rvsa_sampling_fwd_hilo: unsupported geometry");
   const RvsaGeom g = make_rvsa_geom(B, h, w, C, nH);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if ((sampling_fused_mask() & 1)) return launch_rvsa_sampling_fused_fwd(yn_hilo, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, 2 * C, C, st);
+  if ((sampling_fused_mask() & 1) && (size_t)B * h * w * 2 * C < ((size_t)1 << 31))
+    return launch_rvsa_sampling_fused_fwd(yn_hilo, w_off, b_off, w_scale, b_scale, w_angle, b_angle, pooled, params, g, 2 * C, C, st);
   const int n_bw = B * g.nh * g.nw;
   (void)launch_k(rvsa_pool_fwd_kernel, dim3(n_bw, ceil_div(C, 256)), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(yn_hilo), pooled, g, 2 * C, C);
   int rc = check_launch("rvsa_pool_fwd_kernel");
