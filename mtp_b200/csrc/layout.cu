@@ -145,6 +145,82 @@ nchw_to_tok_kernel(const TIn* __restrict__ in, TOut* __restrict__ tok, int ld, c
   }
 }
 
+// bf16 -> bf16, 16-byte accesses on both sides (the 56 x 56 pyramid maps are 51 MB each way; the scalar 32 x 32 transposes above spend 22
+// thread instructions per element and run at 1.8 TB/s).  CTA = (b, Y, 32 X, 64 channels), 256 threads: the token side moves 8 channels per
+// thread (one X), the NCHW side 8 X per thread (one channel); the tile goes through shared memory as 32-bit words [64 c][33]: the token-side
+// accesses are 2-way, the NCHW-side accesses conflict-free.  Needs Wo % 8 == 0 and C % 64 == 0.
+__global__ void __launch_bounds__(256)
+tok_to_nchw_vec_kernel(const __nv_bfloat16* __restrict__ tok, int ld, __nv_bfloat16* __restrict__ out, const MapGeom g) {
+  MTP_PDL_ENTRY();
+  __shared__ uint32_t tile[64][33];
+  const int Ho = g.h << g.L, Wo = g.w << g.L;
+  const int x_tiles = ceil_div(Wo, 32);
+  const int xt = blockIdx.x % x_tiles, Y = blockIdx.x / x_tiles;
+  const int c0 = blockIdx.y * 64, b = blockIdx.z;
+  {
+    const int xi = threadIdx.x >> 3, ch = threadIdx.x & 7;      // X within the tile, 8-channel chunk
+    const int X = xt * 32 + xi;
+    if (X < Wo) {
+      size_t row; int cb;
+      map_index(g, b, Y, X, row, cb);
+      const uint4 u = *reinterpret_cast<const uint4*>(tok + row * ld + cb + c0 + ch * 8);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        tile[ch * 8 + 2 * k][xi] = w4[k] & 0xffffu;
+        tile[ch * 8 + 2 * k + 1][xi] = w4[k] >> 16;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int c = threadIdx.x >> 2, xq = threadIdx.x & 3;        // channel within the tile, group of 8 X
+    const int X0 = xt * 32 + xq * 8;
+    if (X0 < Wo) {                                               // Wo % 8 == 0: the group is all in or all out
+      uint32_t w4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w4[k] = tile[c][xq * 8 + 2 * k] | (tile[c][xq * 8 + 2 * k + 1] << 16);
+      *reinterpret_cast<uint4*>(out + (((size_t)b * g.C + c0 + c) * Ho + Y) * Wo + X0) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nchw_to_tok_vec_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ tok, int ld, const MapGeom g) {
+  MTP_PDL_ENTRY();
+  __shared__ uint32_t tile[64][33];
+  const int Ho = g.h << g.L, Wo = g.w << g.L;
+  const int x_tiles = ceil_div(Wo, 32);
+  const int xt = blockIdx.x % x_tiles, Y = blockIdx.x / x_tiles;
+  const int c0 = blockIdx.y * 64, b = blockIdx.z;
+  {
+    const int c = threadIdx.x >> 2, xq = threadIdx.x & 3;
+    const int X0 = xt * 32 + xq * 8;
+    if (X0 < Wo) {
+      const uint4 u = *reinterpret_cast<const uint4*>(in + (((size_t)b * g.C + c0 + c) * Ho + Y) * Wo + X0);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        tile[c][xq * 8 + 2 * k] = w4[k] & 0xffffu;
+        tile[c][xq * 8 + 2 * k + 1] = w4[k] >> 16;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int xi = threadIdx.x >> 3, ch = threadIdx.x & 7;
+    const int X = xt * 32 + xi;
+    if (X < Wo) {
+      size_t row; int cb;
+      map_index(g, b, Y, X, row, cb);
+      uint32_t w4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w4[k] = tile[ch * 8 + 2 * k][xi] | (tile[ch * 8 + 2 * k + 1][xi] << 16);
+      *reinterpret_cast<uint4*>(tok + row * ld + cb + c0 + ch * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- 2x2 max pool (fpn4)
 // token-major f32 [B, h, w, C] -> token-major f32 [B, h/2, w/2, C]                                   [V]:654
 __global__ void __launch_bounds__(256)
@@ -274,6 +350,12 @@ extern "C" int mtp_tok_to_nchw(const void* tok, int tok_is_bf16, int ld, void* o
   const dim3 grid(ceil_div(w << level, 32) * (h << level), ceil_div(C, 32), B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define T2N(TI, TO) (void)launch_k(tok_to_nchw_kernel<TI, TO>, grid, 256, 0, st, reinterpret_cast<const TI*>(tok), ld, reinterpret_cast<TO*>(out), g, 0)
+  if (tok_is_bf16 && out_is_bf16 && (w << level) % 8 == 0 && C % 64 == 0 && ld % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(tok) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const dim3 gridv(ceil_div(w << level, 32) * (h << level), C / 64, B);
+    (void)launch_k(tok_to_nchw_vec_kernel, gridv, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(tok), ld, reinterpret_cast<__nv_bfloat16*>(out), g);
+    return check_launch("tok_to_nchw_vec_kernel");
+  }
   if (tok_is_bf16 && out_is_bf16) T2N(__nv_bfloat16, __nv_bfloat16);
   else if (tok_is_bf16) T2N(__nv_bfloat16, float);
   else if (out_is_bf16) T2N(float, __nv_bfloat16);
@@ -306,6 +388,12 @@ extern "C" int mtp_nchw_to_tok(const void* in, int in_is_bf16, void* tok, int to
     MTP_REQUIRE(!tok_is_bf16, "mtp_nchw_to_tok: accumulate needs an f32 destination");
     if (in_is_bf16) N2T(__nv_bfloat16, float, true); else N2T(float, float, true);
   } else if (tok_is_bf16) {
+    if (in_is_bf16 && (w << level) % 8 == 0 && C % 64 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(tok) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+      const dim3 gridv(ceil_div(w << level, 32) * (h << level), C / 64, B);
+      (void)launch_k(nchw_to_tok_vec_kernel, gridv, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(tok), ld, g);
+      return check_launch("nchw_to_tok_vec_kernel");
+    }
     if (in_is_bf16) N2T(__nv_bfloat16, __nv_bfloat16, false); else N2T(float, __nv_bfloat16, false);
   } else {
     if (in_is_bf16) N2T(__nv_bfloat16, float, false); else N2T(float, float, false);
