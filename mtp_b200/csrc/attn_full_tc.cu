@@ -1,6 +1,6 @@
 // Dense attention with decomposed rel-pos bias on tcgen05 tensor cores, forward and backward, for token grids with
 // N = gh*gw <= 256 (224^2 and 256^2 inputs: the dense blocks of the headline configuration).  Larger grids use the
-// streaming SIMT kernels of attn_full.cu / attn_full_bwd.cu in this round.       [V]:90-111, 142-193; SURVEY.md K6
+// streaming tensor-core kernels of attn_full_stream_tc.cu / attn_full_stream_bwd_tc.cu.       [V]:90-111, 142-193; SURVEY.md K6
 //
 // One CTA (128 threads) per (image, head).  K and V of the head live in shared memory for the whole CTA as 128B-swizzled
 // bf16 tiles ([256 rows] x 128 B); query tiles of 128 rows are processed in turn:

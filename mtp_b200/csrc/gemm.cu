@@ -480,7 +480,7 @@ struct Sched {
   uint16_t item[MAX_SLOTS][MAX_ITEMS];
   int strided_total;   // > 0: the lists above are unused; slot s walks items s, s + slots, s + 2*slots, ... < strided_total
   int n_stages;        // depth of the smem ring actually used (<= GemmCfg::STAGES): fewer stages = less dynamic smem, so that the CTA of
-                       // the NEXT launch can become resident beside this one and hide the SM turnaround (tools/gemm_gaps.py)
+                       // the NEXT launch can become resident beside this one (co-residency experiments, tools/gemm_gaps.py)
   int dbg_mode;        // tuning aid: 0 normal, 1 = skip the TMA loads (MMA pipeline only), 2 = skip the MMAs (TMA pipeline only)
   long long* dbg;      // optional: [gridDim.x][8] globaltimer stamps of the pipeline phases (tuning aid, mtp_gemm_set_debug)
 };
@@ -829,8 +829,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmProblem p0, const __grid_constant__
 // ===================================================================================================================
 // Variant 2: ONE tile per CTA, TWO CTAs per SM (mtp_gemm_set_variant(2) / MTP_GEMM_VARIANT=2).
 //
-// Motivation (profiles/r2_summary.md section 4): behind the persistent kernel above every dependent launch pays 5-8 us of SM turnaround, because
-// a CTA of 200 KB smem / 512 TMEM columns must fully retire before its successor can become resident.  Here a CTA owns 98 KB smem (2-3
+// Motivation (profiles/r2_summary.md section 4): behind the persistent kernel above the epilogue of every SM's last tile is exposed, and a
+// CTA of 200 KB smem / 512 TMEM columns must fully retire before its successor can become resident.  (An experiment, not the default: the step
+// was slower with it -- the shallow operand ring costs more than the overlap gains)  Here a CTA owns 98 KB smem (2-3
 // stage ring), one 128 x BN accumulator (<= 256 TMEM columns) and 192 threads (TMA warp, MMA warp, 4 epilogue warps), so two fit one SM:
 // while one CTA runs its epilogue the other one's mainloop owns the tensor core, and the NEXT launch's CTAs move into the slots freed by
 // early finishers, run their prologue and wait at griddepcontrol.wait before their predecessor grid has drained.  Tiles are handed to the SMs
@@ -1487,14 +1488,14 @@ extern "C" int mtp_gemm_set_debug(void* device_buffer) {
   return MTP_OK;
 }
 extern "C" int mtp_gemm_last_config(void) { return g_last_config; }
-/* 1: persistent warp-specialised kernel (default); 2: one tile per CTA, two CTAs per SM (co-residency hides the SM turnaround between
- * dependent launches).  mtp_gemm_last_config() reports 3000 + BN for variant 2. */
+/* 1: persistent warp-specialised kernel (default); 2: one tile per CTA, two CTAs per SM (the next launch's CTAs become resident while
+ * this launch's last epilogues run).  mtp_gemm_last_config() reports 3000 + BN for variant 2. */
 extern "C" int mtp_gemm_set_variant(int v) {
   g_gemm_variant = (v == 2 || v == 3) ? v : 1;
   return MTP_OK;
 }
 /* tuning aid: cap the depth of the operand ring (0 = fill the smem budget).  A shallow ring leaves room for the next launch's CTA on the
- * same SM (co-residency hides the SM turnaround between dependent launches, at the price of less latency cover in the mainloop). */
+ * same SM (co-residency, at the price of less latency cover in the mainloop). */
 extern "C" int mtp_gemm_set_max_stages(int n) {
   g_gemm_max_stages = n > 0 ? n : 0;
   return MTP_OK;

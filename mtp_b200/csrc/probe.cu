@@ -1,6 +1,7 @@
 // Measurement aid (tools/turnaround_probe.py): a do-nothing kernel with a configurable resource footprint -- dynamic shared memory,
-// TMEM allocation, a busy-wait -- stamped with the global timer, to find out what makes the SM turnaround between two dependent
-// heavy launches (5-7 us measured between tcgen05 GEMM launches vs 0.8 us between trivial kernels).
+// TMEM allocation, a busy-wait, end-of-kernel accumulator reads / global reads / stores -- stamped with the global timer: how long after one
+// launch's last CTA is the next launch ready?  (0.9-1.0 us whatever the footprint and the end work: the "5-7 us after a GEMM" this was built to
+// explain turned out to be the GEMM's own exposed last-tile epilogue)
 #include "common.h"
 #include "ptx.cuh"
 

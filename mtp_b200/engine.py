@@ -123,8 +123,7 @@ def _block_forward(d, x0, B, gh, gw, nH, keep_a, keep_m, save):
     N = gh * gw
     y1, mean1, rstd1 = ops.layernorm_fwd(x0, d["norm1_w"], d["norm1_b"], save_stats=save)
     params = pooled = None
-    if d["window"]:      # the sampling heads only need y1: launched BEFORE the qkv GEMM, so that this light kernel follows the light LayerNorm
-        #                  (a kernel that follows a GEMM pays the GEMM's 5-7 us SM turnaround, profiles/r2_summary.md section 4)
+    if d["window"]:      # the sampling heads only need y1: launched BEFORE the qkv GEMM
         params, pooled = ops.rvsa_sampling_fwd(y1, d["off_w"], d["off_b"], d["sc_w"], d["sc_b"], d["ang_w"], d["ang_b"], B, gh, gw, nH,
                                                save_pooled=save)
     qkv = torch.empty(T, 3 * C, device=x0.device, dtype=BF16)
