@@ -94,26 +94,34 @@ __device__ __forceinline__ void ft_rel_terms_fixed(const uint8_t* Qs, const floa
 template <int G>
 __device__ __forceinline__ void ft_build_rel_tiles(uint8_t* hi, uint8_t* lo, const float* __restrict__ rel_h, const float* __restrict__ rel_w) {
   static_assert(2 * G - 1 <= 32, "table rows");
-  for (int i = threadIdx.x; i < 64 * 8; i += FT_THREADS) {
-    const int r = i >> 3, c = i & 7;
+  static_assert(64 * 8 % FT_THREADS == 0, "items per thread");
+  constexpr int NI = 64 * 8 / FT_THREADS;      // 4 (row, 8-column chunk) items per thread: all their loads are issued before the first conversion
+  float4 va[NI], vb[NI];
+#pragma unroll
+  for (int k = 0; k < NI; ++k) {
+    const int i = threadIdx.x + k * FT_THREADS, r = i >> 3, c = i & 7;
     const int t = r < 32 ? r : r - 32;
-    uint4 uh = make_uint4(0, 0, 0, 0), ul = make_uint4(0, 0, 0, 0);
+    va[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    vb[k] = va[k];
     if (t < 2 * G - 1) {
       const float* src = (r < 32 ? rel_h : rel_w) + t * 64 + c * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      uint32_t h[4], l[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
-        h[k] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
-        l[k] = pack_bf16x2(v[2 * k] - __bfloat162float(h0), v[2 * k + 1] - __bfloat162float(h1));
-      }
-      uh = make_uint4(h[0], h[1], h[2], h[3]);
-      ul = make_uint4(l[0], l[1], l[2], l[3]);
+      va[k] = __ldg(reinterpret_cast<const float4*>(src));
+      vb[k] = __ldg(reinterpret_cast<const float4*>(src + 4));
     }
-    *reinterpret_cast<uint4*>(hi + tile_chunk_off(r, c)) = uh;
-    *reinterpret_cast<uint4*>(lo + tile_chunk_off(r, c)) = ul;
+  }
+#pragma unroll
+  for (int k = 0; k < NI; ++k) {
+    const int i = threadIdx.x + k * FT_THREADS, r = i >> 3, c = i & 7;
+    const float v[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float h0 = __bfloat162float(__float2bfloat16_rn(v[2 * e])), h1 = __bfloat162float(__float2bfloat16_rn(v[2 * e + 1]));
+      h[e] = pack_bf16x2(h0, h1);
+      l[e] = pack_bf16x2(v[2 * e] - h0, v[2 * e + 1] - h1);
+    }
+    *reinterpret_cast<uint4*>(hi + tile_chunk_off(r, c)) = make_uint4(h[0], h[1], h[2], h[3]);      // rows outside the tables: zeros
+    *reinterpret_cast<uint4*>(lo + tile_chunk_off(r, c)) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 

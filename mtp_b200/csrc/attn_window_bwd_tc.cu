@@ -84,18 +84,46 @@ rvsa_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     const int row = rr < 15 ? NTOK + rr : 64 + NTOK + (rr - 15);
     *reinterpret_cast<uint4*>(Qs + tile * WB_TILE + tile_chunk_off(row, c)) = make_uint4(0, 0, 0, 0);
   }
-  for (int i = tid; i < 2 * 13 * 64; i += WB_THREADS) {      // chunk-swizzled rows (tab_chunk_off): lanes of a warp read different rows
-    const int t = i / (13 * 64), r = (i % (13 * 64)) >> 6, d = i & 63;
-    relt[t * 13 * 64 + tab_chunk_off(r, d >> 2) + (d & 3)] = t == 0 ? rel_h[i] : rel_w[i - 13 * 64];
-  }
-  for (int i = tid; i < 2 * 169; i += WB_THREADS) tabs[i] = bias_table[(i % 169) * g.nH + 2 * hp + i / 169];
-  if (tid < 98) {
-    const int p = tid / NTOK, j = tid % NTOK;
-    const float* prm = params + ((size_t)bw * g.nH + 2 * hp + p) * 8;
-    float px, py;
-    rvsa_sample_coord(g, wy, wx, j / WS, j % WS, prm[0], prm[1], prm[2], prm[3], prm[4], px, py);
-    cpx[tid] = px;
-    cpy[tid] = py;
+  {
+    // Prologue loads (rel-pos tables, the two heads' bias-table columns, the sampling parameters) are issued as ONE batch and stored afterwards:
+    // written as `smem[i] = global[i]` loops they stayed in program order -- seven dependent L2 round trips on every CTA's critical path
+    // (ncu source view of the backward: the table store waiting on its load was the kernel's top stall).
+    static_assert(WB_THREADS == 256, "batch sizes below assume 256 threads");
+    constexpr int NT = (2 * 13 * 64 + 255) / 256;      // 7 table elements per thread
+    float tv[NT], bv[2], pr[5];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+      const int i = tid + k * 256;
+      tv[k] = i < 2 * 13 * 64 ? (i < 13 * 64 ? __ldg(rel_h + i) : __ldg(rel_w + i - 13 * 64)) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * 256;
+      bv[k] = i < 2 * 169 ? __ldg(bias_table + (i % 169) * g.nH + 2 * hp + i / 169) : 0.f;
+    }
+    if (tid < 98) {
+      const float* prm = params + ((size_t)bw * g.nH + 2 * hp + tid / NTOK) * 8;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) pr[k] = prm[k];
+    }
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {      // chunk-swizzled rows (tab_chunk_off): lanes of a warp read different rows
+      const int i = tid + k * 256;
+      if (i < 2 * 13 * 64) {
+        const int t = i / (13 * 64), r = (i % (13 * 64)) >> 6, d = i & 63;
+        relt[t * 13 * 64 + tab_chunk_off(r, d >> 2) + (d & 3)] = tv[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (tid + k * 256 < 2 * 169) tabs[tid + k * 256] = bv[k];
+    if (tid < 98) {
+      const int j = tid % NTOK;
+      float px, py;
+      rvsa_sample_coord(g, wy, wx, j / WS, j % WS, pr[0], pr[1], pr[2], pr[3], pr[4], px, py);
+      cpx[tid] = px;
+      cpy[tid] = py;
+    }
   }
   tc_fence_before();
   __syncthreads();
