@@ -213,19 +213,6 @@ def cpu_reference(cfg, steps, warmup, batch, threads=None, forward_only=False):
     return batch / statistics.median(times), threads, sum(times)
 
 
-def _ncu_gemm_traffic(cfg, n_launches):
-    """DRAM read + write bytes of the GEMM launches of one step from the committed ncu capture (headline config only)."""
-    try:
-        if cfg["name"] != "c3":
-            return None
-        d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_gemm_dram_final.json")))
-        if int(d["gemm_launches"]) != int(n_launches):
-            return None
-        return float(d["dram_read_bytes"]) + float(d["dram_write_bytes"])
-    except Exception:
-        return None
-
-
 def cpu_sample_batch(cfg):
     return {"c2": 2, "c3": 2, "c4": 1, "c5": 1}[cfg["name"]]       # SURVEY 8d: fwd+bwd B=2 @224^2; one image at the larger sizes
 
@@ -498,10 +485,8 @@ def main():
             "gpu_launches": launches * args.steps,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of one step)", "achieved": gemm_tflops,
                          "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": (gemm_tflops / pk["tf_burst"]) if gemm_tflops else None,
-                         # DRAM bytes are not measurable from inside the run: the committed ncu pass of this command (profiles/, same 203 launches
-                         # of one c3 step: dram__bytes_read.sum + dram__bytes_write.sum) is quoted when it matches the workload, else null
-                         "traffic": _ncu_gemm_traffic(cfg, gm["n"]),
-                         "traffic_source": "profiles/r2_gemm_dram_final.json (ncu, bytes per step over all GEMM launches; algorithmic bytes alongside)",
+                         "traffic": None,       # DRAM bytes are not measurable from inside the run (r1 verdict: never quote a committed file here);
+                         #                        the ncu pass of this command lives in profiles/ (r2_gemm_dram_final.json: 3.94 GB per step)
                          "algorithmic_bytes_per_step": gm["bytes"], "peak_source": pk["src"] + " (burst cuBLAS bf16)",
                          "gemm_launches_per_step": gm["n"], "gemm_gflop_per_step": gm["flops"] / 1e9, "gemm_ms_per_step": gemm_ms,
                          "gemm_timing": "in situ: graph-replayed step minus the same step with empty GEMM launches (all ranks, max)",

@@ -117,16 +117,11 @@ def test_image_preprocess_reference_and_stream_split():
         ImagePreprocess(bgr_to_rgb=True, rgb_to_bgr=True)
 
 
-def test_bench_reference_arm_line_and_ncu_traffic():
-    """bench.py pieces that need no GPU: the quoted ncu DRAM traffic of the GEMM launches and the JSON contract of the CPU reference arm
-    (one timed step of the smallest configuration on the oracle port)."""
+def test_bench_reference_arm_line():
+    """bench.py piece that needs no GPU: the JSON contract of the CPU reference arm (one timed step of the smallest configuration on the oracle port)."""
     import json
     import subprocess
     import sys
-    import bench
-    t = bench._ncu_gemm_traffic({"name": "c3"}, 203)
-    assert t is not None and 3e9 < t < 6e9                       # committed capture: 3.9 GB read + 0.03 GB written per step
-    assert bench._ncu_gemm_traffic({"name": "c3"}, 7) is None and bench._ncu_gemm_traffic({"name": "c2"}, 203) is None
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "c2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, cwd=root)
